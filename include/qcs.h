@@ -1,0 +1,207 @@
+/*
+ * qcs.h -- C ABI of libqcs.so, the B200 (sm_100a) state-vector engine that
+ * replaces the gate-application path of adamalderton/QuantumComputer's
+ * qc_shor.c.  "Q:a-b" below cites /root/reference/qc_shor.c lines a-b and
+ * "T:a-b" cites testing_and_debug.c.
+ *
+ * The reference has no header and no FFI: every function is `static` in one
+ * translation unit.  The boundary is therefore the set of calls the classical
+ * driver makes into the gate path (find_period, Q:922-928; main, Q:1316-1333)
+ * plus the individual gate operators, with the reference's argument order.
+ * The `gsl_spmatrix_complex *matrix` scratch argument of the reference is
+ * dropped: no gate matrix is ever materialised here.
+ *
+ * Conventions (identical to the reference):
+ *   - amplitudes are complex double, interleaved (re, im), 16 bytes each, the
+ *     layout of gsl_vector_complex.data (Q:385-386, 405-412);
+ *   - qubit b is bit b of the basis-state index, least significant = qubit 0
+ *     (GET_BIT, Q:150-151);
+ *   - the M ("f") register is qubits 0..M-1, the L ("x") register is qubits
+ *     M..L+M-1 (Q:620, 650, 720).
+ *
+ * Every entry point returns one of the reference's ErrorCode values (Q:164-170)
+ * as an int.  Gate calls are asynchronous on the register's CUDA stream;
+ * qcs_measure_state, qcs_norm2, qcs_get_state and qcs_synchronize block.
+ * One host thread per register.  There is no CPU fallback: without a usable
+ * CUDA device qcs_register_create fails with QCS_UNKNOWN_ERROR.
+ */
+#ifndef QCS_H
+#define QCS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ErrorCode, Q:164-170 */
+enum {
+    QCS_NO_ERROR = 0,
+    QCS_INSUFFICIENT_MEMORY = 1,
+    QCS_BAD_ARGUMENTS = 2,
+    QCS_PERIOD_NOT_FOUND = 3,
+    QCS_UNKNOWN_ERROR = 4
+};
+
+/* Opaque device register: replaces `Register` (Q:194-203).  One in-place
+ * amplitude array per GPU; the state_a/state_b ping-pong and swap_states
+ * (Q:242-249) do not exist. */
+typedef struct qcs_register qcs_register;
+
+/* how quantum_computation derives `atox` for gate k of the modular
+ * exponentiation (Q:728-731) */
+enum {
+    QCS_POW_VERBATIM = 0,   /* INT_POW(a, 2^k) exactly as Q:158-159 behaves on x86-64 */
+    QCS_POW_MODULAR = 1     /* a^(2^k) mod C by modular squaring (the intended value) */
+};
+
+/* options for qcs_set_option */
+enum {
+    /* 1 (default): composite operators (inverse_QFT, quantum_computation) run
+     * as fused tile sweeps -- amplitudes agree with the reference to <= 1e-12
+     * relative L2.  0: they run gate by gate in the reference's order with the
+     * reference's floating-point operations -- amplitudes are value-identical. */
+    QCS_OPT_FUSION = 1,
+    /* 1: record a CUDA-event pair around every kernel launch so that
+     * qcs_profile_get can report per-kernel device time.  Default 0. */
+    QCS_OPT_PROFILE = 2,
+    /* log2 of the shared-memory tile (amplitudes) used by the fused sweeps;
+     * 0 = library default. */
+    QCS_OPT_TILE_BITS = 3
+};
+
+/* kernel classes reported by qcs_profile_get */
+enum {
+    QCS_K_HADAMARD = 0,      /* pair-stride H                       32*2^n B/launch */
+    QCS_K_CPHASE = 1,        /* controlled phase, |11> quarter       8*2^n B/launch */
+    QCS_K_AMODC = 2,         /* controlled a^x mod C permutation                     */
+    QCS_K_FILL = 3,          /* reset / synthetic fill / collapse    16*2^n B/launch */
+    QCS_K_REDUCE = 4,        /* norm^2, measurement scan             16*2^n B/launch */
+    QCS_K_TILE_SWEEP = 5,    /* fused QFT tile sweep                 32*2^n B/launch */
+    QCS_K_MODEXP_SWEEP = 6,  /* fused H^L + all L a^x mod C gates                    */
+    QCS_K_EXCHANGE = 7,      /* global-qubit exchange (multi-GPU)                    */
+    QCS_K_SCALE = 8,         /* in-place scaling                     32*2^n B/launch */
+    QCS_K_COUNT = 9
+};
+
+const char *qcs_version(void);
+const char *qcs_error_string(int code);
+/* number of CUDA devices visible to this process (0 if none) */
+int qcs_device_count(void);
+
+/* ---- register life-cycle ------------------------------------------------
+ * replaces the allocation block of main(), Q:1316-1324 (two state vectors and
+ * a COO matrix with nzmax = 2N) and the frees at Q:1330-1333.  num_qubits =
+ * L_size + M_size and num_states = 2^num_qubits as in Q:1255-1261.
+ * `device` is a CUDA device ordinal, or -1 for the current device.          */
+int qcs_register_create(qcs_register **out, int L_size, int M_size, int device);
+void qcs_register_destroy(qcs_register *reg);
+
+/* Sharded register: this process holds shard `rank` of `world_size` = 2^p
+ * equal shards; the top p qubits are global.  `comm_id` is the
+ * 128-byte id produced by qcs_comm_unique_id on rank 0 and distributed by the
+ * launcher (torch.distributed, MPI, a file ...).                            */
+#define QCS_COMM_ID_BYTES 128
+int qcs_comm_unique_id(void *id_out);
+int qcs_register_create_sharded(qcs_register **out, int L_size, int M_size, int device,
+                                int rank, int world_size, const void *comm_id);
+
+int qcs_L_size(const qcs_register *reg);
+int qcs_M_size(const qcs_register *reg);
+unsigned qcs_num_qubits(const qcs_register *reg);
+unsigned long long qcs_num_states(const qcs_register *reg);        /* 2^n, all shards */
+unsigned long long qcs_local_states(const qcs_register *reg);      /* this shard      */
+int qcs_rank(const qcs_register *reg);
+int qcs_world_size(const qcs_register *reg);
+
+int qcs_set_option(qcs_register *reg, int option, long long value);
+long long qcs_get_option(const qcs_register *reg, int option);
+int qcs_synchronize(qcs_register *reg);
+
+/* ---- gate path ---------------------------------------------------------- */
+
+/* void reset_register(Register), Q:318-324: state <- |0...01> (index 1). */
+int qcs_reset_register(qcs_register *reg);
+
+/* void hadamard_gate(unsigned qubit_num, Register*, matrix*), Q:442-484. */
+int qcs_hadamard_gate(qcs_register *reg, unsigned qubit_num);
+
+/* void c_phase_shift_gate(unsigned c_qubit_num, unsigned qubit_num,
+ *                         double theta, Register*, matrix*), Q:513-565. */
+int qcs_c_phase_shift_gate(qcs_register *reg, unsigned c_qubit_num, unsigned qubit_num,
+                           double theta);
+
+/* void c_amodc_gate(unsigned C, unsigned long long atox, unsigned c_qubit_num,
+ *                   Register*, matrix*), Q:595-660.  Bit-exact index map;
+ * non-bijective maps (gcd(atox % C, C) != 1, atox % C == 0) sum colliding
+ * sources in ascending source order like operate_matrix does. */
+int qcs_c_amodc_gate(qcs_register *reg, unsigned C, unsigned long long atox,
+                     unsigned c_qubit_num);
+
+/* void inverse_QFT(Register*, matrix*), Q:678-690, on the L register. */
+int qcs_inverse_QFT(qcs_register *reg);
+/* the adjoint circuit (not in the reference): same gates, reverse order, -theta */
+int qcs_QFT(qcs_register *reg);
+/* the same circuits on qubits lo..hi-1 (lo plays the role of M_size) */
+int qcs_inverse_QFT_range(qcs_register *reg, unsigned lo, unsigned hi);
+int qcs_QFT_range(qcs_register *reg, unsigned lo, unsigned hi);
+
+/* void quantum_computation(unsigned C, unsigned a, Register*, matrix*),
+ * Q:712-737: H on the L register, L controlled a^(2^k) mod C gates, inverse QFT. */
+int qcs_quantum_computation(qcs_register *reg, unsigned C, unsigned a, int pow_mode);
+
+/* unsigned long measure_state(Register, gsl_rng*), Q:272-306.  The caller
+ * draws r = gsl_rng_uniform(rng) on the host (Q:281); the scan, the `>=`
+ * comparison, the N-1 fall-through and the collapse are done on the device
+ * with the reference's sequential summation semantics (bit-exact index). */
+int qcs_measure_state(qcs_register *reg, double r, unsigned long long *state_num);
+
+/* check_normalisation, T:28-37: sum of |amp|^2 (deterministic parallel order) */
+int qcs_norm2(qcs_register *reg, double *sum_of_sq);
+
+/* display_state, T:7-26: indices and |amp| of the non-zero amplitudes, in
+ * index order; at most `capacity` are written, *count receives the total. */
+int qcs_nonzero_states(qcs_register *reg, unsigned long long capacity,
+                       unsigned long long *indices, double *abs_values,
+                       unsigned long long *count);
+
+/* bulk access to this shard's amplitudes [first, first+count), interleaved
+ * doubles, host memory (pinned memory makes the copies asynchronous-capable) */
+int qcs_get_state(qcs_register *reg, unsigned long long first, unsigned long long count,
+                  double *interleaved_out);
+int qcs_set_state(qcs_register *reg, unsigned long long first, unsigned long long count,
+                  const double *interleaved_in);
+
+/* synthetic benchmark state: amp[i] = (u(2i), u(2i+1)),
+ * u(k) = (mix64(seed + k) >> 11) * 2^-53 - 0.5, generated on the device */
+int qcs_fill_synthetic(qcs_register *reg, unsigned long long seed);
+int qcs_scale(qcs_register *reg, double factor);
+
+/* ---- host-side scalar helpers (no device work) -------------------------- */
+/* INT_POW, Q:158-159, with the out-of-range cast resolved as on x86-64 */
+unsigned qcs_int_pow(unsigned base, unsigned power);
+/* a^(2^k) mod C */
+unsigned long long qcs_modpow2k(unsigned a, unsigned k, unsigned C);
+
+/* pinned host memory for qcs_get_state / qcs_set_state */
+int qcs_host_alloc(void **ptr, size_t bytes);
+int qcs_host_free(void *ptr);
+
+/* ---- measurement of the engine itself ----------------------------------- */
+/* CUDA-event stopwatch on the register's stream */
+int qcs_timer_start(qcs_register *reg);
+int qcs_timer_stop(qcs_register *reg, double *milliseconds);
+/* kernels launched by this register since creation / since the last reset */
+unsigned long long qcs_launch_count(const qcs_register *reg);
+int qcs_profile_reset(qcs_register *reg);
+/* per kernel class: launches, summed device milliseconds (QCS_OPT_PROFILE=1
+ * only, else 0) and summed algorithmic bytes of those launches */
+int qcs_profile_get(qcs_register *reg, int kernel_class, unsigned long long *launches,
+                    double *milliseconds, double *algorithmic_bytes);
+const char *qcs_kernel_class_name(int kernel_class);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCS_H */

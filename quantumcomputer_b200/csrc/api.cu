@@ -1,0 +1,617 @@
+// api.cu -- the C ABI of include/qcs.h: register life-cycle, gate dispatch
+// (local vs. global qubits), composite operators and bookkeeping.
+#include "qcs_internal.h"
+
+#include <math.h>
+#include <new>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846264338328
+#endif
+
+// ---------------------------------------------------------------------------
+// error plumbing and launch accounting
+// ---------------------------------------------------------------------------
+int qcs_map_cuda_error(cudaError_t e, const char *what, const char *file, int line)
+{
+    fprintf(stderr, "qcs: CUDA error %d (%s) at %s:%d in %s\n", (int) e, cudaGetErrorString(e), file, line, what);
+    if (e == cudaErrorMemoryAllocation) return QCS_INSUFFICIENT_MEMORY;
+    if (e == cudaErrorInvalidValue || e == cudaErrorInvalidDevice) return QCS_BAD_ARGUMENTS;
+    return QCS_UNKNOWN_ERROR;
+}
+
+void qcs_launch_begin(qcs_register *reg, int kind, double algorithmic_bytes)
+{
+    reg->launches_total++;
+    reg->launches[kind]++;
+    reg->alg_bytes[kind] += algorithmic_bytes;
+    if (reg->opt_profile) {
+        qcs_profile_slot s;
+        if (!reg->free_slots.empty()) {
+            s = reg->free_slots.back();
+            reg->free_slots.pop_back();
+        } else {
+            cudaEventCreate(&s.begin);
+            cudaEventCreate(&s.end);
+        }
+        s.kind = kind;
+        cudaEventRecord(s.begin, reg->stream);
+        reg->pending.push_back(s);
+    }
+}
+
+int qcs_launch_end(qcs_register *reg, int kind, const char *name)
+{
+    (void) kind;
+    if (reg->opt_profile && !reg->pending.empty()) cudaEventRecord(reg->pending.back().end, reg->stream);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return qcs_map_cuda_error(e, name, __FILE__, __LINE__);
+    if (reg->pending.size() > 4096) return qcs_profile_resolve(reg);
+    return QCS_NO_ERROR;
+}
+
+int qcs_profile_resolve(qcs_register *reg)
+{
+    if (reg->pending.empty()) return QCS_NO_ERROR;
+    QCS_CUDA(cudaStreamSynchronize(reg->stream));
+    for (auto &s : reg->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.begin, s.end) == cudaSuccess) reg->ms[s.kind] += (double) ms;
+        reg->free_slots.push_back(s);
+    }
+    reg->pending.clear();
+    return QCS_NO_ERROR;
+}
+
+// ---------------------------------------------------------------------------
+// misc
+// ---------------------------------------------------------------------------
+extern "C" const char *qcs_version(void) { return "qcs 0.1.0 (sm_100a)"; }
+
+extern "C" const char *qcs_error_string(int code)
+{
+    switch (code) {
+        case QCS_NO_ERROR: return "NO_ERROR";
+        case QCS_INSUFFICIENT_MEMORY: return "INSUFFICIENT_MEMORY";
+        case QCS_BAD_ARGUMENTS: return "BAD_ARGUMENTS";
+        case QCS_PERIOD_NOT_FOUND: return "PERIOD_NOT_FOUND";
+        default: return "UNKNOWN_ERROR";
+    }
+}
+
+extern "C" const char *qcs_kernel_class_name(int k)
+{
+    static const char *names[QCS_K_COUNT] = {"hadamard", "cphase", "amodc", "fill", "reduce",
+                                             "tile_sweep", "modexp_sweep", "exchange", "scale"};
+    return (k >= 0 && k < QCS_K_COUNT) ? names[k] : "?";
+}
+
+extern "C" int qcs_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// INT_POW, qc_shor.c:158-159: (unsigned int)(pow(base, power) + 0.5); the
+// out-of-range cast is resolved the way gcc/x86-64 compiles it (64-bit
+// truncating conversion, low 32 bits kept; >= 2^63 or NaN -> 0).
+extern "C" unsigned qcs_int_pow(unsigned base, unsigned power)
+{
+    const double d = pow((double) base, (double) power) + 0.5;
+    if (!(d < 9223372036854775808.0) || !(d > -9223372036854775808.0)) return 0u;
+    return (unsigned) (uint64_t) (int64_t) d;
+}
+
+extern "C" unsigned long long qcs_modpow2k(unsigned a, unsigned k, unsigned C)
+{
+    if (C == 0) return 0;
+    unsigned long long v = a % C;
+    for (unsigned s = 0; s < k; s++) v = (v * v) % C;
+    return v;
+}
+
+extern "C" int qcs_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return QCS_BAD_ARGUMENTS;
+    QCS_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return QCS_NO_ERROR;
+}
+
+extern "C" int qcs_host_free(void *ptr)
+{
+    QCS_CUDA(cudaFreeHost(ptr));
+    return QCS_NO_ERROR;
+}
+
+// ---------------------------------------------------------------------------
+// register life-cycle
+// ---------------------------------------------------------------------------
+static int create_common(qcs_register **out, int L_size, int M_size, int device, int rank, int world,
+                         const void *comm_id)
+{
+    if (!out) return QCS_BAD_ARGUMENTS;
+    *out = nullptr;
+    if (L_size < 0 || M_size < 0 || L_size + M_size < 1 || L_size + M_size > 62) return QCS_BAD_ARGUMENTS;
+    if (world < 1 || (world & (world - 1)) != 0 || rank < 0 || rank >= world) return QCS_BAD_ARGUMENTS;
+    int p = 0;
+    while ((1 << p) < world) p++;
+    if (p >= L_size + M_size) return QCS_BAD_ARGUMENTS;
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fprintf(stderr, "qcs: no usable CUDA device (%s); this library has no CPU path\n",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return QCS_UNKNOWN_ERROR;
+    }
+    if (device < 0) QCS_CUDA(cudaGetDevice(&device));
+    if (device >= ndev) return QCS_BAD_ARGUMENTS;
+    QCS_CUDA(cudaSetDevice(device));
+
+    qcs_register *reg = new (std::nothrow) qcs_register();
+    if (!reg) return QCS_INSUFFICIENT_MEMORY;
+    reg->L_size = L_size;
+    reg->M_size = M_size;
+    reg->n = (unsigned) (L_size + M_size);
+    reg->n_local = reg->n - (unsigned) p;
+    reg->N = 1ull << reg->n;
+    reg->N_local = 1ull << reg->n_local;
+    reg->device = device;
+    reg->rank = rank;
+    reg->world = world;
+    reg->p_global = p;
+    reg->dist = nullptr;
+    reg->opt_fusion = 0;
+    reg->opt_profile = 0;
+    reg->opt_tile_bits = 0;
+    reg->launches_total = 0;
+    memset(reg->launches, 0, sizeof reg->launches);
+    memset(reg->alg_bytes, 0, sizeof reg->alg_bytes);
+    memset(reg->ms, 0, sizeof reg->ms);
+    reg->amp = nullptr;
+    reg->d_partials = nullptr;
+    reg->d_small = nullptr;
+    reg->h_small = nullptr;
+    reg->stream = nullptr;
+    reg->timer_begin = reg->timer_end = nullptr;
+
+    int rc = QCS_NO_ERROR;
+    cudaDeviceProp prop;
+    do {
+        if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) break;
+        reg->sm_count = prop.multiProcessorCount;
+        reg->smem_optin = prop.sharedMemPerBlockOptin;
+        if ((e = cudaStreamCreateWithFlags(&reg->stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = cudaMalloc((void **) &reg->amp, reg->N_local * sizeof(double2))) != cudaSuccess) break;
+        reg->partials_cap = (size_t) reg->sm_count * 16;
+        if ((e = cudaMalloc((void **) &reg->d_partials, reg->partials_cap * sizeof(double))) != cudaSuccess) break;
+        if ((e = cudaMalloc(&reg->d_small, 4096)) != cudaSuccess) break;
+        if ((e = cudaHostAlloc(&reg->h_small, 4096, cudaHostAllocDefault)) != cudaSuccess) break;
+        if ((e = cudaEventCreate(&reg->timer_begin)) != cudaSuccess) break;
+        if ((e = cudaEventCreate(&reg->timer_end)) != cudaSuccess) break;
+    } while (0);
+    if (e != cudaSuccess) {
+        rc = qcs_map_cuda_error(e, "register allocation", __FILE__, __LINE__);
+        qcs_register_destroy(reg);
+        return rc;
+    }
+    if (world > 1) {
+        rc = qcs_dist_init(reg, comm_id);
+        if (rc != QCS_NO_ERROR) { qcs_register_destroy(reg); return rc; }
+    }
+    *out = reg;
+    return QCS_NO_ERROR;
+}
+
+extern "C" int qcs_register_create(qcs_register **out, int L_size, int M_size, int device)
+{
+    return create_common(out, L_size, M_size, device, 0, 1, nullptr);
+}
+
+extern "C" int qcs_register_create_sharded(qcs_register **out, int L_size, int M_size, int device,
+                                           int rank, int world_size, const void *comm_id)
+{
+    if (world_size > 1 && !comm_id) return QCS_BAD_ARGUMENTS;
+    return create_common(out, L_size, M_size, device, rank, world_size, comm_id);
+}
+
+extern "C" void qcs_register_destroy(qcs_register *reg)
+{
+    if (!reg) return;
+    cudaSetDevice(reg->device);
+    if (reg->stream) cudaStreamSynchronize(reg->stream);
+    if (reg->dist) qcs_dist_destroy(reg);
+    for (auto &s : reg->pending) { cudaEventDestroy(s.begin); cudaEventDestroy(s.end); }
+    for (auto &s : reg->free_slots) { cudaEventDestroy(s.begin); cudaEventDestroy(s.end); }
+    if (reg->timer_begin) cudaEventDestroy(reg->timer_begin);
+    if (reg->timer_end) cudaEventDestroy(reg->timer_end);
+    if (reg->amp) cudaFree(reg->amp);
+    if (reg->d_partials) cudaFree(reg->d_partials);
+    if (reg->d_small) cudaFree(reg->d_small);
+    if (reg->h_small) cudaFreeHost(reg->h_small);
+    if (reg->stream) cudaStreamDestroy(reg->stream);
+    delete reg;
+}
+
+extern "C" int qcs_L_size(const qcs_register *reg) { return reg ? reg->L_size : -1; }
+extern "C" int qcs_M_size(const qcs_register *reg) { return reg ? reg->M_size : -1; }
+extern "C" unsigned qcs_num_qubits(const qcs_register *reg) { return reg ? reg->n : 0; }
+extern "C" unsigned long long qcs_num_states(const qcs_register *reg) { return reg ? reg->N : 0; }
+extern "C" unsigned long long qcs_local_states(const qcs_register *reg) { return reg ? reg->N_local : 0; }
+extern "C" int qcs_rank(const qcs_register *reg) { return reg ? reg->rank : -1; }
+extern "C" int qcs_world_size(const qcs_register *reg) { return reg ? reg->world : 0; }
+
+extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
+{
+    if (!reg) return QCS_BAD_ARGUMENTS;
+    switch (option) {
+        case QCS_OPT_FUSION: reg->opt_fusion = value != 0; return QCS_NO_ERROR;
+        case QCS_OPT_PROFILE:
+            if (!value) QCS_TRY(qcs_profile_resolve(reg));
+            reg->opt_profile = value != 0;
+            return QCS_NO_ERROR;
+        case QCS_OPT_TILE_BITS:
+            if (value != 0 && (value < 8 || value > 13)) return QCS_BAD_ARGUMENTS;
+            reg->opt_tile_bits = (int) value;
+            return QCS_NO_ERROR;
+        default: return QCS_BAD_ARGUMENTS;
+    }
+}
+
+extern "C" long long qcs_get_option(const qcs_register *reg, int option)
+{
+    if (!reg) return -1;
+    switch (option) {
+        case QCS_OPT_FUSION: return reg->opt_fusion;
+        case QCS_OPT_PROFILE: return reg->opt_profile;
+        case QCS_OPT_TILE_BITS: return reg->opt_tile_bits;
+        default: return -1;
+    }
+}
+
+extern "C" int qcs_synchronize(qcs_register *reg)
+{
+    if (!reg) return QCS_BAD_ARGUMENTS;
+    QCS_CUDA(cudaSetDevice(reg->device));
+    QCS_CUDA(cudaStreamSynchronize(reg->stream));
+    return QCS_NO_ERROR;
+}
+
+#define QCS_ENTER(reg)                              \
+    do {                                            \
+        if (!(reg)) return QCS_BAD_ARGUMENTS;       \
+        QCS_CUDA(cudaSetDevice((reg)->device));     \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// single gates
+// ---------------------------------------------------------------------------
+extern "C" int qcs_reset_register(qcs_register *reg)
+{
+    QCS_ENTER(reg);
+    return qcs_k_reset(reg);
+}
+
+static int hadamard_any(qcs_register *reg, unsigned q)
+{
+    if (q >= reg->n) return QCS_BAD_ARGUMENTS;
+    if (q < reg->n_local) return qcs_k_hadamard_local(reg, q);
+    return qcs_dist_hadamard_global(reg, q);
+}
+
+extern "C" int qcs_hadamard_gate(qcs_register *reg, unsigned qubit_num)
+{
+    QCS_ENTER(reg);
+    return hadamard_any(reg, qubit_num);
+}
+
+// diagonal gate: a global qubit only contributes this rank's (constant) bit
+static int cphase_any(qcs_register *reg, unsigned c, unsigned q, double co, double si)
+{
+    if (c >= reg->n || q >= reg->n) return QCS_BAD_ARGUMENTS;
+    unsigned bits[2];
+    int nb = 0;
+    const unsigned both[2] = {c, q};
+    for (int k = 0; k < (c == q ? 1 : 2); k++) {
+        const unsigned b = both[k];
+        if (b < reg->n_local) bits[nb++] = b;
+        else if (!(((unsigned) reg->rank >> (b - reg->n_local)) & 1u)) return QCS_NO_ERROR;
+    }
+    return qcs_k_phase_masked(reg, nb, nb > 0 ? bits[0] : 0, nb > 1 ? bits[1] : 0, co, si);
+}
+
+extern "C" int qcs_c_phase_shift_gate(qcs_register *reg, unsigned c_qubit_num, unsigned qubit_num, double theta)
+{
+    QCS_ENTER(reg);
+    // gsl_complex_polar(1.0, theta), qc_shor.c:526: host libm like the reference
+    return cphase_any(reg, c_qubit_num, qubit_num, 1.0 * cos(theta), 1.0 * sin(theta));
+}
+
+static int amodc_any(qcs_register *reg, unsigned C, unsigned long long atox, unsigned c)
+{
+    if (C == 0 || c >= reg->n) return QCS_BAD_ARGUMENTS;
+    if (C > 65536u) {
+        fprintf(stderr, "qcs: c_amodc_gate: C > 65536 would wrap the reference's 32-bit product (qc_shor.c:639)\n");
+        return QCS_BAD_ARGUMENTS;
+    }
+    if ((unsigned) reg->M_size > reg->n_local) return QCS_BAD_ARGUMENTS;
+    if (reg->M_size == 0) return QCS_NO_ERROR;               // f = f' = 0: identity
+    const unsigned A = (unsigned) (atox % C);                // qc_shor.c:605
+    if (c >= reg->n_local) {
+        const bool on = ((unsigned) reg->rank >> (c - reg->n_local)) & 1u;
+        return qcs_k_amodc(reg, C, A, -1, !on);
+    }
+    return qcs_k_amodc(reg, C, A, (int) c, false);
+}
+
+extern "C" int qcs_c_amodc_gate(qcs_register *reg, unsigned C, unsigned long long atox, unsigned c_qubit_num)
+{
+    QCS_ENTER(reg);
+    return amodc_any(reg, C, atox, c_qubit_num);
+}
+
+// ---------------------------------------------------------------------------
+// composite operators
+// ---------------------------------------------------------------------------
+// theta = M_PI / INT_POW(2, d) (qc_shor.c:686); exact power of two for d <= 31,
+// continued as ldexp beyond the reference's overflow point
+static double qft_theta(unsigned d)
+{
+    return d <= 31 ? M_PI / (double) qcs_int_pow(2, d) : ldexp(M_PI, -(int) d);
+}
+
+static int qft_gate_by_gate(qcs_register *reg, unsigned lo, unsigned hi, bool inverse)
+{
+    if (inverse) {
+        // qc_shor.c:682-689
+        for (int l = (int) hi - 1; l >= (int) lo; l--) {
+            QCS_TRY(hadamard_any(reg, (unsigned) l));
+            for (int k = l - 1; k >= (int) lo; k--) {
+                const double th = qft_theta((unsigned) (l - k));
+                QCS_TRY(cphase_any(reg, (unsigned) l, (unsigned) k, 1.0 * cos(th), 1.0 * sin(th)));
+            }
+        }
+    } else {
+        for (int l = (int) lo; l < (int) hi; l++) {
+            for (int k = (int) lo; k < l; k++) {
+                const double th = -qft_theta((unsigned) (l - k));
+                QCS_TRY(cphase_any(reg, (unsigned) l, (unsigned) k, 1.0 * cos(th), 1.0 * sin(th)));
+            }
+            QCS_TRY(hadamard_any(reg, (unsigned) l));
+        }
+    }
+    return QCS_NO_ERROR;
+}
+
+static int qft_any(qcs_register *reg, unsigned lo, unsigned hi, bool inverse)
+{
+    if (lo > hi || hi > reg->n) return QCS_BAD_ARGUMENTS;
+    if (lo == hi) return QCS_NO_ERROR;
+    if (reg->opt_fusion) return qcs_fused_qft(reg, lo, hi, inverse);
+    return qft_gate_by_gate(reg, lo, hi, inverse);
+}
+
+extern "C" int qcs_inverse_QFT(qcs_register *reg)
+{
+    QCS_ENTER(reg);
+    return qft_any(reg, (unsigned) reg->M_size, reg->n, true);
+}
+
+extern "C" int qcs_QFT(qcs_register *reg)
+{
+    QCS_ENTER(reg);
+    return qft_any(reg, (unsigned) reg->M_size, reg->n, false);
+}
+
+extern "C" int qcs_inverse_QFT_range(qcs_register *reg, unsigned lo, unsigned hi)
+{
+    QCS_ENTER(reg);
+    return qft_any(reg, lo, hi, true);
+}
+
+extern "C" int qcs_QFT_range(qcs_register *reg, unsigned lo, unsigned hi)
+{
+    QCS_ENTER(reg);
+    return qft_any(reg, lo, hi, false);
+}
+
+extern "C" int qcs_quantum_computation(qcs_register *reg, unsigned C, unsigned a, int pow_mode)
+{
+    QCS_ENTER(reg);
+    if (C == 0 || (pow_mode != QCS_POW_VERBATIM && pow_mode != QCS_POW_MODULAR)) return QCS_BAD_ARGUMENTS;
+    const unsigned first = reg->n - (unsigned) reg->L_size;          // qc_shor.c:720
+    // atox per gate, qc_shor.c:728-731 (x doubles as an unsigned int)
+    std::vector<unsigned long long> atox((size_t) reg->L_size);
+    unsigned x = 1;
+    for (int k = 0; k < reg->L_size; k++) {
+        atox[(size_t) k] = pow_mode == QCS_POW_MODULAR ? qcs_modpow2k(a, (unsigned) k, C)
+                                                       : (unsigned long long) qcs_int_pow(a, x);
+        x *= 2;
+    }
+    if (reg->opt_fusion && reg->L_size > 0) {
+        std::vector<unsigned> A((size_t) reg->L_size);
+        for (int k = 0; k < reg->L_size; k++) A[(size_t) k] = (unsigned) (atox[(size_t) k] % C);
+        int rc = qcs_fused_modexp(reg, C, A.data(), (unsigned) reg->L_size);
+        if (rc != QCS_NO_ERROR) return rc;
+        return qft_any(reg, (unsigned) reg->M_size, reg->n, true);
+    }
+    for (unsigned l = first; l < reg->n; l++) QCS_TRY(hadamard_any(reg, l));
+    for (unsigned l = first; l < reg->n; l++) QCS_TRY(amodc_any(reg, C, atox[l - first], l));
+    return qft_any(reg, (unsigned) reg->M_size, reg->n, true);
+}
+
+// ---------------------------------------------------------------------------
+// measurement and read-back
+// ---------------------------------------------------------------------------
+extern "C" int qcs_norm2(qcs_register *reg, double *sum_of_sq)
+{
+    QCS_ENTER(reg);
+    if (!sum_of_sq) return QCS_BAD_ARGUMENTS;
+    double mine = 0.0;
+    QCS_TRY(qcs_k_norm2_local(reg, &mine));
+    if (reg->world == 1) { *sum_of_sq = mine; return QCS_NO_ERROR; }
+    std::vector<double> all((size_t) reg->world);
+    QCS_TRY(qcs_dist_allgather_double(reg, mine, all.data()));
+    double s = 0.0;
+    for (int r = 0; r < reg->world; r++) s += all[(size_t) r];   // rank order: deterministic
+    *sum_of_sq = s;
+    return QCS_NO_ERROR;
+}
+
+extern "C" int qcs_measure_state(qcs_register *reg, double r, unsigned long long *state_num)
+{
+    QCS_ENTER(reg);
+    if (!state_num) return QCS_BAD_ARGUMENTS;
+    // qc_shor.c:283: the scan covers indices 0 .. N-2; N-1 is the fall-through
+    int found = 0;
+    uint64_t index = 0;
+    double cum = 0.0;
+    uint64_t global_index = reg->N - 1;
+    if (reg->world == 1) {
+        QCS_TRY(qcs_k_measure_scan(reg, 0.0, r, reg->N_local - 1, &found, &index, &cum));
+        if (found) global_index = index;
+    } else {
+        // the running sum is handed from rank to rank in index order
+        for (int turn = 0; turn < reg->world; turn++) {
+            double state[3] = {cum, (double) found, 0.0};
+            if (turn == reg->rank && !found) {
+                const uint64_t limit = reg->rank == reg->world - 1 ? reg->N_local - 1 : reg->N_local;
+                QCS_TRY(qcs_k_measure_scan(reg, cum, r, limit, &found, &index, &cum));
+                if (found) global_index = (uint64_t) reg->rank * reg->N_local + index;
+            }
+            // share (cum, found, index) of the rank whose turn it was
+            std::vector<double> all((size_t) reg->world);
+            QCS_TRY(qcs_dist_allgather_double(reg, cum, all.data()));
+            cum = all[(size_t) turn];
+            QCS_TRY(qcs_dist_allgather_double(reg, found ? 1.0 : 0.0, all.data()));
+            found = all[(size_t) turn] != 0.0;
+            // indices < 2^53 are exact in a double
+            QCS_TRY(qcs_dist_allgather_double(reg, (double) global_index, all.data()));
+            global_index = (uint64_t) all[(size_t) turn];
+            (void) state;
+            if (found) break;
+        }
+    }
+    // collapse, qc_shor.c:302-303
+    const uint64_t owner = global_index >> reg->n_local;
+    QCS_TRY(qcs_k_collapse(reg, global_index & (reg->N_local - 1), owner == (uint64_t) reg->rank));
+    QCS_CUDA(cudaStreamSynchronize(reg->stream));
+    *state_num = global_index;
+    return QCS_NO_ERROR;
+}
+
+extern "C" int qcs_get_state(qcs_register *reg, unsigned long long first, unsigned long long count,
+                             double *interleaved_out)
+{
+    QCS_ENTER(reg);
+    if (first > reg->N_local || count > reg->N_local - first || (!interleaved_out && count)) return QCS_BAD_ARGUMENTS;
+    QCS_CUDA(cudaMemcpyAsync(interleaved_out, reg->amp + first, count * sizeof(double2),
+                             cudaMemcpyDeviceToHost, reg->stream));
+    QCS_CUDA(cudaStreamSynchronize(reg->stream));
+    return QCS_NO_ERROR;
+}
+
+extern "C" int qcs_set_state(qcs_register *reg, unsigned long long first, unsigned long long count,
+                             const double *interleaved_in)
+{
+    QCS_ENTER(reg);
+    if (first > reg->N_local || count > reg->N_local - first || (!interleaved_in && count)) return QCS_BAD_ARGUMENTS;
+    QCS_CUDA(cudaMemcpyAsync(reg->amp + first, interleaved_in, count * sizeof(double2),
+                             cudaMemcpyHostToDevice, reg->stream));
+    return QCS_NO_ERROR;
+}
+
+extern "C" int qcs_nonzero_states(qcs_register *reg, unsigned long long capacity,
+                                  unsigned long long *indices, double *abs_values,
+                                  unsigned long long *count)
+{
+    QCS_ENTER(reg);
+    if (!count) return QCS_BAD_ARGUMENTS;
+    // display_state, testing_and_debug.c:7-26: a console listing, so the
+    // amplitudes are streamed to the host in bounded pieces and filtered there
+    const uint64_t piece = 1ull << 20;
+    double *buf = nullptr;
+    QCS_CUDA(cudaHostAlloc((void **) &buf, piece * sizeof(double2), cudaHostAllocDefault));
+    unsigned long long total = 0;
+    int rc = QCS_NO_ERROR;
+    for (uint64_t at = 0; at < reg->N_local && rc == QCS_NO_ERROR; at += piece) {
+        const uint64_t len = reg->N_local - at < piece ? reg->N_local - at : piece;
+        rc = qcs_get_state(reg, at, len, buf);
+        for (uint64_t i = 0; i < len && rc == QCS_NO_ERROR; i++) {
+            const double mag = hypot(buf[2 * i], buf[2 * i + 1]);    // gsl_complex_abs
+            if (mag != 0.0) {
+                if (total < capacity) {
+                    if (indices) indices[total] = (uint64_t) reg->rank * reg->N_local + at + i;
+                    if (abs_values) abs_values[total] = mag;
+                }
+                total++;
+            }
+        }
+    }
+    cudaFreeHost(buf);
+    *count = total;
+    return rc;
+}
+
+extern "C" int qcs_fill_synthetic(qcs_register *reg, unsigned long long seed)
+{
+    QCS_ENTER(reg);
+    return qcs_k_fill_synthetic(reg, seed);
+}
+
+extern "C" int qcs_scale(qcs_register *reg, double factor)
+{
+    QCS_ENTER(reg);
+    return qcs_k_scale(reg, factor);
+}
+
+// ---------------------------------------------------------------------------
+// stopwatch and profile
+// ---------------------------------------------------------------------------
+extern "C" int qcs_timer_start(qcs_register *reg)
+{
+    QCS_ENTER(reg);
+    QCS_CUDA(cudaEventRecord(reg->timer_begin, reg->stream));
+    return QCS_NO_ERROR;
+}
+
+extern "C" int qcs_timer_stop(qcs_register *reg, double *milliseconds)
+{
+    QCS_ENTER(reg);
+    if (!milliseconds) return QCS_BAD_ARGUMENTS;
+    QCS_CUDA(cudaEventRecord(reg->timer_end, reg->stream));
+    QCS_CUDA(cudaEventSynchronize(reg->timer_end));
+    float ms = 0.f;
+    QCS_CUDA(cudaEventElapsedTime(&ms, reg->timer_begin, reg->timer_end));
+    *milliseconds = (double) ms;
+    return QCS_NO_ERROR;
+}
+
+extern "C" unsigned long long qcs_launch_count(const qcs_register *reg) { return reg ? reg->launches_total : 0; }
+
+extern "C" int qcs_profile_reset(qcs_register *reg)
+{
+    QCS_ENTER(reg);
+    QCS_TRY(qcs_profile_resolve(reg));
+    reg->launches_total = 0;
+    memset(reg->launches, 0, sizeof reg->launches);
+    memset(reg->alg_bytes, 0, sizeof reg->alg_bytes);
+    memset(reg->ms, 0, sizeof reg->ms);
+    return QCS_NO_ERROR;
+}
+
+extern "C" int qcs_profile_get(qcs_register *reg, int k, unsigned long long *launches, double *milliseconds,
+                               double *algorithmic_bytes)
+{
+    QCS_ENTER(reg);
+    if (k < 0 || k >= QCS_K_COUNT) return QCS_BAD_ARGUMENTS;
+    QCS_TRY(qcs_profile_resolve(reg));
+    if (launches) *launches = reg->launches[k];
+    if (milliseconds) *milliseconds = reg->ms[k];
+    if (algorithmic_bytes) *algorithmic_bytes = reg->alg_bytes[k];
+    return QCS_NO_ERROR;
+}

@@ -1,0 +1,222 @@
+// dist.cu -- sharded registers: one process per GPU, the top log2(P) qubits
+// are global.  Gates on local qubits and all diagonal gates run
+// without communication (api.cu); the only gate of the reference that needs
+// an exchange is a Hadamard on a global qubit.
+//
+// NCCL is resolved with dlopen("libnccl.so.2") at the first sharded create, so
+// libqcs.so has no link-time dependency on it and, inside a torch process,
+// binds to the NCCL instance torch already loaded.
+#include "qcs_internal.h"
+
+#include <dlfcn.h>
+#include <nccl.h>     // types only; every entry point is looked up at run time
+#include <string.h>
+
+namespace {
+
+struct nccl_api {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+nccl_api g_nccl;
+
+int load_nccl()
+{
+    if (g_nccl.handle) return QCS_NO_ERROR;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        fprintf(stderr, "qcs: cannot load NCCL (%s); sharded registers are unavailable\n", dlerror());
+        return QCS_UNKNOWN_ERROR;
+    }
+#define QCS_SYM(field, name)                                              \
+    *(void **) (&g_nccl.field) = dlsym(h, name);                          \
+    if (!g_nccl.field) { fprintf(stderr, "qcs: NCCL symbol %s missing\n", name); dlclose(h); return QCS_UNKNOWN_ERROR; }
+    QCS_SYM(GetUniqueId, "ncclGetUniqueId")
+    QCS_SYM(CommInitRank, "ncclCommInitRank")
+    QCS_SYM(CommDestroy, "ncclCommDestroy")
+    QCS_SYM(Send, "ncclSend")
+    QCS_SYM(Recv, "ncclRecv")
+    QCS_SYM(AllGather, "ncclAllGather")
+    QCS_SYM(GroupStart, "ncclGroupStart")
+    QCS_SYM(GroupEnd, "ncclGroupEnd")
+    QCS_SYM(GetErrorString, "ncclGetErrorString")
+#undef QCS_SYM
+    g_nccl.handle = h;
+    return QCS_NO_ERROR;
+}
+
+int nccl_fail(ncclResult_t r, const char *what)
+{
+    fprintf(stderr, "qcs: NCCL error in %s: %s\n", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    return QCS_UNKNOWN_ERROR;
+}
+#define QCS_NCCL(call)                                              \
+    do {                                                            \
+        ncclResult_t qcs_nr_ = (call);                              \
+        if (qcs_nr_ != ncclSuccess) return nccl_fail(qcs_nr_, #call); \
+    } while (0)
+
+// combine step of a Hadamard whose target qubit is global.  `mine` holds the
+// amplitudes of this rank, `theirs` the partner's copy of the same local
+// indices.  Arithmetic and order are those of gates_exact.cu / qc_shor.c:409-412:
+//   bit 0 rank:  new = (0 + h*mine)   + h*theirs
+//   bit 1 rank:  new = (0 + h*theirs) + (-h)*mine
+__global__ void __launch_bounds__(256)
+k_hadamard_global_combine(double2 *__restrict__ mine, const double2 *__restrict__ theirs, uint64_t count, int my_bit)
+{
+    const double h = 0.70710678118654752440;
+    const uint64_t stride = (uint64_t) gridDim.x * 256;
+    for (uint64_t i = (uint64_t) blockIdx.x * 256 + threadIdx.x; i < count; i += stride) {
+        const double2 a = mine[i], b = theirs[i];
+        const double2 lo = my_bit ? b : a;        // amplitude with target bit 0
+        const double2 hi = my_bit ? a : b;        // amplitude with target bit 1
+        const double m1 = my_bit ? -h : h;
+        double2 r;
+        // h * lo + 0.0 * ... with the imaginary part of H being literally 0.0
+        const double t0x = __dsub_rn(__dmul_rn(h, lo.x), __dmul_rn(0.0, lo.y));
+        const double t0y = __dadd_rn(__dmul_rn(h, lo.y), __dmul_rn(0.0, lo.x));
+        const double t1x = __dsub_rn(__dmul_rn(m1, hi.x), __dmul_rn(0.0, hi.y));
+        const double t1y = __dadd_rn(__dmul_rn(m1, hi.y), __dmul_rn(0.0, hi.x));
+        r.x = __dadd_rn(__dadd_rn(0.0, t0x), t1x);
+        r.y = __dadd_rn(__dadd_rn(0.0, t0y), t1y);
+        mine[i] = r;
+    }
+}
+
+}  // namespace
+
+struct qcs_dist {
+    ncclComm_t comm = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    double2 *staging[2] = {nullptr, nullptr};
+    uint64_t staging_amps = 0;
+    cudaEvent_t recv_done[2] = {nullptr, nullptr};
+    cudaEvent_t buf_free[2] = {nullptr, nullptr};
+    cudaEvent_t ready = nullptr;
+    double *d_gather = nullptr;     // world doubles
+    double *h_gather = nullptr;     // pinned
+};
+
+extern "C" int qcs_comm_unique_id(void *id_out)
+{
+    if (!id_out) return QCS_BAD_ARGUMENTS;
+    QCS_TRY(load_nccl());
+    ncclUniqueId id;
+    QCS_NCCL(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == QCS_COMM_ID_BYTES, "id size");
+    memcpy(id_out, &id, sizeof id);
+    return QCS_NO_ERROR;
+}
+
+int qcs_dist_init(qcs_register *reg, const void *comm_id)
+{
+    QCS_TRY(load_nccl());
+    qcs_dist *d = new qcs_dist();
+    reg->dist = d;
+    ncclUniqueId id;
+    memcpy(&id, comm_id, sizeof id);
+    QCS_NCCL(g_nccl.CommInitRank(&d->comm, reg->world, id, reg->rank));
+    QCS_CUDA(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
+    // bounded staging: two buffers of at most 2^24 amplitudes (256 MiB) each
+    d->staging_amps = reg->N_local < (1ull << 24) ? reg->N_local : (1ull << 24);
+    for (int b = 0; b < 2; b++) {
+        QCS_CUDA(cudaMalloc((void **) &d->staging[b], d->staging_amps * sizeof(double2)));
+        QCS_CUDA(cudaEventCreateWithFlags(&d->recv_done[b], cudaEventDisableTiming));
+        QCS_CUDA(cudaEventCreateWithFlags(&d->buf_free[b], cudaEventDisableTiming));
+    }
+    QCS_CUDA(cudaEventCreateWithFlags(&d->ready, cudaEventDisableTiming));
+    QCS_CUDA(cudaMalloc((void **) &d->d_gather, (size_t) (reg->world + 1) * sizeof(double)));
+    QCS_CUDA(cudaHostAlloc((void **) &d->h_gather, (size_t) (reg->world + 1) * sizeof(double), cudaHostAllocDefault));
+    return QCS_NO_ERROR;
+}
+
+void qcs_dist_destroy(qcs_register *reg)
+{
+    qcs_dist *d = reg->dist;
+    if (!d) return;
+    if (d->comm_stream) cudaStreamSynchronize(d->comm_stream);
+    if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+    for (int b = 0; b < 2; b++) {
+        if (d->staging[b]) cudaFree(d->staging[b]);
+        if (d->recv_done[b]) cudaEventDestroy(d->recv_done[b]);
+        if (d->buf_free[b]) cudaEventDestroy(d->buf_free[b]);
+    }
+    if (d->ready) cudaEventDestroy(d->ready);
+    if (d->d_gather) cudaFree(d->d_gather);
+    if (d->h_gather) cudaFreeHost(d->h_gather);
+    if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
+    delete d;
+    reg->dist = nullptr;
+}
+
+int qcs_dist_allgather_double(qcs_register *reg, double mine, double *all_host)
+{
+    qcs_dist *d = reg->dist;
+    if (!d) return QCS_BAD_ARGUMENTS;
+    d->h_gather[reg->world] = mine;
+    QCS_CUDA(cudaMemcpyAsync(d->d_gather + reg->world, d->h_gather + reg->world, sizeof(double),
+                             cudaMemcpyHostToDevice, reg->stream));
+    QCS_NCCL(g_nccl.AllGather(d->d_gather + reg->world, d->d_gather, 1, ncclDouble, d->comm, reg->stream));
+    QCS_CUDA(cudaMemcpyAsync(d->h_gather, d->d_gather, (size_t) reg->world * sizeof(double),
+                             cudaMemcpyDeviceToHost, reg->stream));
+    QCS_CUDA(cudaStreamSynchronize(reg->stream));
+    memcpy(all_host, d->h_gather, (size_t) reg->world * sizeof(double));
+    return QCS_NO_ERROR;
+}
+
+int qcs_dist_barrier(qcs_register *reg)
+{
+    if (reg->world == 1) return QCS_NO_ERROR;
+    std::vector<double> all((size_t) reg->world);
+    return qcs_dist_allgather_double(reg, 0.0, all.data());
+}
+
+// Hadamard on a global qubit: pairwise exchange with rank ^ 2^(q - n_local),
+// chunked through two staging buffers so that the combine kernel of chunk c
+// overlaps the NVLink transfer of chunk c+1.
+int qcs_dist_hadamard_global(qcs_register *reg, unsigned q)
+{
+    qcs_dist *d = reg->dist;
+    if (!d || q < reg->n_local || q >= reg->n) return QCS_BAD_ARGUMENTS;
+    const int bitpos = (int) (q - reg->n_local);
+    const int partner = reg->rank ^ (1 << bitpos);
+    const int my_bit = (reg->rank >> bitpos) & 1;
+    const uint64_t chunk = d->staging_amps;
+    const uint64_t n_chunks = reg->N_local / chunk;
+
+    // the exchange reads amplitudes produced by earlier kernels on the compute stream
+    QCS_CUDA(cudaEventRecord(d->ready, reg->stream));
+    QCS_CUDA(cudaStreamWaitEvent(d->comm_stream, d->ready, 0));
+    for (uint64_t c = 0; c < n_chunks; c++) {
+        const int b = (int) (c & 1);
+        double2 *mine = reg->amp + c * chunk;
+        if (c >= 2) QCS_CUDA(cudaStreamWaitEvent(d->comm_stream, d->buf_free[b], 0));
+        reg->launches_total++;
+        reg->launches[QCS_K_EXCHANGE]++;
+        reg->alg_bytes[QCS_K_EXCHANGE] += 16.0 * (double) chunk;
+        QCS_NCCL(g_nccl.GroupStart());
+        QCS_NCCL(g_nccl.Send(mine, chunk * 2, ncclDouble, partner, d->comm, d->comm_stream));
+        QCS_NCCL(g_nccl.Recv(d->staging[b], chunk * 2, ncclDouble, partner, d->comm, d->comm_stream));
+        QCS_NCCL(g_nccl.GroupEnd());
+        QCS_CUDA(cudaEventRecord(d->recv_done[b], d->comm_stream));
+        QCS_CUDA(cudaStreamWaitEvent(reg->stream, d->recv_done[b], 0));
+        uint64_t grid = (chunk + 255) / 256;
+        const uint64_t cap = (uint64_t) reg->sm_count * 8;
+        if (grid > cap) grid = cap;
+        qcs_launch_begin(reg, QCS_K_HADAMARD, 48.0 * (double) chunk);
+        k_hadamard_global_combine<<<(unsigned) grid, 256, 0, reg->stream>>>(mine, d->staging[b], chunk, my_bit);
+        QCS_TRY(qcs_launch_end(reg, QCS_K_HADAMARD, "k_hadamard_global_combine"));
+        QCS_CUDA(cudaEventRecord(d->buf_free[b], reg->stream));
+    }
+    return QCS_NO_ERROR;
+}

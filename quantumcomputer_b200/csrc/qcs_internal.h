@@ -1,0 +1,114 @@
+// qcs_internal.h -- shared declarations of libqcs.so (not installed).
+//
+// The register is one in-place array of 2^n_local complex doubles in HBM
+// (double2 = 16 B, interleaved re/im: the gsl_vector_complex.data layout of
+// the reference, qc_shor.c:385-386).  All indices are 64-bit.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <vector>
+
+#include "../../include/qcs.h"
+
+struct qcs_dist;   // multi-GPU state (dist.cu)
+
+struct qcs_profile_slot {
+    cudaEvent_t begin, end;
+    int kind;
+};
+
+struct qcs_register {
+    int L_size, M_size;
+    unsigned n;             // total qubits
+    unsigned n_local;       // qubits addressed inside this shard
+    uint64_t N;             // 2^n
+    uint64_t N_local;       // 2^n_local
+    int device;
+    cudaStream_t stream;
+    double2 *amp;           // this shard, in place
+
+    // small device/host scratch
+    double *d_partials;     // reduction partials
+    size_t partials_cap;    // in doubles
+    void *d_small;          // 4 KiB device scratch (measurement result etc.)
+    void *h_small;          // 4 KiB pinned host mirror
+
+    // options
+    int opt_fusion;
+    int opt_profile;
+    int opt_tile_bits;
+
+    // accounting
+    unsigned long long launches_total;
+    unsigned long long launches[QCS_K_COUNT];
+    double alg_bytes[QCS_K_COUNT];
+    double ms[QCS_K_COUNT];
+    std::vector<qcs_profile_slot> pending;     // event pairs not yet resolved
+    std::vector<qcs_profile_slot> free_slots;
+    cudaEvent_t timer_begin, timer_end;
+
+    int sm_count;
+    size_t smem_optin;      // max dynamic shared memory per block
+
+    // sharding: rank holds amplitudes whose top log2(world) index bits == rank
+    int rank, world, p_global;
+    qcs_dist *dist;
+};
+
+// ---- error plumbing -------------------------------------------------------
+int qcs_map_cuda_error(cudaError_t e, const char *what, const char *file, int line);
+#define QCS_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t qcs_e_ = (call);                                                \
+        if (qcs_e_ != cudaSuccess) return qcs_map_cuda_error(qcs_e_, #call, __FILE__, __LINE__); \
+    } while (0)
+#define QCS_TRY(call)                                \
+    do {                                             \
+        int qcs_rc_ = (call);                        \
+        if (qcs_rc_ != QCS_NO_ERROR) return qcs_rc_; \
+    } while (0)
+
+// ---- launch accounting ----------------------------------------------------
+// Every kernel launch of the library goes through these two calls so that
+// launches are counted and, with QCS_OPT_PROFILE, timed on the launching stream.
+void qcs_launch_begin(qcs_register *reg, int kind, double algorithmic_bytes);
+int qcs_launch_end(qcs_register *reg, int kind, const char *name);
+int qcs_profile_resolve(qcs_register *reg);
+
+// ---- device-side index helpers --------------------------------------------
+__host__ __device__ __forceinline__ uint64_t qcs_insert_zero_bit(uint64_t x, unsigned pos)
+{
+    const uint64_t low = (1ull << pos) - 1ull;
+    return ((x & ~low) << 1) | (x & low);
+}
+
+// ---- per-gate (reference-order) kernels: gates_exact.cu -------------------
+int qcs_k_reset(qcs_register *reg);
+int qcs_k_collapse(qcs_register *reg, uint64_t local_index, bool owner);
+int qcs_k_fill_synthetic(qcs_register *reg, uint64_t seed);
+int qcs_k_scale(qcs_register *reg, double s);
+int qcs_k_hadamard_local(qcs_register *reg, unsigned q);
+// multiply by (c + i s) every local amplitude whose bits in `mask_bits` are all 1
+int qcs_k_phase_masked(qcs_register *reg, int nbits, unsigned b0, unsigned b1, double c, double s);
+int qcs_k_amodc(qcs_register *reg, unsigned C, unsigned A, int ctrl_local /* -1: always on */,
+                bool ctrl_off);
+
+// ---- reductions / measurement: measure.cu ---------------------------------
+int qcs_k_norm2_local(qcs_register *reg, double *out_host);
+// sequential-semantics scan of this shard starting from `cum_in`; *found / *index
+// as in measure_state (qc_shor.c:283-292) restricted to [0, limit)
+int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limit,
+                       int *found, uint64_t *index, double *cum_out);
+
+// ---- fused sweeps: qft_fused.cu / modexp_fused.cu ---------------------------
+int qcs_fused_qft(qcs_register *reg, unsigned lo, unsigned hi, bool inverse);
+int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, unsigned n_gates);
+
+// ---- multi-GPU: dist.cu ---------------------------------------------------
+int qcs_dist_init(qcs_register *reg, const void *comm_id);
+void qcs_dist_destroy(qcs_register *reg);
+int qcs_dist_hadamard_global(qcs_register *reg, unsigned q);
+int qcs_dist_allgather_double(qcs_register *reg, double mine, double *all_host);
+int qcs_dist_barrier(qcs_register *reg);

@@ -1,0 +1,160 @@
+"""GPU parity tests, per-gate (reference-order) kernels, through the C ABI.
+
+Checker: the oracle restatement (bit-identical to the reference, see
+test_oracle.py) and the committed golden vectors of the unmodified reference.
+Bar: amplitudes value-identical (every double compares ==; the sign of an exact
+zero is the only freedom), measured indices and factors identical."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, unhex_c128, values_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def exact_register(qcs, L, M):
+    reg = qcs.Register(L, M)
+    reg.set_option(qcs.OPT_FUSION, 0)
+    return reg
+
+
+def test_reset_register(qcs):
+    with exact_register(qcs, 3, 4) as reg:
+        reg.reset_register()
+        s = reg.get_state()
+        assert s[1] == 1.0 and np.count_nonzero(s) == 1
+        assert reg.norm2() == 1.0
+
+
+def test_single_gates_match_reference_golden(qcs):
+    g = load_golden("single_gates.json")
+    base = unhex_c128(g["input"])
+    with exact_register(qcs, g["L"], g["M"]) as reg:
+        for h in g["hadamard"]:
+            reg.set_state(base)
+            reg.hadamard_gate(h["q"])
+            assert values_equal(reg.get_state(), unhex_c128(h["state"])), ("H", h["q"])
+        for c in g["cphase"]:
+            reg.set_state(base)
+            reg.c_phase_shift_gate(c["c"], c["q"], float.fromhex(c["theta"]))
+            assert values_equal(reg.get_state(), unhex_c128(c["state"])), ("CP", c["c"], c["q"])
+        for a in g["amodc"]:
+            reg.set_state(base)
+            reg.c_amodc_gate(a["C"], a["atox"], a["c"])
+            assert values_equal(reg.get_state(), unhex_c128(a["state"])), ("amodc", a["C"], a["atox"], a["c"])
+
+
+def test_inverse_qft_gate_by_gate_matches_reference_golden(qcs):
+    for case in load_golden("inverse_qft.json")["cases"]:
+        with exact_register(qcs, case["L"], case["M"]) as reg:
+            reg.set_state(unhex_c128(case["input"]))
+            reg.inverse_QFT()
+            assert values_equal(reg.get_state(), unhex_c128(case["output"])), (case["L"], case["M"])
+
+
+def test_shor_states_and_measurement_match_reference_golden(qcs):
+    for case in load_golden("shor_states.json")["cases"]:
+        with exact_register(qcs, case["L"], case["M"]) as reg:
+            reg.reset_register()
+            reg.quantum_computation(case["C"], case["a"], qcs.POW_VERBATIM)
+            want = unhex_c128(case["state"])
+            assert values_equal(reg.get_state(), want), case["C"]
+            assert abs(reg.norm2() - float.fromhex(case["norm2"])) < 1e-14
+            for m in case["measured"]:
+                reg.set_state(want)
+                idx = reg.measure_state(float.fromhex(m["r"]))
+                assert idx == m["index"], (case["C"], m)
+                collapsed = reg.get_state()
+                assert collapsed[idx] == 1.0 and np.count_nonzero(collapsed) == 1
+
+
+@pytest.mark.parametrize("L,M", [(1, 1), (2, 3), (7, 4), (9, 5), (10, 7), (13, 3)])
+def test_random_circuits_match_oracle(qcs, oracle_built, L, M):
+    """Random H / C-phase / a^x mod C sequences at sizes up to n = 17."""
+    n = L + M
+    rng = np.random.default_rng(1000 * L + M)
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    v /= np.linalg.norm(v)
+    o = oracle_built.Restatement(L, M)
+    o.set_state(v)
+    with exact_register(qcs, L, M) as reg:
+        reg.set_state(v)
+        for step in range(14):
+            kind = int(rng.integers(0, 3))
+            if kind == 0:
+                q = int(rng.integers(0, n))
+                o.hadamard_gate(q)
+                reg.hadamard_gate(q)
+            elif kind == 1:
+                c, q = (int(x) for x in rng.choice(n, size=2, replace=False))
+                th = float(rng.uniform(-math.pi, math.pi))
+                o.c_phase_shift_gate(c, q, th)
+                reg.c_phase_shift_gate(c, q, th)
+            else:
+                Cn = int(rng.integers(2, (1 << M) + 1))
+                atox = int(rng.integers(0, 5000))
+                c = int(rng.integers(M, n))
+                o.c_amodc_gate(Cn, atox, c)
+                reg.c_amodc_gate(Cn, atox, c)
+        assert values_equal(reg.get_state(), o.get_state())
+        # ragged measurement cases: first index, last index, fall-through, interior
+        state = o.get_state().copy()
+        for r in (0.0, 1e-300, 0.25, 0.5, 0.999999, 1.0 - 2 ** -32, 2.0):
+            o.set_state(state)
+            reg.set_state(state)
+            assert reg.measure_state(r) == o.measure_state(r), r
+
+
+def test_amodc_edge_cases_match_oracle(qcs, oracle_built):
+    """control inside the M register, C > 2^M, C = 1, A = 0, atox >= 2^32."""
+    L, M = 4, 4
+    n = L + M
+    rng = np.random.default_rng(77)
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    with exact_register(qcs, L, M) as reg:
+        for (Cn, atox, c) in [(13, 5, 2), (13, 5, 0), (23, 7, 5), (40, 3, 6), (1, 9, 4), (12, 24, 7),
+                              (16, 3, 4), (9, 2 ** 50 + 1, 5), (15, 10, 6)]:
+            o = oracle_built.Restatement(L, M)
+            o.set_state(v)
+            o.c_amodc_gate(Cn, atox, c)
+            reg.set_state(v)
+            reg.c_amodc_gate(Cn, atox, c)
+            assert values_equal(reg.get_state(), o.get_state()), (Cn, atox, c)
+
+
+def test_bad_arguments(qcs):
+    with exact_register(qcs, 3, 4) as reg:
+        for call in (lambda: reg.hadamard_gate(7), lambda: reg.c_phase_shift_gate(7, 0, 0.1),
+                     lambda: reg.c_amodc_gate(0, 3, 4), lambda: reg.c_amodc_gate(15, 3, 9)):
+            with pytest.raises(qcs.QcsError) as e:
+                call()
+            assert e.value.code == qcs.BAD_ARGUMENTS
+
+
+def test_nonzero_states_is_display_state(qcs):
+    case = load_golden("shor_states.json")["cases"][0]
+    with exact_register(qcs, case["L"], case["M"]) as reg:
+        reg.set_state(unhex_c128(case["state"]))
+        idx, mag, count = reg.nonzero_states()
+        assert count == 16 and idx == [1, 4, 7, 13, 17, 20, 23, 29, 33, 36, 39, 45, 49, 52, 55, 61]
+        assert all(abs(m - 0.25) < 1e-15 for m in mag)
+
+
+def test_hh_identity_and_norm_at_scale(qcs):
+    """Size-independent properties at n = 26 (1 GiB): H.H = I to rounding, norm kept."""
+    n = 26
+    with exact_register(qcs, n, 0) as reg:
+        reg.fill_synthetic(1234)
+        s0 = reg.norm2()
+        reg.scale(1.0 / math.sqrt(s0))
+        assert abs(reg.norm2() - 1.0) < 1e-12
+        probe = [0, 1, 12345, (1 << n) - 1]
+        before = [reg.get_state(i, 1)[0] for i in probe]
+        for q in (0, 3, 5, 17, n - 1):
+            reg.hadamard_gate(q)
+            assert abs(reg.norm2() - 1.0) < 1e-12
+            reg.hadamard_gate(q)
+        after = [reg.get_state(i, 1)[0] for i in probe]
+        assert max(abs(a - b) for a, b in zip(before, after)) < 1e-15

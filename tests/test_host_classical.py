@@ -1,0 +1,79 @@
+"""CPU tests of the C host driver's classical half (quantumcomputer_b200/host),
+against vectors produced by the unmodified reference (tests/golden/scalars.json)."""
+import ctypes as C
+import os
+
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+@pytest.fixture(scope="module")
+def host(qcs):
+    lib = C.CDLL(os.path.join(ROOT, "quantumcomputer_b200", "lib", "libqcshost.so"))
+    lib.qcsh_gcd.restype = C.c_uint
+    lib.qcsh_gcd.argtypes = [C.c_uint, C.c_uint]
+    lib.qcsh_read_omega.restype = C.c_double
+    lib.qcsh_read_omega.argtypes = [C.c_ulonglong, C.c_int, C.c_int]
+    lib.qcsh_continued_fraction_denominators.restype = C.c_uint
+    lib.qcsh_continued_fraction_denominators.argtypes = [C.c_double, C.c_uint, C.POINTER(C.c_uint), C.c_int]
+    lib.qcsh_period_is_valid.restype = C.c_int
+    lib.qcsh_period_is_valid.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_int]
+    lib.qcsh_modpow.restype = C.c_ulonglong
+    lib.qcsh_modpow.argtypes = [C.c_uint, C.c_ulonglong, C.c_uint]
+    lib.qcsh_rng_seed.argtypes = [C.c_void_p, C.c_ulong]
+    lib.qcsh_rng_uniform.restype = C.c_double
+    lib.qcsh_rng_uniform.argtypes = [C.c_void_p]
+    lib.qcsh_rng_u32.restype = C.c_uint32
+    lib.qcsh_rng_u32.argtypes = [C.c_void_p]
+    return lib
+
+
+def new_rng(host, seed):
+    buf = C.create_string_buffer(624 * 4 + 16)
+    host.qcsh_rng_seed(buf, seed)
+    return buf
+
+
+def test_mt19937_kat3(host):
+    g = new_rng(host, 5489)
+    assert [host.qcsh_rng_u32(g), host.qcsh_rng_u32(g)] == [3499211612, 581869302]
+    gold = load_golden("scalars.json")["mt19937"]
+    for key, seed in (("seed5489_first_uniform", 5489), ("seed0_first_uniform", 0), ("seed4357_first_uniform", 4357)):
+        g = new_rng(host, seed)
+        assert [host.qcsh_rng_uniform(g).hex() for _ in gold[key]] == gold[key]
+    g = new_rng(host, 12345)
+    assert host.qcsh_rng_uniform(g) == 0.92961608665063977      # KAT-1's r
+
+
+def test_gcd_and_read_omega(host):
+    g = load_golden("scalars.json")
+    for e in g["gcd"]:
+        assert host.qcsh_gcd(e["a"], e["b"]) == e["g"], e
+    for e in g["read_omega"]:
+        assert host.qcsh_read_omega(e["state"], e["L"], e["M"]).hex() == e["omega"], e
+
+
+def test_continued_fractions_verbatim(host):
+    for e in load_golden("scalars.json")["continued_fractions"]:
+        out = (C.c_uint * 15)()
+        n = host.qcsh_continued_fraction_denominators(float.fromhex(e["omega"]), 15, out, 0)
+        assert n == 15 and list(out) == e["den"], e
+
+
+def test_continued_fractions_robust_terminate(host):
+    out = (C.c_uint * 15)()
+    n = host.qcsh_continued_fraction_denominators(0.75, 15, out, 1)
+    assert list(out[:n])[:3] == [1, 1, 4] and n <= 15
+    n0 = host.qcsh_continued_fraction_denominators(0.0, 15, out, 1)
+    assert n0 == 1 and out[0] == 1
+    n = host.qcsh_continued_fraction_denominators(5.0 / 32.0, 15, out, 1)     # KAT-2's omega = 0.15625
+    assert 6 in [out[i] * m for i in range(n) for m in range(1, 11)]
+
+
+def test_period_validity(host):
+    assert host.qcsh_period_is_valid(7, 4, 15, 0) == 1 and host.qcsh_period_is_valid(7, 4, 15, 1) == 1
+    assert host.qcsh_period_is_valid(7, 2, 15, 0) == 0
+    # 2^60 wraps INT_POW (verbatim says 0 % 21 != 1) but is 1 mod 21
+    assert host.qcsh_period_is_valid(2, 60, 21, 0) == 0 and host.qcsh_period_is_valid(2, 60, 21, 1) == 1
+    assert host.qcsh_modpow(7, 123456789, 1000003) == pow(7, 123456789, 1000003)

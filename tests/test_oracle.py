@@ -1,0 +1,170 @@
+"""CPU tests: the oracle restatement (oracle/qcs_oracle.c) pinned against the
+golden vectors produced by the unmodified reference, and -- when
+oracle/_ref/libqcref.so is present -- against the reference itself, live."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, unhex_c128, unhex_f64
+
+
+def bits_equal(a, b):
+    return np.array_equal(np.asarray(a).view(np.uint64), np.asarray(b).view(np.uint64))
+
+
+def test_kat3_mt19937(oracle_built):
+    g = oracle_built.Restatement(1, 1).rng(5489)
+    assert [g.next_u32(), g.next_u32()] == [3499211612, 581869302]
+    gold = load_golden("scalars.json")["mt19937"]
+    for key, seed in (("seed5489_first_uniform", 5489), ("seed0_first_uniform", 0), ("seed4357_first_uniform", 4357)):
+        g = oracle_built.Restatement(1, 1).rng(seed)
+        assert [g.uniform().hex() for _ in gold[key]] == gold[key]
+    # seed 0 is replaced by 4357
+    assert gold["seed0_first_uniform"] == gold["seed4357_first_uniform"]
+
+
+def test_kat1_state_and_measurement(oracle_built):
+    o = oracle_built.Restatement(3, 4)
+    o.reset_register()
+    o.quantum_computation(15, 7, 0)
+    s = o.get_state()
+    nz = np.nonzero(s)[0].tolist()
+    assert nz == [1, 4, 7, 13, 17, 20, 23, 29, 33, 36, 39, 45, 49, 52, 55, 61]
+    assert all(abs(abs(s[i]) - 0.25000000000000006) < 1e-17 for i in nz)
+    assert s[39] == complex(1.5308084989341921e-17, 0.25000000000000006)
+    assert o.norm2() == 1.0000000000000002
+    r = o.rng(12345).uniform()
+    assert r == 0.92961608665063977
+    assert o.measure_state(r) == 55
+    assert oracle_built.Restatement.read_omega(55, 3, 4) == 0.75
+    assert oracle_built.Restatement.cf_denominators(0.75)[:5] == [1, 1, 4, 1, 4]
+
+
+def test_shor_states_bit_identical_to_reference_golden(oracle_built):
+    for case in load_golden("shor_states.json")["cases"]:
+        o = oracle_built.Restatement(case["L"], case["M"])
+        o.reset_register()
+        o.quantum_computation(case["C"], case["a"], 0)
+        want = unhex_c128(case["state"])
+        assert bits_equal(o.get_state(), want), case
+        assert o.norm2().hex() == case["norm2"]
+        for m in case["measured"]:
+            o.set_state(want)
+            r = float.fromhex(m["r"])
+            assert o.rng(m["seed"]).uniform() == r
+            assert o.measure_state(r) == m["index"]
+            assert oracle_built.Restatement.read_omega(m["index"], case["L"], case["M"]) == m["omega"]
+            collapsed = o.get_state()
+            assert collapsed[m["index"]] == 1.0 and np.count_nonzero(collapsed) == 1
+
+
+def test_kat2_counts(oracle_built):
+    case = [c for c in load_golden("shor_states.json")["cases"] if c["C"] == 21 and c["L"] == 5][0]
+    s = unhex_c128(case["state"])
+    assert int((np.abs(s) ** 2 > 1e-14).sum()) == 188
+    assert float.fromhex(case["norm2"]) == 0.99999999999999933
+    assert [m["index"] for m in case["measured"] if m["seed"] == 2021] == [651]
+
+
+def test_single_gates_bit_identical(oracle_built):
+    g = load_golden("single_gates.json")
+    base = unhex_c128(g["input"])
+    for h in g["hadamard"]:
+        o = oracle_built.Restatement(g["L"], g["M"])
+        o.set_state(base)
+        o.hadamard_gate(h["q"])
+        assert bits_equal(o.get_state(), unhex_c128(h["state"])), h["q"]
+    for c in g["cphase"]:
+        o = oracle_built.Restatement(g["L"], g["M"])
+        o.set_state(base)
+        o.c_phase_shift_gate(c["c"], c["q"], float.fromhex(c["theta"]))
+        assert bits_equal(o.get_state(), unhex_c128(c["state"])), (c["c"], c["q"])
+    for a in g["amodc"]:
+        o = oracle_built.Restatement(g["L"], g["M"])
+        o.set_state(base)
+        o.c_amodc_gate(a["C"], a["atox"], a["c"])
+        assert bits_equal(o.get_state(), unhex_c128(a["state"])), (a["C"], a["atox"], a["c"])
+
+
+def test_inverse_qft_bit_identical(oracle_built):
+    for case in load_golden("inverse_qft.json")["cases"]:
+        o = oracle_built.Restatement(case["L"], case["M"])
+        o.set_state(unhex_c128(case["input"]))
+        o.inverse_QFT()
+        assert bits_equal(o.get_state(), unhex_c128(case["output"])), (case["L"], case["M"])
+
+
+def test_kat4_iqft_is_bit_reversed_dft(oracle_built):
+    """inverse_QFT == (R . F+) (x) I_{2^M}: F+[j,k] = e^{+2 pi i jk/2^L}/sqrt(2^L), R = bit reversal."""
+    L, M = 3, 2
+    n = L + M
+    rng = np.random.default_rng(4)
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    v /= np.linalg.norm(v)
+    o = oracle_built.Restatement(L, M)
+    o.set_state(v)
+    o.inverse_QFT()
+    got = o.get_state().reshape(1 << L, 1 << M)
+    F = np.exp(2j * np.pi * np.outer(np.arange(1 << L), np.arange(1 << L)) / (1 << L)) / math.sqrt(1 << L)
+    y = F @ v.reshape(1 << L, 1 << M)
+    rev = [int(format(j, f"0{L}b")[::-1], 2) for j in range(1 << L)]
+    want = np.empty_like(y)
+    for j in range(1 << L):
+        want[rev[j]] = y[j]
+    assert np.max(np.abs(got - want)) < 1e-15
+
+
+def test_scalar_helpers_against_reference_golden(oracle_built):
+    R = oracle_built.Restatement
+    g = load_golden("scalars.json")
+    for e in g["int_pow"]:
+        assert R.int_pow(e["base"], e["power"]) == e["value"], e
+    for e in g["gcd"]:
+        assert R.gcd(e["a"], e["b"]) == e["g"]
+    for e in g["read_omega"]:
+        assert R.read_omega(e["state"], e["L"], e["M"]).hex() == e["omega"]
+    for e in g["continued_fractions"]:
+        assert R.cf_denominators(float.fromhex(e["omega"]), 15) == e["den"], e
+
+
+def test_shor_runs_match_reference(oracle_built):
+    for run in load_golden("shor_runs.json")["runs"]:
+        o = oracle_built.Restatement(run["L"], run["M"])
+        err, factors = o.shors_algorithm(run["C"], run["a"], o.rng(run["seed"]), 0)
+        assert err == run["error"] and list(factors) == run["factors"], run
+
+
+def test_live_reference_agrees_on_random_circuits(oracle_built):
+    """Random gate sequences, restatement vs the compiled reference, bit for bit."""
+    if not oracle_built.have_reference():
+        pytest.skip("oracle/_ref/libqcref.so not built (no /root/reference here)")
+    rng = np.random.default_rng(2024)
+    for trial in range(6):
+        L, M = int(rng.integers(1, 5)), int(rng.integers(1, 4))
+        n = L + M
+        v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+        v /= np.linalg.norm(v)
+        ref, o = oracle_built.Reference(L, M), oracle_built.Restatement(L, M)
+        ref.set_state(v)
+        o.set_state(v)
+        for _ in range(12):
+            kind = int(rng.integers(0, 3))
+            if kind == 0:
+                q = int(rng.integers(0, n))
+                ref.hadamard_gate(q)
+                o.hadamard_gate(q)
+            elif kind == 1 and n >= 2:
+                c, q = (int(x) for x in rng.choice(n, size=2, replace=False))
+                th = float(rng.uniform(-math.pi, math.pi))
+                ref.c_phase_shift_gate(c, q, th)
+                o.c_phase_shift_gate(c, q, th)
+            else:
+                Cn = int(rng.integers(2, (1 << M) + 1))
+                atox = int(rng.integers(0, 1000))
+                c = int(rng.integers(M, n))
+                ref.c_amodc_gate(Cn, atox, c)
+                o.c_amodc_gate(Cn, atox, c)
+        assert bits_equal(ref.get_state(), o.get_state()), trial
+        r = float(rng.uniform())
+        assert ref.measure_state_r(r) == o.measure_state(r)
