@@ -165,7 +165,7 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->world = world;
     reg->p_global = p;
     reg->dist = nullptr;
-    reg->opt_fusion = 0;
+    reg->opt_fusion = 1;
     reg->opt_profile = 0;
     reg->opt_tile_bits = 0;
     reg->launches_total = 0;

@@ -1,0 +1,147 @@
+"""GPU parity tests of the fused tile sweeps (QCS_OPT_FUSION = 1) through the C ABI.
+
+Bar (north_star): amplitude L2 error <= 1e-12 relative to the reference's
+double-precision state; measured indices and factors identical."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_l2, unhex_c128
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def bitrev(k, bits):
+    out = 0
+    for b in range(bits):
+        if k >> b & 1:
+            out |= 1 << (bits - 1 - b)
+    return out
+
+
+def test_inverse_qft_matches_reference_golden(qcs):
+    for case in load_golden("inverse_qft.json")["cases"]:
+        for tile_bits in (0, 8, 9, 11, 13):
+            with qcs.Register(case["L"], case["M"]) as reg:
+                reg.set_option(qcs.OPT_TILE_BITS, tile_bits)
+                reg.set_state(unhex_c128(case["input"]))
+                reg.inverse_QFT()
+                err = rel_l2(reg.get_state(), unhex_c128(case["output"]))
+                assert err <= TOL, (case["L"], case["M"], tile_bits, err)
+
+
+@pytest.mark.parametrize("L,M,tile_bits", [(14, 0, 0), (14, 0, 8), (13, 3, 0), (16, 2, 10), (18, 0, 0),
+                                           (17, 1, 13), (20, 0, 11), (20, 0, 13), (12, 5, 9)])
+def test_inverse_qft_matches_oracle_with_strided_sweeps(qcs, oracle_built, L, M, tile_bits):
+    n = L + M
+    o = oracle_built.Restatement(L, M)
+    o.fill_synthetic(1234 + n)
+    o.scale(1.0 / math.sqrt(o.norm2()))
+    base = o.get_state().copy()
+    o.inverse_QFT()
+    with qcs.Register(L, M) as reg:
+        reg.set_option(qcs.OPT_TILE_BITS, tile_bits)
+        reg.set_state(base)
+        reg.inverse_QFT()
+        err = rel_l2(reg.get_state(), o.get_state())
+        assert err <= TOL, err
+
+
+@pytest.mark.parametrize("L,M,tile_bits", [(5, 2, 0), (10, 0, 8), (14, 1, 0), (16, 0, 9), (18, 0, 13)])
+def test_forward_qft_is_the_adjoint_circuit(qcs, L, M, tile_bits):
+    """fused forward QFT == gate-by-gate adjoint circuit (reverse order, -theta)."""
+    n = L + M
+    rng = np.random.default_rng(n)
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    v /= np.linalg.norm(v)
+    with qcs.Register(L, M) as a, qcs.Register(L, M) as b:
+        a.set_option(qcs.OPT_FUSION, 0)
+        b.set_option(qcs.OPT_TILE_BITS, tile_bits)
+        a.set_state(v)
+        b.set_state(v)
+        a.QFT()
+        b.QFT()
+        assert rel_l2(b.get_state(), a.get_state()) <= TOL
+        b.inverse_QFT()
+        assert rel_l2(b.get_state(), v) <= TOL
+
+
+def test_ranged_qft(qcs):
+    n = 15
+    rng = np.random.default_rng(5)
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    v /= np.linalg.norm(v)
+    with qcs.Register(n, 0) as a, qcs.Register(n, 0) as b:
+        a.set_option(qcs.OPT_FUSION, 0)
+        for (lo, hi) in [(3, 11), (0, 15), (13, 15), (6, 7)]:
+            a.set_state(v)
+            b.set_state(v)
+            a.inverse_QFT(lo, hi)
+            b.inverse_QFT(lo, hi)
+            assert rel_l2(b.get_state(), a.get_state()) <= TOL, (lo, hi)
+
+
+def test_shor_states_fused_match_reference_golden(qcs):
+    for case in load_golden("shor_states.json")["cases"]:
+        with qcs.Register(case["L"], case["M"]) as reg:
+            reg.reset_register()
+            reg.quantum_computation(case["C"], case["a"], qcs.POW_VERBATIM)
+            want = unhex_c128(case["state"])
+            got = reg.get_state()
+            assert rel_l2(got, want) <= TOL, case["C"]
+            for m in case["measured"]:
+                reg.set_state(got)
+                assert reg.measure_state(float.fromhex(m["r"])) == m["index"], (case["C"], m)
+
+
+def test_shor_full_size_n14_intended_power_mode(qcs, oracle_built):
+    """BASELINE configs[1] at full size: C=21, a=2, L=9, M=5 (n=14), modular powers."""
+    L, M, Cn, a = 9, 5, 21, 2
+    o = oracle_built.Restatement(L, M)
+    o.reset_register()
+    o.quantum_computation(Cn, a, 1)
+    want = o.get_state().copy()
+    with qcs.Register(L, M) as reg:
+        reg.reset_register()
+        reg.quantum_computation(Cn, a, qcs.POW_MODULAR)
+        got = reg.get_state()
+        assert rel_l2(got, want) <= TOL
+        g = o.rng(2021)
+        for _ in range(20):
+            r = g.uniform()
+            o.set_state(want)
+            reg.set_state(got)
+            assert reg.measure_state(r) == o.measure_state(r)
+
+
+def test_qft_closed_form_and_round_trip_at_scale(qcs):
+    """n = 27 (2 GiB): inverse_QFT |k> = e^{2 pi i jk/N}/sqrt(N) at bit-reversed j; QFT undoes it."""
+    n = 27
+    N = 1 << n
+    k = 0x2C0FFEE
+    with qcs.Register(n, 0) as reg:
+        reg.reset_register()                       # |0...01>
+        reg.set_state(np.array([0j, 0j]), first=0)
+        reg.set_state(np.array([1 + 0j]), first=k)
+        reg.inverse_QFT()
+        assert abs(reg.norm2() - 1.0) < 1e-12
+        for j in (0, 1, 2, 12345, 0x155555, N - 1, N // 2 + 77):
+            got = reg.get_state(bitrev(j, n), 1)[0]
+            want = np.exp(2j * math.pi * ((j * k) % N) / N) / math.sqrt(N)
+            assert abs(got - want) <= 1e-12 * abs(want), j
+        reg.QFT()
+        assert abs(reg.get_state(k, 1)[0] - 1.0) < 1e-12
+        assert abs(reg.norm2() - 1.0) < 1e-12
+
+
+def test_fused_sweep_count(qcs):
+    """n = 26: the whole 351-gate inverse QFT is a handful of kernel launches."""
+    with qcs.Register(26, 0) as reg:
+        reg.fill_synthetic(1)
+        reg.profile_reset()
+        reg.inverse_QFT()
+        reg.synchronize()
+        launches, _, by = reg.profile()["tile_sweep"]
+        assert 1 <= launches <= 5 and by == launches * 32.0 * (1 << 26)
