@@ -68,7 +68,14 @@ enum {
     QCS_OPT_PROFILE = 2,
     /* log2 of the shared-memory tile (amplitudes) used by the fused sweeps;
      * 0 = library default. */
-    QCS_OPT_TILE_BITS = 3
+    QCS_OPT_TILE_BITS = 3,
+    /* 1: measure_state always uses the single-CTA sequential scan; 0 (default):
+     * registers of >= 2^17 amplitudes use the parallel scan that reproduces the
+     * sequential rounding exactly (same index, see csrc/measure.cu). */
+    QCS_OPT_MEASURE_SEQUENTIAL = 4,
+    /* 1 (default): fused sweeps use the TMA + mbarrier pipelined kernel where it
+     * applies (tile = 2^11 amplitudes); 0: the direct global<->register kernel. */
+    QCS_OPT_PIPELINE = 5
 };
 
 /* kernel classes reported by qcs_profile_get */

@@ -168,6 +168,9 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->opt_fusion = 1;
     reg->opt_profile = 0;
     reg->opt_tile_bits = 0;
+    reg->opt_measure_sequential = 0;
+    reg->opt_pipeline = 1;
+    reg->d_meas = nullptr;
     reg->launches_total = 0;
     memset(reg->launches, 0, sizeof reg->launches);
     memset(reg->alg_bytes, 0, sizeof reg->alg_bytes);
@@ -232,6 +235,7 @@ extern "C" void qcs_register_destroy(qcs_register *reg)
     if (reg->amp) cudaFree(reg->amp);
     if (reg->d_partials) cudaFree(reg->d_partials);
     if (reg->d_small) cudaFree(reg->d_small);
+    if (reg->d_meas) cudaFree(reg->d_meas);
     if (reg->h_small) cudaFreeHost(reg->h_small);
     if (reg->stream) cudaStreamDestroy(reg->stream);
     delete reg;
@@ -258,6 +262,8 @@ extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
             if (value != 0 && (value < 8 || value > 13)) return QCS_BAD_ARGUMENTS;
             reg->opt_tile_bits = (int) value;
             return QCS_NO_ERROR;
+        case QCS_OPT_MEASURE_SEQUENTIAL: reg->opt_measure_sequential = value != 0; return QCS_NO_ERROR;
+        case QCS_OPT_PIPELINE: reg->opt_pipeline = value != 0; return QCS_NO_ERROR;
         default: return QCS_BAD_ARGUMENTS;
     }
 }
@@ -269,6 +275,8 @@ extern "C" long long qcs_get_option(const qcs_register *reg, int option)
         case QCS_OPT_FUSION: return reg->opt_fusion;
         case QCS_OPT_PROFILE: return reg->opt_profile;
         case QCS_OPT_TILE_BITS: return reg->opt_tile_bits;
+        case QCS_OPT_MEASURE_SEQUENTIAL: return reg->opt_measure_sequential;
+        case QCS_OPT_PIPELINE: return reg->opt_pipeline;
         default: return -1;
     }
 }

@@ -125,6 +125,316 @@ k_measure_scan(const double2 *__restrict__ amp, uint64_t limit, double cum_in, d
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Exact parallel emulation of the sequential scan (large registers).
+//
+// s_{i+1} = RN(s_i + p_i) with p_i >= 0.  While s stays inside one binade
+// [2^e, 2^(e+1)) it is an integer multiple a of ulp = 2^(e-52), and
+// RN(s + p) = (a + RNint(p / ulp)) ulp, where the round-to-nearest-even tie
+// break depends only on the parity of a.  One element is therefore the map
+//     a -> a + (a even ? de : do)
+// and such maps compose associatively, so whole chunks (and runs of chunks)
+// collapse into one (de, do) pair computed in parallel.
+//
+//  pass 1  per-chunk approximate sums (any order; only used for bounds)
+//  pass 2  prefix of those sums; a chunk is CLEAN(e) when rigorous error
+//          bounds (relative margin delta >= 4 N 2^-53) prove that the exact
+//          sequential sum stays inside binade e throughout the chunk AND stays
+//          below r; ZERO when all its p are 0; otherwise SEQ
+//  pass 3  (de, do) of every CLEAN chunk, then of every uniform super-chunk
+//  pass 4  one CTA walks the summaries in index order carrying the exact s;
+//          SEQ chunks (binade crossings, the neighbourhood of r) are added
+//          element by element with the `>=` test of qc_shor.c:289
+//
+// The result is the index the reference's loop (qc_shor.c:283-292) returns.
+// ---------------------------------------------------------------------------
+constexpr int kChunkBits = 12;
+constexpr int kChunk = 1 << kChunkBits;
+constexpr int kSuperBits = 8;
+constexpr int kSuper = 1 << kSuperBits;
+constexpr int kWalkBlock = 512;                  // summaries staged per round of the walk (>= kSuper)
+constexpr int kCodeSeq = -1, kCodeZero = -2;     // otherwise: binade exponent + 2000
+
+struct pair64 { long long de, od; };
+
+__device__ __forceinline__ pair64 compose(pair64 f1, pair64 f2)
+{
+    pair64 r;
+    r.de = f1.de + ((f1.de & 1) ? f2.od : f2.de);
+    r.od = f1.od + (((1 + f1.od) & 1) ? f2.od : f2.de);
+    return r;
+}
+
+// the map of one addend p inside binade e
+__device__ __forceinline__ pair64 element_map(double p, int e)
+{
+    const unsigned long long bits = (unsigned long long) __double_as_longlong(p);
+    const int ef = (int) ((bits >> 52) & 0x7ff);
+    unsigned long long m = bits & 0xfffffffffffffull;
+    int ep;
+    if (ef == 0) ep = -1022; else { m |= 1ull << 52; ep = ef - 1023; }
+    pair64 r;
+    const int shift = e - ep;                    // p / ulp = m * 2^-shift
+    if (m == 0 || shift >= 55) { r.de = r.od = 0; return r; }
+    if (shift <= 0) {                            // cannot happen in a CLEAN chunk; keep it exact anyway
+        const long long k = (long long) (m << (-shift > 10 ? 10 : -shift));
+        r.de = r.od = k;
+        return r;
+    }
+    const unsigned long long k = shift >= 64 ? 0ull : (m >> shift);
+    const unsigned long long rem = m & ((1ull << shift) - 1ull);
+    const unsigned long long half = 1ull << (shift - 1);
+    if (rem < half) { r.de = r.od = (long long) k; }
+    else if (rem > half) { r.de = r.od = (long long) k + 1; }
+    else { r.de = (long long) (k + (k & 1ull)); r.od = (long long) (k + 1ull - (k & 1ull)); }
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_chunk_sums(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks, double *__restrict__ csum)
+{
+    __shared__ double warp_part[8];
+    for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const uint64_t base = c << kChunkBits;
+        double s = 0.0;
+#pragma unroll 4
+        for (int u = 0; u < kChunk / 256; u++) {
+            const uint64_t i = base + (uint64_t) u * 256 + threadIdx.x;
+            if (i < limit) s += abs2_ref(amp[i]);
+        }
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double v = threadIdx.x < 8 ? warp_part[threadIdx.x] : 0.0;
+            v = warp_sum(v);
+            if (threadIdx.x == 0) csum[c] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// single CTA: exclusive prefix over chunk sums + classification
+__global__ void __launch_bounds__(1024)
+k_classify(const double *__restrict__ csum, uint64_t n_chunks, double cum_in, double r, double delta,
+           int *__restrict__ code, int *__restrict__ super_code)
+{
+    __shared__ double warp_tot[32];
+    __shared__ double carry_s;
+    if (threadIdx.x == 0) carry_s = cum_in;
+    __syncthreads();
+    for (uint64_t seg = 0; seg < n_chunks; seg += 1024) {
+        const uint64_t c = seg + threadIdx.x;
+        const double v = c < n_chunks ? csum[c] : 0.0;
+        // inclusive warp scan
+        double x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+        __syncthreads();
+        double before = carry_s;
+        for (int w = 0; w < (int) (threadIdx.x >> 5); w++) before += warp_tot[w];
+        const double P = before + (x - v);          // approximate sum before the chunk
+        if (c < n_chunks) {
+            int cd = kCodeSeq;
+            const double lo = P * (1.0 - delta), hi = (P + v) * (1.0 + delta);
+            if (v == 0.0) cd = kCodeZero;
+            else if (hi < r && lo > 0.0) {
+                int e;
+                frexp(lo, &e);                       // lo = f * 2^e, f in [0.5, 1)  ->  binade e-1
+                e -= 1;
+                if (hi < ldexp(1.0, e + 1) && e > -1000) cd = e + 2000;
+            }
+            code[c] = cd;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = before + x;
+        __syncthreads();
+    }
+    // super-chunks: uniform when every chunk is ZERO or CLEAN with one common binade
+    const uint64_t n_super = (n_chunks + kSuper - 1) >> kSuperBits;
+    for (uint64_t sc = threadIdx.x; sc < n_super; sc += 1024) {
+        int common = kCodeZero;
+        bool ok = true;
+        const uint64_t end = ((sc + 1) << kSuperBits) < n_chunks ? ((sc + 1) << kSuperBits) : n_chunks;
+        for (uint64_t c = sc << kSuperBits; c < end && ok; c++) {
+            const int cd = code[c];
+            if (cd == kCodeSeq) ok = false;
+            else if (cd != kCodeZero) {
+                if (common == kCodeZero) common = cd;
+                else if (common != cd) ok = false;
+            }
+        }
+        super_code[sc] = ok ? common : kCodeSeq;
+    }
+}
+
+// (de, do) of every CLEAN chunk: 128 threads, each composes 32 consecutive
+// elements from shared memory, then an ordered tree over the threads
+__global__ void __launch_bounds__(128)
+k_chunk_maps(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks, const int *__restrict__ code,
+             pair64 *__restrict__ maps)
+{
+    __shared__ double p[kChunk + kChunk / 32];
+    __shared__ pair64 warp_map[4];
+    for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const int cd = code[c];
+        if (cd < 0) continue;
+        const int e = cd - 2000;
+        const uint64_t base = c << kChunkBits;
+        for (int u = 0; u < kChunk / 128; u++) {
+            const int i = u * 128 + threadIdx.x;
+            p[i + (i >> 5)] = base + i < limit ? abs2_ref(amp[base + i]) : 0.0;
+        }
+        __syncthreads();
+        pair64 f = {0, 0};
+        for (int k = 0; k < 32; k++) f = compose(f, element_map(p[threadIdx.x * 33 + k], e));
+        // ordered reduction: lane 0 ends with the composition of lanes 0..31 in order
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            pair64 g;
+            g.de = __shfl_down_sync(0xffffffffu, f.de, o);
+            g.od = __shfl_down_sync(0xffffffffu, f.od, o);
+            if ((threadIdx.x & 31) + o < 32 && ((threadIdx.x & 31) & (2 * o - 1)) == 0) f = compose(f, g);
+        }
+        if ((threadIdx.x & 31) == 0) warp_map[threadIdx.x >> 5] = f;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            maps[c] = compose(compose(warp_map[0], warp_map[1]), compose(warp_map[2], warp_map[3]));
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_super_maps(uint64_t n_chunks, uint64_t n_super, const int *__restrict__ code, const int *__restrict__ super_code,
+             const pair64 *__restrict__ maps, pair64 *__restrict__ super_maps)
+{
+    const uint64_t sc = (uint64_t) blockIdx.x * 256 + threadIdx.x;
+    if (sc >= n_super || super_code[sc] < 0) return;
+    pair64 f = {0, 0};
+    const uint64_t end = ((sc + 1) << kSuperBits) < n_chunks ? ((sc + 1) << kSuperBits) : n_chunks;
+    for (uint64_t c = sc << kSuperBits; c < end; c++)
+        if (code[c] >= 0) f = compose(f, maps[c]);
+    super_maps[sc] = f;
+}
+
+struct walk_result {
+    double cum;
+    unsigned long long index;
+    int found;
+    int bad;           // an invariant failed: caller falls back to the plain sequential scan
+};
+
+// apply a (de, do) map valid in binade e to the exact running sum
+__device__ __forceinline__ bool apply_map(double &s, pair64 f, int e)
+{
+    const double a_d = ldexp(s, 52 - e);
+    if (!(a_d >= 4503599627370496.0 && a_d < 9007199254740992.0)) return false;
+    const long long a = (long long) a_d;
+    const long long a2 = a + ((a & 1) ? f.od : f.de);
+    if (a2 >= 9007199254740992ll) return false;
+    s = ldexp((double) a2, e - 52);
+    return true;
+}
+
+__global__ void __launch_bounds__(1024)
+k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks, double cum_in, double r,
+             const int *__restrict__ code, const int *__restrict__ super_code, const pair64 *__restrict__ maps,
+             const pair64 *__restrict__ super_maps, walk_result *__restrict__ out)
+{
+    __shared__ double p[kChunk];
+    __shared__ int s_code[kWalkBlock];
+    __shared__ pair64 s_map[kWalkBlock];
+    __shared__ long long req;          // index requested by thread 0 (-1: none)
+    __shared__ int s_found, s_bad;
+    const uint64_t n_super = (n_chunks + kSuper - 1) >> kSuperBits;
+    double s = cum_in;
+    uint64_t hit = 0;
+    if (threadIdx.x == 0) { s_found = 0; s_bad = 0; req = -1; }
+    __syncthreads();
+
+    for (uint64_t sb = 0; sb < n_super && !s_found && !s_bad; sb += kWalkBlock) {
+        const uint64_t sb_end = sb + kWalkBlock < n_super ? sb + kWalkBlock : n_super;
+        uint64_t sc_next = sb;
+        while (sc_next < sb_end && !s_found && !s_bad) {
+            // stage the super-chunk summaries [sc_next, sb_end)
+            __syncthreads();
+            if (threadIdx.x < kWalkBlock && sc_next + threadIdx.x < sb_end) {
+                s_code[threadIdx.x] = super_code[sc_next + threadIdx.x];
+                s_map[threadIdx.x] = s_code[threadIdx.x] >= 0 ? super_maps[sc_next + threadIdx.x] : pair64{0, 0};
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                req = -1;
+                uint64_t sc = sc_next;
+                for (; sc < sb_end; sc++) {
+                    const int cd = s_code[sc - sc_next];
+                    if (cd == kCodeZero) continue;
+                    if (cd == kCodeSeq) { req = (long long) sc; break; }
+                    if (!apply_map(s, s_map[sc - sc_next], cd - 2000)) { s_bad = 1; break; }
+                }
+            }
+            __syncthreads();
+            if (s_bad) break;
+            if (req < 0) { sc_next = sb_end; break; }
+            const uint64_t sc = (uint64_t) req;
+            // walk the chunks of the non-uniform super-chunk sc
+            const uint64_t c_begin = sc << kSuperBits;
+            const uint64_t c_end = c_begin + kSuper < n_chunks ? c_begin + kSuper : n_chunks;
+            __syncthreads();
+            if (threadIdx.x < kWalkBlock && c_begin + threadIdx.x < c_end) {
+                s_code[threadIdx.x] = code[c_begin + threadIdx.x];
+                s_map[threadIdx.x] = s_code[threadIdx.x] >= 0 ? maps[c_begin + threadIdx.x] : pair64{0, 0};
+            }
+            __syncthreads();
+            uint64_t c_next = c_begin;
+            while (c_next < c_end && !s_found && !s_bad) {
+                if (threadIdx.x == 0) {
+                    req = -1;
+                    uint64_t c = c_next;
+                    for (; c < c_end; c++) {
+                        const int cd = s_code[c - c_begin];
+                        if (cd == kCodeZero) continue;
+                        if (cd == kCodeSeq) { req = (long long) c; break; }
+                        if (!apply_map(s, s_map[c - c_begin], cd - 2000)) { s_bad = 1; break; }
+                    }
+                }
+                __syncthreads();
+                if (s_bad || req < 0) break;
+                const uint64_t c = (uint64_t) req;
+                const uint64_t base = c << kChunkBits;
+#pragma unroll
+                for (int u = 0; u < kChunk / 1024; u++) {
+                    const uint64_t i = base + (uint64_t) u * 1024 + threadIdx.x;
+                    p[u * 1024 + threadIdx.x] = i < limit ? abs2_ref(amp[i]) : 0.0;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const uint64_t len = limit - base < (uint64_t) kChunk ? limit - base : (uint64_t) kChunk;
+                    for (uint64_t j = 0; j < len; j++) {
+                        s = __dadd_rn(s, p[j]);                 // qc_shor.c:286
+                        if (s >= r) { hit = base + j; s_found = 1; break; }   // qc_shor.c:289
+                    }
+                }
+                __syncthreads();
+                c_next = c + 1;
+            }
+            sc_next = sc + 1;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out->cum = s;
+        out->index = hit;
+        out->found = s_found;
+        out->bad = s_bad;
+    }
+}
+
 }  // namespace
 
 int qcs_k_norm2_local(qcs_register *reg, double *out_host)
@@ -147,8 +457,8 @@ int qcs_k_norm2_local(qcs_register *reg, double *out_host)
     return QCS_NO_ERROR;
 }
 
-int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limit,
-                       int *found, uint64_t *index, double *cum_out)
+static int measure_scan_sequential(qcs_register *reg, double cum_in, double r, uint64_t limit,
+                                   int *found, uint64_t *index, double *cum_out)
 {
     scan_result *d_res = (scan_result *) reg->d_small;
     qcs_launch_begin(reg, QCS_K_REDUCE, 16.0 * (double) limit);
@@ -157,6 +467,69 @@ int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limi
     QCS_CUDA(cudaMemcpyAsync(reg->h_small, d_res, sizeof(scan_result), cudaMemcpyDeviceToHost, reg->stream));
     QCS_CUDA(cudaStreamSynchronize(reg->stream));
     const scan_result *h = (const scan_result *) reg->h_small;
+    *found = h->found;
+    *index = h->index;
+    *cum_out = h->cum;
+    return QCS_NO_ERROR;
+}
+
+int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limit,
+                       int *found, uint64_t *index, double *cum_out)
+{
+    // small registers: the plain sequential scan is already fast
+    if (limit < (1ull << 17) || reg->opt_measure_sequential)
+        return measure_scan_sequential(reg, cum_in, r, limit, found, index, cum_out);
+
+    const uint64_t n_chunks = (limit + kChunk - 1) >> kChunkBits;
+    const uint64_t n_super = (n_chunks + kSuper - 1) >> kSuperBits;
+    if (!reg->d_meas) {
+        const uint64_t cap_chunks = (reg->N_local + kChunk - 1) >> kChunkBits;
+        const uint64_t cap_super = (cap_chunks + kSuper - 1) >> kSuperBits;
+        const size_t bytes = cap_chunks * (sizeof(double) + sizeof(int) + sizeof(pair64)) +
+                             cap_super * (sizeof(int) + sizeof(pair64)) + 64;
+        QCS_CUDA(cudaMalloc(&reg->d_meas, bytes));
+    }
+    const uint64_t cap_chunks = (reg->N_local + kChunk - 1) >> kChunkBits;
+    const uint64_t cap_super = (cap_chunks + kSuper - 1) >> kSuperBits;
+    unsigned char *at = (unsigned char *) reg->d_meas;
+    pair64 *maps = (pair64 *) at;            at += cap_chunks * sizeof(pair64);
+    pair64 *super_maps = (pair64 *) at;      at += cap_super * sizeof(pair64);
+    double *csum = (double *) at;            at += cap_chunks * sizeof(double);
+    int *code = (int *) at;                  at += cap_chunks * sizeof(int);
+    int *super_code = (int *) at;
+
+    // rigorous relative margin: |sequential - exact| <= (N-1) u and the same for
+    // the tree sums, u = 2^-53; 2^(n+3-53) covers both with slack
+    const double delta = ldexp(1.0, (int) reg->n + 3 - 53);
+    uint64_t grid = n_chunks;
+    const uint64_t cap = (uint64_t) reg->sm_count * 8;
+    if (grid > cap) grid = cap;
+
+    qcs_launch_begin(reg, QCS_K_REDUCE, 16.0 * (double) limit);
+    k_chunk_sums<<<(unsigned) grid, 256, 0, reg->stream>>>(reg->amp, limit, n_chunks, csum);
+    QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_chunk_sums"));
+    qcs_launch_begin(reg, QCS_K_REDUCE, 12.0 * (double) n_chunks);
+    k_classify<<<1, 1024, 0, reg->stream>>>(csum, n_chunks, cum_in, r, delta, code, super_code);
+    QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_classify"));
+    qcs_launch_begin(reg, QCS_K_REDUCE, 16.0 * (double) limit * (r < 1.0 ? (r > 0.0 ? r : 0.0) : 1.0));
+    k_chunk_maps<<<(unsigned) grid, 128, 0, reg->stream>>>(reg->amp, limit, n_chunks, code, maps);
+    QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_chunk_maps"));
+    qcs_launch_begin(reg, QCS_K_REDUCE, 20.0 * (double) n_chunks);
+    k_super_maps<<<(unsigned) ((n_super + 255) / 256), 256, 0, reg->stream>>>(n_chunks, n_super, code, super_code,
+                                                                              maps, super_maps);
+    QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_super_maps"));
+    walk_result *d_res = (walk_result *) reg->d_small;
+    qcs_launch_begin(reg, QCS_K_REDUCE, 20.0 * (double) n_super);
+    k_exact_walk<<<1, 1024, 0, reg->stream>>>(reg->amp, limit, n_chunks, cum_in, r, code, super_code, maps,
+                                              super_maps, d_res);
+    QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_exact_walk"));
+    QCS_CUDA(cudaMemcpyAsync(reg->h_small, d_res, sizeof(walk_result), cudaMemcpyDeviceToHost, reg->stream));
+    QCS_CUDA(cudaStreamSynchronize(reg->stream));
+    const walk_result *h = (const walk_result *) reg->h_small;
+    if (h->bad) {
+        fprintf(stderr, "qcs: measure_state: binade invariant failed, falling back to the sequential GPU scan\n");
+        return measure_scan_sequential(reg, cum_in, r, limit, found, index, cum_out);
+    }
     *found = h->found;
     *index = h->index;
     *cum_out = h->cum;

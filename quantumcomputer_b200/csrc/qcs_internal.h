@@ -34,11 +34,14 @@ struct qcs_register {
     size_t partials_cap;    // in doubles
     void *d_small;          // 4 KiB device scratch (measurement result etc.)
     void *h_small;          // 4 KiB pinned host mirror
+    void *d_meas;           // chunk summaries of the exact parallel measurement scan (lazy)
 
     // options
     int opt_fusion;
     int opt_profile;
     int opt_tile_bits;
+    int opt_pipeline;             // 1: TMA/mbarrier pipelined sweep kernel where it applies
+    int opt_measure_sequential;   // 1: always use the single-CTA sequential scan
 
     // accounting
     unsigned long long launches_total;

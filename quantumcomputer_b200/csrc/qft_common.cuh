@@ -1,0 +1,354 @@
+// qft_common.cuh -- pieces shared by the two fused-QFT sweep kernels
+// (qft_fused.cu: direct global<->register kernel; qft_pipeline.cu: TMA +
+// mbarrier pipelined kernel): the sweep descriptor, the register butterfly
+// networks, the external-twiddle power tree and the host-side sweep planner.
+#pragma once
+
+#include "qcs_internal.h"
+
+#include <algorithm>
+#include <math.h>
+#include <vector>
+
+namespace qft {
+
+
+constexpr int kMaxSteps = 5;
+
+struct sweep_step {
+    int s;          // tile-local position of the lowest bit of the step
+    int r;          // number of stages in the step (radix 2^r)
+    int j;          // stage index of the step's top bit (physical bit - lo)
+    int low_phys;   // physical position of the step's lowest bit
+    int col_off;    // offset of the step's column-twiddle table (in double2)
+};
+
+struct sweep_desc {
+    int a, g_lo, g_hi, t;   // tile = physical bits [0,a) U [g_lo,g_hi); t = a + g_hi - g_lo
+    int lo;                 // lowest qubit of the transform (the reference's M_size)
+    int n_steps;
+    int sw;                 // swizzle: phys(e) = e ^ ((e >> sw) & 7)
+    int inverse;            // 1: inverse_QFT of the reference, 0: its adjoint
+    int wcol_total;         // total column-twiddle entries
+    double scale;           // (1/sqrt 2)^(stages in this sweep), applied in the last step
+    sweep_step step[kMaxSteps];
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b)
+{
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 csqr(double2 a)
+{
+    return make_double2(a.x * a.x - a.y * a.y, 2.0 * a.x * a.y);
+}
+
+// v * exp(+i pi q / 8) (INV) or v * exp(-i pi q / 8) (!INV); q is a compile-time
+// constant after unrolling
+template <bool INV>
+__device__ __forceinline__ double2 rot8(double2 v, int q)
+{
+    const double H = 0.70710678118654752440, C1 = 0.92387953251128673848, S1 = 0.38268343236508977173;
+    double c, s;
+    switch (q) {
+        case 0: return v;
+        case 4: return INV ? make_double2(-v.y, v.x) : make_double2(v.y, -v.x);
+        case 2: return INV ? make_double2(H * (v.x - v.y), H * (v.x + v.y))
+                           : make_double2(H * (v.x + v.y), H * (v.y - v.x));
+        case 6: return INV ? make_double2(-H * (v.x + v.y), H * (v.x - v.y))
+                           : make_double2(H * (v.y - v.x), -H * (v.x + v.y));
+        case 1: c = C1; s = S1; break;
+        case 3: c = S1; s = C1; break;
+        case 5: c = -S1; s = C1; break;
+        default: c = -C1; s = S1; break;
+    }
+    if (!INV) s = -s;
+    return make_double2(v.x * c - v.y * s, v.x * s + v.y * c);
+}
+
+// r stages of the reference circuit on R = 2^r register-resident amplitudes,
+// x[d] = amplitude whose step digit is d (top stage bit = MSB of d).
+// Decimation in frequency, positive exponent, unscaled: afterwards x[d] holds
+// frequency bitrev(d).
+template <int R>
+__device__ __forceinline__ void dif_inverse(double2 (&x)[R])
+{
+#pragma unroll
+    for (int span = R / 2; span >= 1; span >>= 1) {
+#pragma unroll
+        for (int start = 0; start < R; start += 2 * span) {
+#pragma unroll
+            for (int m = 0; m < span; m++) {
+                const double2 u = x[start + m], v = x[start + m + span];
+                x[start + m] = make_double2(u.x + v.x, u.y + v.y);
+                x[start + m + span] = rot8<true>(make_double2(u.x - v.x, u.y - v.y), m * (8 / span));
+            }
+        }
+    }
+}
+
+// the adjoint network: decimation in time, negative exponent
+template <int R>
+__device__ __forceinline__ void dit_forward(double2 (&x)[R])
+{
+#pragma unroll
+    for (int span = 1; span <= R / 2; span <<= 1) {
+#pragma unroll
+        for (int start = 0; start < R; start += 2 * span) {
+#pragma unroll
+            for (int m = 0; m < span; m++) {
+                const double2 u = x[start + m];
+                const double2 v = rot8<false>(x[start + m + span], m * (8 / span));
+                x[start + m] = make_double2(u.x + v.x, u.y + v.y);
+                x[start + m + span] = make_double2(u.x - v.x, u.y - v.y);
+            }
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ constexpr int bitrev(int k)
+{
+    int out = 0;
+    for (int b = 1, o = R >> 1; b < R; b <<= 1, o >>= 1)
+        if (k & b) out |= o;
+    return out;
+}
+
+// x[d] *= w^bitrev(d)
+template <int R>
+__device__ __forceinline__ void external_twiddle(double2 (&x)[R], double2 w)
+{
+    double2 p[R];
+    p[1] = w;
+#pragma unroll
+    for (int k = 2; k < R; k++) p[k] = (k & 1) ? cmul(p[k - 1], w) : csqr(p[k >> 1]);
+#pragma unroll
+    for (int k = 1; k < R; k++) x[bitrev<R>(k)] = cmul(x[bitrev<R>(k)], p[k]);
+}
+
+__device__ __forceinline__ double2 ld256_lo(const double2 *p, double2 &hi)
+{
+    double a, b, c, d;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+    hi = make_double2(c, d);
+    return make_double2(a, b);
+}
+__device__ __forceinline__ void st256(double2 *p, double2 lo, double2 hi)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(lo.x), "d"(lo.y), "d"(hi.x), "d"(hi.y) : "memory");
+}
+
+struct tile_geom {
+    int a, g_lo, sw;
+    __device__ __forceinline__ uint64_t spread(unsigned e) const
+    {
+        return (uint64_t) (e & ((1u << a) - 1u)) | ((uint64_t) (e >> a) << g_lo);
+    }
+    __device__ __forceinline__ int phys(int s) const { return s < a ? s : g_lo + (s - a); }
+    __device__ __forceinline__ unsigned swz(unsigned e) const { return e ^ ((e >> sw) & 7u); }
+};
+
+template <int R, bool INV>
+__device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__restrict__ tile,
+                                         const double2 *__restrict__ wcol, double2 wb, const tile_geom G,
+                                         const sweep_step S, int t, uint64_t base, bool from_global,
+                                         bool to_global, bool apply_scale, double scale,
+                                         unsigned tid, unsigned nthreads)
+{
+    const unsigned n_cols = 1u << (t - S.r);
+    const unsigned low_mask = (1u << S.s) - 1u;
+    for (unsigned c = tid; c < n_cols; c += nthreads) {
+        const unsigned e_base = ((c >> S.s) << (S.s + S.r)) | (c & low_mask);
+        double2 *g = amp + base + G.spread(e_base);
+        const uint64_t g_stride = 1ull << G.phys(S.s);
+        double2 x[R];
+        if (from_global) {
+            if (S.s == 0 && R >= 2) {
+#pragma unroll
+                for (int d = 0; d < R; d += 2) x[d] = ld256_lo(g + d, x[d + 1]);
+            } else {
+#pragma unroll
+                for (int d = 0; d < R; d++) x[d] = g[(uint64_t) d * g_stride];
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < R; d++) x[d] = tile[G.swz(e_base + ((unsigned) d << S.s))];
+        }
+        const double2 w = cmul(wb, wcol[c]);
+        if (INV) {
+            dif_inverse<R>(x);
+            external_twiddle<R>(x, w);
+        } else {
+            external_twiddle<R>(x, w);
+            dit_forward<R>(x);
+        }
+        if (apply_scale) {
+#pragma unroll
+            for (int d = 0; d < R; d++) { x[d].x *= scale; x[d].y *= scale; }
+        }
+        if (to_global) {
+            if (S.s == 0 && R >= 2) {
+#pragma unroll
+                for (int d = 0; d < R; d += 2) st256(g + d, x[d], x[d + 1]);
+            } else {
+#pragma unroll
+                for (int d = 0; d < R; d++) g[(uint64_t) d * g_stride] = x[d];
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < R; d++) tile[G.swz(e_base + ((unsigned) d << S.s))] = x[d];
+        }
+    }
+}
+
+template <bool INV>
+__device__ __forceinline__ void dispatch_step(double2 *amp, double2 *tile, const double2 *wcol, double2 wb,
+                                              const tile_geom G, const sweep_step S, int t, uint64_t base,
+                                              bool from_global, bool to_global, bool apply_scale, double scale,
+                                              unsigned tid, unsigned nthreads)
+{
+    switch (S.r) {
+        case 4: run_step<16, INV>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
+        case 3: run_step<8, INV>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
+        case 2: run_step<4, INV>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
+        default: run_step<2, INV>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
+    }
+}
+
+// exp(sign * i pi y / 2^j)
+__device__ __forceinline__ double2 unit_phase(uint64_t y, int j, bool positive)
+{
+    double s, c;
+    sincospi(ldexp((double) y, -j), &s, &c);
+    return make_double2(c, positive ? s : -s);
+}
+
+// ---------------------------------------------------------------------------
+// host-side planning
+// ---------------------------------------------------------------------------
+struct sweep_plan {
+    sweep_desc d;
+    uint64_t n_tiles;
+    int stages;
+};
+
+// pick the XOR-swizzle shift that minimises shared-memory bank conflicts over
+// every shared-memory access pattern of the sweep (quarter-warp = 8 lanes must
+// hit 8 distinct 16-byte bank groups)
+// worst-case serialisation (extra wavefronts) of the shared-memory accesses of a
+// sweep under the XOR swizzle `sw`; all_steps: every step reads and writes smem
+inline long conflict_cost(const sweep_desc &d, int sw, bool all_steps)
+{
+    long cost = 0;
+    for (int k = 0; k < d.n_steps; k++) {
+        const sweep_step &S = d.step[k];
+        const bool reads = all_steps || k > 0, writes = all_steps || k < d.n_steps - 1;
+        if (!reads && !writes) continue;
+        const unsigned n_cols = 1u << (d.t - S.r);
+        const unsigned lanes = n_cols < 8 ? n_cols : 8;
+        for (unsigned c0 = 0; c0 < n_cols && c0 < 64; c0 += 8) {
+            for (int dd = 0; dd < (1 << S.r); dd++) {
+                int seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                int worst = 0;
+                for (unsigned ln = 0; ln < lanes; ln++) {
+                    const unsigned c = c0 + ln;
+                    const unsigned e = (((c >> S.s) << (S.s + S.r)) | (c & ((1u << S.s) - 1u))) + ((unsigned) dd << S.s);
+                    const unsigned ph = e ^ ((e >> sw) & 7u);
+                    worst = std::max(worst, ++seen[ph & 7u]);
+                }
+                cost += (worst - 1) * ((reads ? 1 : 0) + (writes ? 1 : 0));
+            }
+        }
+    }
+    return cost;
+}
+
+inline int choose_swizzle(const sweep_desc &d)
+{
+    int best_sw = 4;
+    long best_cost = -1;
+    for (int sw = 3; sw <= 9; sw++) {
+        const long cost = conflict_cost(d, sw, false);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_sw = sw; }
+    }
+    return best_sw;
+}
+
+inline void split_even(int total, int cap, std::vector<int> &out)
+{
+    out.clear();
+    if (total <= 0) return;
+    const int m = (total + cap - 1) / cap;
+    for (int i = 0; i < m; i++) out.push_back(total / m + (i < total % m ? 1 : 0));
+}
+
+// sweeps of the inverse transform on qubits [lo, hi), top stages first
+inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int a_req, std::vector<sweep_plan> &plans)
+{
+    plans.clear();
+    const int t = std::min<int>(T, (int) n_local);
+    const int a = (int) n_local <= t ? t : std::min(a_req, t - 1);
+    int top = (int) hi;
+    std::vector<int> sizes;
+    const int first_hi = std::max<int>((int) lo, t);
+    if ((int) n_local > t) split_even(top - first_hi, t - a, sizes);
+    struct raw { int a, g_lo, g_hi, s_lo, s_hi; };
+    std::vector<raw> raws;
+    for (int g : sizes) {
+        raws.push_back({t - g, top - g, top, top - g, top});     // low run widened so the tile has exactly t bits
+        top -= g;
+    }
+    if (top > (int) lo) raws.push_back({t, t, t, (int) lo, top});
+    for (const raw &rw : raws) {
+        sweep_plan p;
+        sweep_desc &d = p.d;
+        d.a = rw.a;
+        d.g_lo = rw.g_lo;
+        d.g_hi = rw.g_hi;
+        d.t = rw.a + (rw.g_hi - rw.g_lo);
+        d.lo = (int) lo;
+        d.inverse = 1;
+        p.stages = rw.s_hi - rw.s_lo;
+        d.scale = pow(0.70710678118654752440, (double) p.stages);
+        if (p.stages % 2 == 0) d.scale = ldexp(1.0, -p.stages / 2);      // exact power of two
+        std::vector<int> rs;
+        split_even(p.stages, 4, rs);
+        d.n_steps = (int) rs.size();
+        int l = rw.s_hi, off = 0;
+        for (int k = 0; k < d.n_steps; k++) {
+            sweep_step &S = d.step[k];
+            S.r = rs[(size_t) k];
+            S.low_phys = l - S.r;
+            S.s = S.low_phys < d.a ? S.low_phys : d.a + (S.low_phys - d.g_lo);
+            S.j = (l - 1) - (int) lo;
+            S.col_off = off;
+            off += 1 << (d.t - S.r);
+            l -= S.r;
+        }
+        d.wcol_total = off;
+        d.sw = choose_swizzle(d);
+        p.n_tiles = 1ull << (n_local - (unsigned) d.t);
+        plans.push_back(p);
+    }
+}
+
+
+// turn an inverse plan into the plan of the adjoint circuit: sweeps and steps in
+// reverse order, conjugated twiddles
+inline void make_forward(std::vector<sweep_plan> &plans)
+{
+    std::reverse(plans.begin(), plans.end());
+    for (sweep_plan &p : plans) {
+        p.d.inverse = 0;
+        std::reverse(p.d.step, p.d.step + p.d.n_steps);
+        int off = 0;
+        for (int k = 0; k < p.d.n_steps; k++) {
+            p.d.step[k].col_off = off;
+            off += 1 << (p.d.t - p.d.step[k].r);
+        }
+        p.d.sw = choose_swizzle(p.d);
+    }
+}
+
+}  // namespace qft

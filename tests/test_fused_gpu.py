@@ -35,6 +35,16 @@ def test_inverse_qft_matches_reference_golden(qcs):
 @pytest.mark.parametrize("L,M,tile_bits", [(14, 0, 0), (14, 0, 8), (13, 3, 0), (16, 2, 10), (18, 0, 0),
                                            (17, 1, 13), (20, 0, 11), (20, 0, 13), (12, 5, 9)])
 def test_inverse_qft_matches_oracle_with_strided_sweeps(qcs, oracle_built, L, M, tile_bits):
+    _check_iqft_vs_oracle(qcs, oracle_built, L, M, tile_bits, pipeline=1)
+
+
+@pytest.mark.parametrize("L,M", [(14, 0), (15, 2), (19, 0), (16, 5)])
+def test_inverse_qft_direct_kernel_matches_oracle(qcs, oracle_built, L, M):
+    """QCS_OPT_PIPELINE = 0: the global<->register sweep kernel at the default tile size."""
+    _check_iqft_vs_oracle(qcs, oracle_built, L, M, 0, pipeline=0)
+
+
+def _check_iqft_vs_oracle(qcs, oracle_built, L, M, tile_bits, pipeline):
     n = L + M
     o = oracle_built.Restatement(L, M)
     o.fill_synthetic(1234 + n)
@@ -43,6 +53,7 @@ def test_inverse_qft_matches_oracle_with_strided_sweeps(qcs, oracle_built, L, M,
     o.inverse_QFT()
     with qcs.Register(L, M) as reg:
         reg.set_option(qcs.OPT_TILE_BITS, tile_bits)
+        reg.set_option(qcs.OPT_PIPELINE, pipeline)
         reg.set_state(base)
         reg.inverse_QFT()
         err = rel_l2(reg.get_state(), o.get_state())

@@ -158,3 +158,62 @@ def test_hh_identity_and_norm_at_scale(qcs):
             reg.hadamard_gate(q)
         after = [reg.get_state(i, 1)[0] for i in probe]
         assert max(abs(a - b) for a, b in zip(before, after)) < 1e-15
+
+
+@pytest.mark.parametrize("n,kind", [(18, "random"), (20, "random"), (22, "random"), (21, "sparse"),
+                                    (20, "ties"), (19, "spiky")])
+def test_parallel_measurement_reproduces_sequential_rounding(qcs, oracle_built, n, kind):
+    """The parallel scan (csrc/measure.cu) must return the index of the reference's
+    sequential loop (qc_shor.c:283-292) -- checked against the oracle and against the
+    single-CTA sequential GPU scan, including r values placed exactly on and next to
+    prefix sums."""
+    rng = np.random.default_rng(n)
+    N = 1 << n
+    if kind == "random":
+        v = rng.normal(size=N) + 1j * rng.normal(size=N)
+    elif kind == "sparse":
+        v = np.zeros(N, dtype=np.complex128)
+        idx = rng.choice(N, size=64, replace=False)
+        v[idx] = rng.normal(size=64) + 1j * rng.normal(size=64)
+    elif kind == "ties":
+        # equal power-of-two probabilities: every addition is exact or an exact tie
+        v = np.zeros(N, dtype=np.complex128)
+        v[:: N // 4096] = 1.0
+        v[1:: N // 2048] = 0.5
+    else:
+        v = (rng.normal(size=N) + 1j * rng.normal(size=N)) * np.exp(rng.normal(size=N) * 6)
+    v /= np.linalg.norm(v)
+    o = oracle_built.Restatement(n, 0)
+    p = np.abs(v.real) ** 2 + np.abs(v.imag) ** 2
+    prefix = np.cumsum(p)
+    rs = [0.0, 1e-12, 0.1, 0.25, 0.5, 0.75, 0.9999, 1.0, 1.5]
+    rs += [float(rng.uniform()) for _ in range(6)]
+    for k in rng.integers(1, N - 1, size=4):
+        rs += [float(prefix[k]), float(np.nextafter(prefix[k], 0)), float(np.nextafter(prefix[k], 2))]
+    with qcs.Register(n, 0) as reg, qcs.Register(n, 0) as seq:
+        seq.set_option(qcs.OPT_MEASURE_SEQUENTIAL, 1)
+        for r in rs:
+            o.set_state(v)
+            reg.set_state(v)
+            seq.set_state(v)
+            want = o.measure_state(r)
+            assert seq.measure_state(r) == want, (kind, r)
+            assert reg.measure_state(r) == want, (kind, r)
+
+
+def test_parallel_measurement_after_qft_at_scale(qcs):
+    """n = 26: parallel-exact scan == single-CTA sequential scan on a QFT output state."""
+    n = 26
+    with qcs.Register(n, 0) as reg:
+        reg.fill_synthetic(7)
+        reg.scale(1.0 / math.sqrt(reg.norm2()))
+        reg.inverse_QFT()
+        state = reg.get_state().copy()
+        for r in (0.001, 0.37, 0.93):
+            reg.set_state(state)
+            reg.set_option(qcs.OPT_MEASURE_SEQUENTIAL, 0)
+            a = reg.measure_state(r)
+            reg.set_state(state)
+            reg.set_option(qcs.OPT_MEASURE_SEQUENTIAL, 1)
+            b = reg.measure_state(r)
+            assert a == b, r
