@@ -1,0 +1,202 @@
+// modexp_fused.cu -- the first half of quantum_computation (qc_shor.c:720-731)
+// as fused sweeps: Hadamards on the L register (Walsh-Hadamard tile sweeps, see
+// qft_common.cuh) and then ALL L controlled a^(2^k) mod C gates in one
+// block-local pass.
+//
+// Gate k (control qubit first + k, multiplier A_k = atox_k % C) maps, inside
+// every block of 2^M consecutive amplitudes whose control bit is 1,
+//     f -> A_k f mod C   (f < C;  rows f >= C stay put)          qc_shor.c:619-652
+// The blocks never mix, so a chunk of 2^T >= 2^M amplitudes is staged in
+// shared memory once and all gates are applied to it there:
+//   * every A_k coprime to C (the normal case): the L maps commute and compose
+//     into one bijection f -> B(x) f mod C with B(x) = prod_{k: x_k = 1} A_k,
+//     applied as a single gather with B(x)^-1 -- pure moves, bit-exact;
+//   * otherwise (gcd(A_k, C) != 1, A_k = 0 from INT_POW overflow): the gates
+//     are applied one after another between two shared-memory buffers, each
+//     row summing its sources in ascending order exactly like
+//     gates_exact.cu / operate_matrix do.
+// Either way the result is value-identical to applying the L gates one by one.
+#include "qcs_internal.h"
+
+namespace {
+
+constexpr int kMaxGates = 62;
+
+struct modexp_params {
+    unsigned T, M, C, L;
+    unsigned first;            // control qubit of gate 0
+    unsigned n_local;
+    unsigned rank;             // supplies control bits >= n_local
+    int bijective;
+    unsigned A[kMaxGates];
+    unsigned inv[kMaxGates];   // bijective: A^-1 mod C;  general: (A/g)^-1 mod C/g
+    unsigned g[kMaxGates];     // gcd(A, C)
+};
+
+__device__ __forceinline__ double2 ref_term1(double2 c)
+{
+    // the entry 1 + 0i applied as qc_shor.c:409,412 does
+    return make_double2(__dsub_rn(__dmul_rn(1.0, c.x), __dmul_rn(0.0, c.y)),
+                        __dadd_rn(__dmul_rn(1.0, c.y), __dmul_rn(0.0, c.x)));
+}
+
+// control bit of gate k for an element whose shard-local index is `local`
+__device__ __forceinline__ unsigned control_bit(const modexp_params &P, unsigned k, uint64_t local)
+{
+    const unsigned pos = P.first + k;
+    if (pos >= P.n_local) return (P.rank >> (pos - P.n_local)) & 1u;
+    return (unsigned) (local >> pos) & 1u;
+}
+
+__global__ void __launch_bounds__(1024)
+k_modexp_sweep(double2 *__restrict__ amp, uint64_t n_chunks, const modexp_params P)
+{
+    extern __shared__ double2 smem[];
+    double2 *buf0 = smem;
+    const unsigned chunk_len = 1u << P.T;
+    double2 *buf1 = smem + chunk_len;                       // general path only
+    unsigned *mult = (unsigned *) (P.bijective ? (smem + chunk_len) : (smem + 2 * chunk_len));
+    const unsigned maskM = (1u << P.M) - 1u;
+    const unsigned n_blocks = 1u << (P.T - P.M);
+
+    for (uint64_t ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
+        const uint64_t chunk_base = ci << P.T;
+        double2 *g_chunk = amp + chunk_base;
+        for (unsigned e = threadIdx.x; e < chunk_len; e += blockDim.x) buf0[e] = g_chunk[e];
+        if (P.bijective) {
+            // per-block inverse multiplier B(x)^-1 = prod A_k^-1 over the set control bits
+            for (unsigned b = threadIdx.x; b < n_blocks; b += blockDim.x) {
+                const uint64_t local = chunk_base | ((uint64_t) b << P.M);
+                unsigned long long m = 1 % P.C;
+                for (unsigned k = 0; k < P.L; k++)
+                    if (control_bit(P, k, local)) m = (m * P.inv[k]) % P.C;
+                mult[b] = (unsigned) m;
+            }
+            __syncthreads();
+            for (unsigned j = threadIdx.x; j < chunk_len; j += blockDim.x) {
+                const unsigned fp = j & maskM;
+                const unsigned mb = mult[j >> P.M];
+                if (fp >= P.C || mb == 1u) continue;          // identity row
+                const unsigned f = (unsigned) (((unsigned long long) mb * fp) % P.C);
+                g_chunk[j] = buf0[(j & ~maskM) | f];
+            }
+            __syncthreads();
+            continue;
+        }
+        __syncthreads();
+        double2 *src = buf0, *dst = buf1;
+        bool moved = false;
+        for (unsigned k = 0; k < P.L; k++) {
+            const unsigned pos = P.first + k;
+            if (pos >= P.T && !control_bit(P, k, chunk_base)) continue;     // off for the whole chunk
+            const unsigned gk = P.g[k], stepk = P.C / gk;
+            for (unsigned j = threadIdx.x; j < chunk_len; j += blockDim.x) {
+                const unsigned fp = j & maskM;
+                const bool on = pos >= P.T || ((j >> pos) & 1u);
+                double2 v;
+                if (!on || fp >= P.C) {
+                    v = src[j];
+                } else {
+                    v = make_double2(0.0, 0.0);
+                    if (fp % gk == 0) {
+                        const unsigned f0 = (unsigned) (((unsigned long long) (fp / gk) * P.inv[k]) % stepk);
+                        for (unsigned t = 0; t < gk; t++) {
+                            const double2 term = ref_term1(src[(j & ~maskM) | (f0 + t * stepk)]);
+                            v.x = __dadd_rn(v.x, term.x);
+                            v.y = __dadd_rn(v.y, term.y);
+                        }
+                    }
+                }
+                dst[j] = v;
+            }
+            __syncthreads();
+            double2 *tmp = src; src = dst; dst = tmp;
+            moved = true;
+        }
+        if (moved)
+            for (unsigned e = threadIdx.x; e < chunk_len; e += blockDim.x) g_chunk[e] = src[e];
+        __syncthreads();
+    }
+}
+
+unsigned h_gcd(unsigned a, unsigned b)
+{
+    while (b) { const unsigned t = a % b; a = b; b = t; }
+    return a;
+}
+
+unsigned h_modinv(unsigned a, unsigned m)
+{
+    if (m == 1) return 0;
+    long long t = 0, nt = 1, r = m, nr = a % m;
+    while (nr != 0) {
+        const long long q = r / nr;
+        long long tmp = t - q * nt; t = nt; nt = tmp;
+        tmp = r - q * nr; r = nr; nr = tmp;
+    }
+    if (t < 0) t += m;
+    return (unsigned) t;
+}
+
+}  // namespace
+
+int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, unsigned n_gates)
+{
+    const unsigned first = reg->n - n_gates;                  // qc_shor.c:720,728
+    const unsigned M = (unsigned) reg->M_size;
+    // Hadamards: local qubits by Walsh-Hadamard sweeps, global ones by exchange
+    const unsigned h_hi = reg->n < reg->n_local ? reg->n : reg->n_local;
+    if (first < h_hi) QCS_TRY(qcs_fused_hadamards(reg, first, h_hi));
+    for (unsigned q = h_hi > first ? h_hi : first; q < reg->n; q++) QCS_TRY(qcs_dist_hadamard_global(reg, q));
+
+    if (M == 0) return QCS_NO_ERROR;                          // f = f' = 0: every gate is the identity
+    const bool weird = C > 65536u || (M < 32 && (uint64_t) C > (1ull << M)) || first < M || M > reg->n_local ||
+                       n_gates > (unsigned) kMaxGates;
+    unsigned T = M < 10 ? 10 : M;
+    if (T > reg->n_local) T = reg->n_local;
+    modexp_params P;
+    P.bijective = 1;
+    for (unsigned k = 0; k < n_gates && !weird; k++) {
+        P.A[k] = A_per_gate[k] % C;
+        P.g[k] = h_gcd(P.A[k], C);
+        if (P.g[k] != 1) P.bijective = 0;
+    }
+    const size_t smem = weird ? 0 : (((size_t) 16 << T) * (P.bijective ? 1 : 2) + 4 * ((size_t) 1 << (T - M)) + 16);
+    if (weird || smem > reg->smem_optin) {
+        // shapes the block-local sweep does not cover: the per-gate kernels handle them
+        for (unsigned k = 0; k < n_gates; k++) {
+            const unsigned c = first + k;
+            if (c >= reg->n_local) {
+                const bool on = ((unsigned) reg->rank >> (c - reg->n_local)) & 1u;
+                QCS_TRY(qcs_k_amodc(reg, C, A_per_gate[k] % C, -1, !on));
+            } else {
+                QCS_TRY(qcs_k_amodc(reg, C, A_per_gate[k] % C, (int) c, false));
+            }
+        }
+        return QCS_NO_ERROR;
+    }
+    for (unsigned k = 0; k < n_gates; k++) {
+        const unsigned stepk = C / P.g[k];
+        P.inv[k] = P.bijective ? h_modinv(P.A[k], C) : h_modinv((P.A[k] / P.g[k]) % (stepk ? stepk : 1), stepk);
+    }
+    P.T = T;
+    P.M = M;
+    P.C = C;
+    P.L = n_gates;
+    P.first = first;
+    P.n_local = reg->n_local;
+    P.rank = (unsigned) reg->rank;
+    const uint64_t n_chunks = reg->N_local >> T;
+    QCS_CUDA(cudaFuncSetAttribute(k_modexp_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    unsigned threads = (1u << T) < 1024u ? (1u << T) : 1024u;
+    if (threads < 32) threads = 32;
+    int per_sm = 1;
+    QCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_modexp_sweep, (int) threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t) reg->sm_count * (uint64_t) per_sm;
+    if (grid > n_chunks) grid = n_chunks;
+    const double frac = (double) C / (double) (1u << M);
+    qcs_launch_begin(reg, QCS_K_MODEXP_SWEEP, 32.0 * (double) reg->N_local * (frac < 1.0 ? frac : 1.0));
+    k_modexp_sweep<<<(unsigned) grid, threads, smem, reg->stream>>>(reg->amp, n_chunks, P);
+    return qcs_launch_end(reg, QCS_K_MODEXP_SWEEP, "k_modexp_sweep");
+}

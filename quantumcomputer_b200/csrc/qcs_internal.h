@@ -107,6 +107,8 @@ int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limi
 
 // ---- fused sweeps: qft_fused.cu / modexp_fused.cu ---------------------------
 int qcs_fused_qft(qcs_register *reg, unsigned lo, unsigned hi, bool inverse);
+int qcs_fused_hadamards(qcs_register *reg, unsigned lo, unsigned hi);
+// H on the L register, then all L controlled a^(2^k) mod C gates in one block-local sweep
 int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, unsigned n_gates);
 
 // ---- multi-GPU: dist.cu ---------------------------------------------------

@@ -30,6 +30,7 @@ struct sweep_desc {
     int sw;                 // swizzle: phys(e) = e ^ ((e >> sw) & 7)
     int inverse;            // 1: inverse_QFT of the reference, 0: its adjoint
     int wcol_total;         // total column-twiddle entries
+    int hadamard_only;      // 1: the stages are bare Hadamards (no phase gates): Walsh-Hadamard sweep
     double scale;           // (1/sqrt 2)^(stages in this sweep), applied in the last step
     sweep_step step[kMaxSteps];
 };
@@ -70,7 +71,7 @@ __device__ __forceinline__ double2 rot8(double2 v, int q)
 // x[d] = amplitude whose step digit is d (top stage bit = MSB of d).
 // Decimation in frequency, positive exponent, unscaled: afterwards x[d] holds
 // frequency bitrev(d).
-template <int R>
+template <int R, bool TW>
 __device__ __forceinline__ void dif_inverse(double2 (&x)[R])
 {
 #pragma unroll
@@ -81,14 +82,15 @@ __device__ __forceinline__ void dif_inverse(double2 (&x)[R])
             for (int m = 0; m < span; m++) {
                 const double2 u = x[start + m], v = x[start + m + span];
                 x[start + m] = make_double2(u.x + v.x, u.y + v.y);
-                x[start + m + span] = rot8<true>(make_double2(u.x - v.x, u.y - v.y), m * (8 / span));
+                const double2 dif = make_double2(u.x - v.x, u.y - v.y);
+                x[start + m + span] = TW ? rot8<true>(dif, m * (8 / span)) : dif;
             }
         }
     }
 }
 
 // the adjoint network: decimation in time, negative exponent
-template <int R>
+template <int R, bool TW>
 __device__ __forceinline__ void dit_forward(double2 (&x)[R])
 {
 #pragma unroll
@@ -98,7 +100,7 @@ __device__ __forceinline__ void dit_forward(double2 (&x)[R])
 #pragma unroll
             for (int m = 0; m < span; m++) {
                 const double2 u = x[start + m];
-                const double2 v = rot8<false>(x[start + m + span], m * (8 / span));
+                const double2 v = TW ? rot8<false>(x[start + m + span], m * (8 / span)) : x[start + m + span];
                 x[start + m] = make_double2(u.x + v.x, u.y + v.y);
                 x[start + m + span] = make_double2(u.x - v.x, u.y - v.y);
             }
@@ -149,7 +151,7 @@ struct tile_geom {
     __device__ __forceinline__ unsigned swz(unsigned e) const { return e ^ ((e >> sw) & 7u); }
 };
 
-template <int R, bool INV>
+template <int R, bool INV, bool TW>
 __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__restrict__ tile,
                                          const double2 *__restrict__ wcol, double2 wb, const tile_geom G,
                                          const sweep_step S, int t, uint64_t base, bool from_global,
@@ -175,13 +177,17 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
 #pragma unroll
             for (int d = 0; d < R; d++) x[d] = tile[G.swz(e_base + ((unsigned) d << S.s))];
         }
-        const double2 w = cmul(wb, wcol[c]);
-        if (INV) {
-            dif_inverse<R>(x);
-            external_twiddle<R>(x, w);
+        if (TW) {
+            const double2 w = cmul(wb, wcol[c]);
+            if (INV) {
+                dif_inverse<R, true>(x);
+                external_twiddle<R>(x, w);
+            } else {
+                external_twiddle<R>(x, w);
+                dit_forward<R, true>(x);
+            }
         } else {
-            external_twiddle<R>(x, w);
-            dit_forward<R>(x);
+            dif_inverse<R, false>(x);       // H on r qubits in any order: a Walsh-Hadamard butterfly
         }
         if (apply_scale) {
 #pragma unroll
@@ -202,17 +208,17 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
     }
 }
 
-template <bool INV>
+template <bool INV, bool TW = true>
 __device__ __forceinline__ void dispatch_step(double2 *amp, double2 *tile, const double2 *wcol, double2 wb,
                                               const tile_geom G, const sweep_step S, int t, uint64_t base,
                                               bool from_global, bool to_global, bool apply_scale, double scale,
                                               unsigned tid, unsigned nthreads)
 {
     switch (S.r) {
-        case 4: run_step<16, INV>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
-        case 3: run_step<8, INV>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
-        case 2: run_step<4, INV>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
-        default: run_step<2, INV>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
+        case 4: run_step<16, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
+        case 3: run_step<8, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
+        case 2: run_step<4, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
+        default: run_step<2, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
     }
 }
 
@@ -309,6 +315,7 @@ inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int 
         d.t = rw.a + (rw.g_hi - rw.g_lo);
         d.lo = (int) lo;
         d.inverse = 1;
+        d.hadamard_only = 0;
         p.stages = rw.s_hi - rw.s_lo;
         d.scale = pow(0.70710678118654752440, (double) p.stages);
         if (p.stages % 2 == 0) d.scale = ldexp(1.0, -p.stages / 2);      // exact power of two

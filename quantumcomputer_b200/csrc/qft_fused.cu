@@ -82,7 +82,8 @@ k_qft_sweep(double2 *__restrict__ amp, uint64_t n_tiles, const sweep_desc P)
             const sweep_step S = P.step[k];
             const bool first = k == 0, last = k == P.n_steps - 1;
             const double2 wb = wbase[parity * kMaxSteps + k];
-            if (inv) dispatch_step<true>(amp, tile, wcol + S.col_off, wb, G, S, P.t, base, first, last, last, P.scale, threadIdx.x, NT);
+            if (P.hadamard_only) dispatch_step<true, false>(amp, tile, wcol + S.col_off, wb, G, S, P.t, base, first, last, last, P.scale, threadIdx.x, NT);
+            else if (inv) dispatch_step<true>(amp, tile, wcol + S.col_off, wb, G, S, P.t, base, first, last, last, P.scale, threadIdx.x, NT);
             else dispatch_step<false>(amp, tile, wcol + S.col_off, wb, G, S, P.t, base, first, last, last, P.scale, threadIdx.x, NT);
             if (!last) __syncthreads();
         }
@@ -109,17 +110,18 @@ int launch_sweep(qcs_register *reg, const sweep_plan &p, size_t smem)
 bool qcs_pipeline_supports(const qcs_register *reg, const qft::sweep_plan &p);
 int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_plan &plan);
 
-int qcs_fused_qft(qcs_register *reg, unsigned lo, unsigned hi, bool inverse)
+static int run_sweeps(qcs_register *reg, unsigned lo, unsigned hi, bool inverse, bool hadamard_only)
 {
     if (hi > reg->n_local) {
-        fprintf(stderr, "qcs: fused QFT over global qubits is handled by the distributed schedule\n");
+        fprintf(stderr, "qcs: fused sweeps over global qubits are handled by the distributed schedule\n");
         return QCS_BAD_ARGUMENTS;
     }
     const int T = reg->opt_tile_bits ? reg->opt_tile_bits : 11;
     std::vector<sweep_plan> plans;
     plan_inverse(reg->n_local, lo, hi, T, 4, plans);
     if (!inverse) make_forward(plans);
-    for (const sweep_plan &p : plans) {
+    for (sweep_plan &p : plans) {
+        p.d.hadamard_only = hadamard_only ? 1 : 0;
         const size_t smem = ((size_t) 16 << p.d.t) + (size_t) 16 * (size_t) p.d.wcol_total + 16 * 2 * kMaxSteps;
         if (smem > reg->smem_optin) return QCS_BAD_ARGUMENTS;
         int rc;
@@ -132,15 +134,15 @@ int qcs_fused_qft(qcs_register *reg, unsigned lo, unsigned hi, bool inverse)
     return QCS_NO_ERROR;
 }
 
-// placeholder: the modular-exponentiation half of quantum_computation still runs
-// gate by gate (modexp_fused.cu replaces this)
-int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, unsigned n_gates)
+int qcs_fused_qft(qcs_register *reg, unsigned lo, unsigned hi, bool inverse)
 {
-    const unsigned first = reg->n - n_gates;
-    for (unsigned l = first; l < reg->n; l++) {
-        if (l >= reg->n_local) return QCS_BAD_ARGUMENTS;
-        QCS_TRY(qcs_k_hadamard_local(reg, l));
-    }
-    for (unsigned k = 0; k < n_gates; k++) QCS_TRY(qcs_k_amodc(reg, C, A_per_gate[k], (int) (first + k), false));
-    return QCS_NO_ERROR;
+    return run_sweeps(reg, lo, hi, inverse, false);
 }
+
+// Hadamard on every qubit of [lo, hi) (the first loop of quantum_computation,
+// qc_shor.c:720-722) as Walsh-Hadamard tile sweeps
+int qcs_fused_hadamards(qcs_register *reg, unsigned lo, unsigned hi)
+{
+    return run_sweeps(reg, lo, hi, true, true);
+}
+

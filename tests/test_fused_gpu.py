@@ -156,3 +156,24 @@ def test_fused_sweep_count(qcs):
         reg.synchronize()
         launches, _, by = reg.profile()["tile_sweep"]
         assert 1 <= launches <= 5 and by == launches * 32.0 * (1 << 26)
+
+
+@pytest.mark.parametrize("L,M,Cn,a,mode", [(3, 4, 15, 7, 0), (5, 5, 21, 2, 0), (6, 5, 21, 4, 0), (3, 4, 15, 6, 0),
+                                           (9, 5, 21, 2, 1), (8, 7, 77, 3, 1), (6, 11, 2047, 5, 1), (12, 6, 35, 4, 1),
+                                           (7, 4, 12, 10, 1), (5, 12, 4001, 7, 1)])
+def test_quantum_computation_on_arbitrary_input_state(qcs, L, M, Cn, a, mode):
+    """Fused H^L + modexp sweep + fused inverse QFT vs the gate-by-gate kernels, from a random
+    (not reset) state; includes non-bijective multipliers and blocks up to 2^12."""
+    n = L + M
+    rng = np.random.default_rng(n * 100 + Cn)
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    v /= np.linalg.norm(v)
+    with qcs.Register(L, M) as exact, qcs.Register(L, M) as fused:
+        exact.set_option(qcs.OPT_FUSION, 0)
+        exact.set_state(v)
+        fused.set_state(v)
+        exact.quantum_computation(Cn, a, mode)
+        fused.quantum_computation(Cn, a, mode)
+        assert rel_l2(fused.get_state(), exact.get_state()) <= TOL
+        prof = fused.profile()
+        assert prof["modexp_sweep"][0] == 1 and prof["amodc"][0] == 0
