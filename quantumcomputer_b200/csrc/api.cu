@@ -37,7 +37,7 @@ void qcs_launch_begin(qcs_register *reg, int kind, double algorithmic_bytes)
             cudaEventCreate(&s.end);
         }
         s.kind = kind;
-        cudaEventRecord(s.begin, reg->stream);
+        cudaEventRecord(s.begin, reg->launch_stream ? reg->launch_stream : reg->stream);
         reg->pending.push_back(s);
     }
 }
@@ -45,7 +45,8 @@ void qcs_launch_begin(qcs_register *reg, int kind, double algorithmic_bytes)
 int qcs_launch_end(qcs_register *reg, int kind, const char *name)
 {
     (void) kind;
-    if (reg->opt_profile && !reg->pending.empty()) cudaEventRecord(reg->pending.back().end, reg->stream);
+    if (reg->opt_profile && !reg->pending.empty())
+        cudaEventRecord(reg->pending.back().end, reg->launch_stream ? reg->launch_stream : reg->stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return qcs_map_cuda_error(e, name, __FILE__, __LINE__);
     if (reg->pending.size() > 4096) return qcs_profile_resolve(reg);
@@ -55,7 +56,7 @@ int qcs_launch_end(qcs_register *reg, int kind, const char *name)
 int qcs_profile_resolve(qcs_register *reg)
 {
     if (reg->pending.empty()) return QCS_NO_ERROR;
-    QCS_CUDA(cudaStreamSynchronize(reg->stream));
+    QCS_CUDA(reg->dist ? cudaDeviceSynchronize() : cudaStreamSynchronize(reg->stream));
     for (auto &s : reg->pending) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s.begin, s.end) == cudaSuccess) reg->ms[s.kind] += (double) ms;
@@ -180,6 +181,7 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->d_small = nullptr;
     reg->h_small = nullptr;
     reg->stream = nullptr;
+    reg->launch_stream = nullptr;
     reg->timer_begin = reg->timer_end = nullptr;
 
     int rc = QCS_NO_ERROR;
@@ -399,8 +401,19 @@ static int qft_any(qcs_register *reg, unsigned lo, unsigned hi, bool inverse)
 {
     if (lo > hi || hi > reg->n) return QCS_BAD_ARGUMENTS;
     if (lo == hi) return QCS_NO_ERROR;
-    if (reg->opt_fusion) return qcs_fused_qft(reg, lo, hi, inverse);
-    return qft_gate_by_gate(reg, lo, hi, inverse);
+    if (!reg->opt_fusion) return qft_gate_by_gate(reg, lo, hi, inverse);
+    if (hi <= reg->n_local) return qcs_fused_qft(reg, lo, hi, inverse);
+    // sharded register, transform reaches the global qubits: their stages run as
+    // exchange + sweep + exchange (dist.cu), the local ones as ordinary sweeps
+    const unsigned q = reg->n_local - (unsigned) reg->p_global;
+    if (hi != reg->n || lo > q || reg->n_local < 2u * (unsigned) reg->p_global)
+        return qft_gate_by_gate(reg, lo, hi, inverse);       // odd shapes: pairwise exchanges, gate by gate
+    if (inverse) {
+        QCS_TRY(qcs_dist_top_stages(reg, lo, true, false));
+        return qcs_fused_qft(reg, lo, reg->n_local, true);
+    }
+    QCS_TRY(qcs_fused_qft(reg, lo, reg->n_local, false));
+    return qcs_dist_top_stages(reg, lo, false, false);
 }
 
 extern "C" int qcs_inverse_QFT(qcs_register *reg)

@@ -104,6 +104,12 @@ struct qcs_dist {
     cudaEvent_t buf_free[2] = {nullptr, nullptr};
     cudaEvent_t ready = nullptr;
     double *d_gather = nullptr;     // world doubles
+    // global<->local exchange slices: kSlices buffers of world * 2^slice_bits amplitudes
+    double2 *slice[3] = {nullptr, nullptr, nullptr};
+    unsigned slice_bits = 0;
+    cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr};     // slice received
+    cudaEvent_t ev_done[3] = {nullptr, nullptr, nullptr};   // slice transformed
+    cudaEvent_t ev_tail = nullptr;
     double *h_gather = nullptr;     // pinned
 };
 
@@ -146,6 +152,12 @@ void qcs_dist_destroy(qcs_register *reg)
     if (!d) return;
     if (d->comm_stream) cudaStreamSynchronize(d->comm_stream);
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+    for (int b = 0; b < 3; b++) {
+        if (d->slice[b]) cudaFree(d->slice[b]);
+        if (d->ev_in[b]) cudaEventDestroy(d->ev_in[b]);
+        if (d->ev_done[b]) cudaEventDestroy(d->ev_done[b]);
+    }
+    if (d->ev_tail) cudaEventDestroy(d->ev_tail);
     for (int b = 0; b < 2; b++) {
         if (d->staging[b]) cudaFree(d->staging[b]);
         if (d->recv_done[b]) cudaEventDestroy(d->recv_done[b]);
@@ -218,5 +230,108 @@ int qcs_dist_hadamard_global(qcs_register *reg, unsigned q)
         QCS_TRY(qcs_launch_end(reg, QCS_K_HADAMARD, "k_hadamard_global_combine"));
         QCS_CUDA(cudaEventRecord(d->buf_free[b], reg->stream));
     }
+    return QCS_NO_ERROR;
+}
+
+
+// ---------------------------------------------------------------------------
+// Stages on the global qubits [n_local, n) -- the first p stages of the
+// inverse QFT (qc_shor.c:682-689), the last p of the forward one, or the bare
+// Hadamards of quantum_computation -- by qubit-swap relabelling:
+//
+//   rank r, local index (s, m)  [s = top p local bits, m = the rest]
+//   exchange in : piece (r; s, m-slice) goes to rank s, so rank r ends up with
+//                 the amplitudes (s'; r, m-slice) of every rank s' : for its
+//                 value r of the swapped-out bits, all values of the global ones
+//   sweep       : one tile sweep over those p bits (qcs_fused_top_sweep); the
+//                 phases see the swapped-out bits through y_const
+//   exchange out: the transformed pieces return to where they came from.
+//
+// Each rank sends (P-1)/P of its shard twice (vs. p full-shard pairwise
+// exchanges gate by gate).  The three phases are pipelined over slices of m
+// through three staging buffers: while slice u is transformed, slice u+1 is
+// arriving and slice u-1 is leaving over NVLink; nothing is staged through
+// host memory and the shard is updated in place.
+// ---------------------------------------------------------------------------
+int qcs_dist_top_stages(qcs_register *reg, unsigned lo, bool inverse, bool hadamard_only)
+{
+    qcs_dist *d = reg->dist;
+    if (!d) return QCS_BAD_ARGUMENTS;
+    const unsigned p = (unsigned) reg->p_global;
+    const int P = reg->world, r = reg->rank;
+    if (reg->n_local < 2 * p) return QCS_BAD_ARGUMENTS;
+    const unsigned q = reg->n_local - p;                 // bits of m
+    if (lo > q) {
+        fprintf(stderr, "qcs: sharded fused QFT needs M_size <= n_local - log2(world)\n");
+        return QCS_BAD_ARGUMENTS;
+    }
+    if (!d->slice[0]) {
+        unsigned c = q < 26u - p ? q : 26u - p;          // at most 1 GiB per buffer
+        if (q >= 2 && c > q - 2) c = q - 2;              // at least 4 slices so the phases overlap
+        d->slice_bits = c;
+        for (int b = 0; b < 3; b++) {
+            QCS_CUDA(cudaMalloc((void **) &d->slice[b], ((size_t) P << c) * sizeof(double2)));
+            QCS_CUDA(cudaEventCreateWithFlags(&d->ev_in[b], cudaEventDisableTiming));
+            QCS_CUDA(cudaEventCreateWithFlags(&d->ev_done[b], cudaEventDisableTiming));
+        }
+        QCS_CUDA(cudaEventCreateWithFlags(&d->ev_tail, cudaEventDisableTiming));
+    }
+    const unsigned c = d->slice_bits;
+    const uint64_t Sc = 1ull << c, B = 1ull << q;
+    const uint64_t n_slices = B >> c;
+
+    // the exchange reads amplitudes produced by earlier kernels on the compute stream
+    QCS_CUDA(cudaEventRecord(d->ready, reg->stream));
+    QCS_CUDA(cudaStreamWaitEvent(d->comm_stream, d->ready, 0));
+
+    auto exchange = [&](uint64_t u, bool inbound) -> int {
+        const int b = (int) (u % 3);
+        reg->launches_total++;
+        reg->launches[QCS_K_EXCHANGE]++;
+        reg->alg_bytes[QCS_K_EXCHANGE] += 16.0 * (double) Sc * (double) (P - 1);
+        QCS_NCCL(g_nccl.GroupStart());
+        for (int s = 0; s < P; s++) {
+            if (s == r) continue;
+            double2 *mine = reg->amp + (uint64_t) s * B + u * Sc;       // piece (r; s, slice u)
+            double2 *stg = d->slice[b] + (uint64_t) s * Sc;             // slot of rank s in the staging slice
+            if (inbound) {
+                QCS_NCCL(g_nccl.Send(mine, Sc * 2, ncclDouble, s, d->comm, d->comm_stream));
+                QCS_NCCL(g_nccl.Recv(stg, Sc * 2, ncclDouble, s, d->comm, d->comm_stream));
+            } else {
+                QCS_NCCL(g_nccl.Send(stg, Sc * 2, ncclDouble, s, d->comm, d->comm_stream));
+                QCS_NCCL(g_nccl.Recv(mine, Sc * 2, ncclDouble, s, d->comm, d->comm_stream));
+            }
+        }
+        QCS_NCCL(g_nccl.GroupEnd());
+        return QCS_NO_ERROR;
+    };
+
+    for (uint64_t u = 0; u <= n_slices; u++) {
+        if (u < n_slices) {
+            const int b = (int) (u % 3);
+            // slice u in: the staging buffer was last sent from by exchange-out(u-3), earlier on this stream
+            QCS_TRY(exchange(u, true));
+            QCS_CUDA(cudaEventRecord(d->ev_in[b], d->comm_stream));
+            // compute stream: own piece into the slice, transform, own piece back
+            double2 *own = reg->amp + (uint64_t) r * B + u * Sc;
+            QCS_CUDA(cudaMemcpyAsync(d->slice[b] + (uint64_t) r * Sc, own, Sc * sizeof(double2),
+                                     cudaMemcpyDeviceToDevice, reg->stream));
+            QCS_CUDA(cudaStreamWaitEvent(reg->stream, d->ev_in[b], 0));
+            const unsigned long long y_const = (((unsigned long long) u << c) >> lo) +
+                                               ((unsigned long long) r << (q - lo));
+            QCS_TRY(qcs_fused_top_sweep(reg, d->slice[b], c, p, lo, y_const, inverse, hadamard_only, reg->stream));
+            QCS_CUDA(cudaMemcpyAsync(own, d->slice[b] + (uint64_t) r * Sc, Sc * sizeof(double2),
+                                     cudaMemcpyDeviceToDevice, reg->stream));
+            QCS_CUDA(cudaEventRecord(d->ev_done[b], reg->stream));
+        }
+        if (u >= 1) {
+            const int b = (int) ((u - 1) % 3);
+            QCS_CUDA(cudaStreamWaitEvent(d->comm_stream, d->ev_done[b], 0));
+            QCS_TRY(exchange(u - 1, false));
+        }
+    }
+    // later kernels on the compute stream see the returned pieces
+    QCS_CUDA(cudaEventRecord(d->ev_tail, d->comm_stream));
+    QCS_CUDA(cudaStreamWaitEvent(reg->stream, d->ev_tail, 0));
     return QCS_NO_ERROR;
 }

@@ -147,7 +147,12 @@ int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, 
     // Hadamards: local qubits by Walsh-Hadamard sweeps, global ones by exchange
     const unsigned h_hi = reg->n < reg->n_local ? reg->n : reg->n_local;
     if (first < h_hi) QCS_TRY(qcs_fused_hadamards(reg, first, h_hi));
-    for (unsigned q = h_hi > first ? h_hi : first; q < reg->n; q++) QCS_TRY(qcs_dist_hadamard_global(reg, q));
+    if (reg->world > 1) {
+        if (first <= reg->n_local && reg->n_local >= 2u * (unsigned) reg->p_global)
+            QCS_TRY(qcs_dist_top_stages(reg, 0, true, true));       // H on every global qubit at once
+        else
+            for (unsigned q = h_hi > first ? h_hi : first; q < reg->n; q++) QCS_TRY(qcs_dist_hadamard_global(reg, q));
+    }
 
     if (M == 0) return QCS_NO_ERROR;                          // f = f' = 0: every gate is the identity
     const bool weird = C > 65536u || (M < 32 && (uint64_t) C > (1ull << M)) || first < M || M > reg->n_local ||

@@ -27,6 +27,7 @@ struct qcs_register {
     uint64_t N_local;       // 2^n_local
     int device;
     cudaStream_t stream;
+    cudaStream_t launch_stream;   // stream the next accounted launch goes to (nullptr: `stream`)
     double2 *amp;           // this shard, in place
 
     // small device/host scratch
@@ -108,6 +109,8 @@ int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limi
 // ---- fused sweeps: qft_fused.cu / modexp_fused.cu ---------------------------
 int qcs_fused_qft(qcs_register *reg, unsigned lo, unsigned hi, bool inverse);
 int qcs_fused_hadamards(qcs_register *reg, unsigned lo, unsigned hi);
+int qcs_fused_top_sweep(qcs_register *reg, double2 *buf, unsigned c, unsigned p, unsigned lo,
+                        unsigned long long y_const, bool inverse, bool hadamard_only, cudaStream_t stream);
 // H on the L register, then all L controlled a^(2^k) mod C gates in one block-local sweep
 int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, unsigned n_gates);
 
@@ -115,5 +118,8 @@ int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, 
 int qcs_dist_init(qcs_register *reg, const void *comm_id);
 void qcs_dist_destroy(qcs_register *reg);
 int qcs_dist_hadamard_global(qcs_register *reg, unsigned q);
+// stages of the (inverse) QFT / Hadamards on the global qubits [n_local, n): exchange in,
+// one sweep, exchange back, pipelined over slices of the shard
+int qcs_dist_top_stages(qcs_register *reg, unsigned lo, bool inverse, bool hadamard_only);
 int qcs_dist_allgather_double(qcs_register *reg, double mine, double *all_host);
 int qcs_dist_barrier(qcs_register *reg);

@@ -31,6 +31,8 @@ struct sweep_desc {
     int inverse;            // 1: inverse_QFT of the reference, 0: its adjoint
     int wcol_total;         // total column-twiddle entries
     int hadamard_only;      // 1: the stages are bare Hadamards (no phase gates): Walsh-Hadamard sweep
+    unsigned long long y_const;   // added to the per-tile y: register bits held by the rank (sharded layouts)
+    unsigned long long tile_first; // first tile of this launch (sub-range launches that overlap an exchange)
     double scale;           // (1/sqrt 2)^(stages in this sweep), applied in the last step
     sweep_step step[kMaxSteps];
 };
@@ -233,6 +235,13 @@ __device__ __forceinline__ double2 unit_phase(uint64_t y, int j, bool positive)
 // ---------------------------------------------------------------------------
 // host-side planning
 // ---------------------------------------------------------------------------
+// where a sweep runs: the register's shard, or a staging buffer holding a slice of it
+struct sweep_target {
+    double2 *amp;
+    unsigned n_bits;        // log2 of the number of amplitudes addressed
+    cudaStream_t stream;
+};
+
 struct sweep_plan {
     sweep_desc d;
     uint64_t n_tiles;
@@ -316,6 +325,8 @@ inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int 
         d.lo = (int) lo;
         d.inverse = 1;
         d.hadamard_only = 0;
+        d.y_const = 0;
+        d.tile_first = 0;
         p.stages = rw.s_hi - rw.s_lo;
         d.scale = pow(0.70710678118654752440, (double) p.stages);
         if (p.stages % 2 == 0) d.scale = ldexp(1.0, -p.stages / 2);      // exact power of two

@@ -67,7 +67,7 @@ k_qft_sweep(double2 *__restrict__ amp, uint64_t n_tiles, const sweep_desc P)
 
     unsigned parity = 0;
     const int lo_gap = P.g_lo - P.a;             // number of index bits between the two tile runs
-    for (uint64_t tix = blockIdx.x; tix < n_tiles; tix += gridDim.x, parity ^= 1u) {
+    for (uint64_t tix = P.tile_first + blockIdx.x; tix < P.tile_first + n_tiles; tix += gridDim.x, parity ^= 1u) {
         // deposit the tile number into the index bits that are not in the tile
         const uint64_t base = lo_gap > 0 ? (((tix >> lo_gap) << P.g_hi) | ((tix & ((1ull << lo_gap) - 1ull)) << P.a))
                                          : (tix << P.t);
@@ -75,7 +75,7 @@ k_qft_sweep(double2 *__restrict__ amp, uint64_t n_tiles, const sweep_desc P)
             const sweep_step S = P.step[threadIdx.x];
             uint64_t y = 0;
             if (S.low_phys > P.lo) y = (base & ((1ull << S.low_phys) - 1ull)) >> P.lo;
-            wbase[parity * kMaxSteps + threadIdx.x] = unit_phase(y, S.j, inv);
+            wbase[parity * kMaxSteps + threadIdx.x] = unit_phase(y + P.y_const, S.j, inv);
         }
         __syncthreads();
         for (int k = 0; k < P.n_steps; k++) {
@@ -91,7 +91,7 @@ k_qft_sweep(double2 *__restrict__ amp, uint64_t n_tiles, const sweep_desc P)
 }
 
 template <int NT, int MINB>
-int launch_sweep(qcs_register *reg, const sweep_plan &p, size_t smem)
+int launch_sweep(qcs_register *reg, const sweep_target &tg, const sweep_plan &p, size_t smem)
 {
     auto kern = k_qft_sweep<NT, MINB>;
     QCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -100,15 +100,35 @@ int launch_sweep(qcs_register *reg, const sweep_plan &p, size_t smem)
     if (per_sm < 1) return QCS_UNKNOWN_ERROR;
     uint64_t grid = (uint64_t) reg->sm_count * (uint64_t) per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
-    qcs_launch_begin(reg, QCS_K_TILE_SWEEP, 32.0 * (double) reg->N_local);
-    kern<<<(unsigned) grid, NT, smem, reg->stream>>>(reg->amp, p.n_tiles, p.d);
+    qcs_launch_begin(reg, QCS_K_TILE_SWEEP, 32.0 * (double) (p.n_tiles << p.d.t));
+    kern<<<(unsigned) grid, NT, smem, tg.stream>>>(tg.amp, p.n_tiles, p.d);
     return qcs_launch_end(reg, QCS_K_TILE_SWEEP, "k_qft_sweep");
 }
 
 }  // namespace
 
-bool qcs_pipeline_supports(const qcs_register *reg, const qft::sweep_plan &p);
-int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_plan &plan);
+bool qcs_pipeline_supports(const qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &p);
+int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &plan);
+
+static int launch_plan_inner(qcs_register *reg, const sweep_target &tg, const sweep_plan &p);
+
+static int launch_plan(qcs_register *reg, const sweep_target &tg, const sweep_plan &p)
+{
+    reg->launch_stream = tg.stream;
+    const int rc = launch_plan_inner(reg, tg, p);
+    reg->launch_stream = nullptr;
+    return rc;
+}
+
+static int launch_plan_inner(qcs_register *reg, const sweep_target &tg, const sweep_plan &p)
+{
+    const size_t smem = ((size_t) 16 << p.d.t) + (size_t) 16 * (size_t) p.d.wcol_total + 16 * 2 * kMaxSteps;
+    if (smem > reg->smem_optin) return QCS_BAD_ARGUMENTS;
+    if (reg->opt_pipeline && qcs_pipeline_supports(reg, tg, p)) return qcs_pipeline_launch(reg, tg, p);
+    if (p.d.t >= 13) return launch_sweep<512, 1>(reg, tg, p, smem);
+    if (p.d.t == 12) return launch_sweep<256, 2>(reg, tg, p, smem);
+    return launch_sweep<128, 4>(reg, tg, p, smem);
+}
 
 static int run_sweeps(qcs_register *reg, unsigned lo, unsigned hi, bool inverse, bool hadamard_only)
 {
@@ -120,18 +140,51 @@ static int run_sweeps(qcs_register *reg, unsigned lo, unsigned hi, bool inverse,
     std::vector<sweep_plan> plans;
     plan_inverse(reg->n_local, lo, hi, T, 4, plans);
     if (!inverse) make_forward(plans);
+    const sweep_target tg = {reg->amp, reg->n_local, reg->stream};
     for (sweep_plan &p : plans) {
         p.d.hadamard_only = hadamard_only ? 1 : 0;
-        const size_t smem = ((size_t) 16 << p.d.t) + (size_t) 16 * (size_t) p.d.wcol_total + 16 * 2 * kMaxSteps;
-        if (smem > reg->smem_optin) return QCS_BAD_ARGUMENTS;
-        int rc;
-        if (reg->opt_pipeline && qcs_pipeline_supports(reg, p)) rc = qcs_pipeline_launch(reg, p);
-        else if (p.d.t >= 13) rc = launch_sweep<512, 1>(reg, p, smem);
-        else if (p.d.t == 12) rc = launch_sweep<256, 2>(reg, p, smem);
-        else rc = launch_sweep<128, 4>(reg, p, smem);
-        if (rc != QCS_NO_ERROR) return rc;
+        QCS_TRY(launch_plan(reg, tg, p));
     }
     return QCS_NO_ERROR;
+}
+
+// One sweep over the top `p` index bits of `buf` (2^(c+p) amplitudes laid out
+// [slot][2^c]) that stand for the register's global qubits [n-p, n) after the
+// global<->local exchange (dist.cu).  y_const carries the register bits that
+// are not index bits of `buf` (the slice offset and the bits held by the rank).
+int qcs_fused_top_sweep(qcs_register *reg, double2 *buf, unsigned c, unsigned p, unsigned lo,
+                        unsigned long long y_const, bool inverse, bool hadamard_only, cudaStream_t stream)
+{
+    if (p < 1 || p > 4) return QCS_BAD_ARGUMENTS;
+    const unsigned nb = c + p;
+    int T = reg->opt_tile_bits ? reg->opt_tile_bits : 11;
+    if ((unsigned) T > nb) T = (int) nb;
+    sweep_plan pl;
+    sweep_desc &d = pl.d;
+    d.t = T;
+    d.a = T - (int) p;
+    if (d.a < 0) return QCS_BAD_ARGUMENTS;
+    d.g_lo = (int) c;
+    d.g_hi = (int) (c + p);
+    if (d.g_lo < d.a) return QCS_BAD_ARGUMENTS;
+    d.lo = (int) lo;
+    d.inverse = inverse ? 1 : 0;
+    d.hadamard_only = hadamard_only ? 1 : 0;
+    d.y_const = y_const;
+    d.tile_first = 0;
+    d.n_steps = 1;
+    d.scale = (p % 2 == 0) ? ldexp(1.0, -(int) p / 2) : pow(0.70710678118654752440, (double) p);
+    d.step[0].r = (int) p;
+    d.step[0].s = d.a;
+    d.step[0].low_phys = (int) c;
+    d.step[0].j = (int) (reg->n - 1) - (int) lo;
+    d.step[0].col_off = 0;
+    d.wcol_total = 1 << (d.t - (int) p);
+    d.sw = 28;
+    pl.n_tiles = 1ull << (nb - (unsigned) T);
+    pl.stages = (int) p;
+    const sweep_target tg = {buf, nb, stream};
+    return launch_plan(reg, tg, pl);
 }
 
 int qcs_fused_qft(qcs_register *reg, unsigned lo, unsigned hi, bool inverse)

@@ -159,7 +159,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
                 const uint32_t round = (uint32_t) (k / kStages);
                 mbar_wait(&empty[s], (round & 1u) ^ 1u);
                 int c0, c1, c2;
-                tile_coords(P, blockIdx.x + k * gridDim.x, c0, c1, c2);
+                tile_coords(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
                 mbar_expect_tx(&full[s], kTileBytes);
                 tma_load_3d(stage_buf + (size_t) s * (1u << kTileBits), &tmap, &full[s], c0, c1, c2);
             }
@@ -172,7 +172,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
                 const uint32_t round = (uint32_t) (k / kStages);
                 mbar_wait(&computed[s], round & 1u);
                 int c0, c1, c2;
-                tile_coords(P, blockIdx.x + k * gridDim.x, c0, c1, c2);
+                tile_coords(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
                 tma_store_3d(&tmap, stage_buf + (size_t) s * (1u << kTileBits), c0, c1, c2);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -189,14 +189,14 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
         for (uint64_t k = group; k < my_tiles; k += kGroups) {
             const int s = (int) (k % kStages);
             const uint32_t round = (uint32_t) (k / kStages);
-            const uint64_t tix = blockIdx.x + k * gridDim.x;
+            const uint64_t tix = P.d.tile_first + blockIdx.x + k * gridDim.x;
             const uint64_t base = lo_gap >= 0 ? (((tix >> lo_gap) << P.d.g_hi) | ((tix & ((1ull << lo_gap) - 1ull)) << P.d.a))
                                               : (tix << kTileBits);
             if (tig < (unsigned) P.d.n_steps) {
                 const sweep_step S = P.d.step[tig];
                 uint64_t y = 0;
                 if (S.low_phys > P.d.lo) y = (base & ((1ull << S.low_phys) - 1ull)) >> P.d.lo;
-                my_wbase[tig] = unit_phase(y, S.j, inv);
+                my_wbase[tig] = unit_phase(y + P.d.y_const, S.j, inv);
             }
             group_barrier(group);
             double2 *tile = stage_buf + (size_t) s * (1u << kTileBits);
@@ -236,9 +236,9 @@ encode_fn_t get_encode()
 }  // namespace
 
 // true when the pipelined kernel can run this sweep
-bool qcs_pipeline_supports(const qcs_register *reg, const qft::sweep_plan &p)
+bool qcs_pipeline_supports(const qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &p)
 {
-    if (p.d.t != kTileBits || reg->n_local < 14) return false;
+    if (p.d.t != kTileBits || tg.n_bits < 14) return false;
     const bool strided = p.d.g_lo > p.d.a;
     if (strided && (p.d.a < 1 || p.d.a > 7 || p.d.g_hi - p.d.g_lo > 8 || p.d.g_lo + 1 > 31)) return false;
     // the layout TMA writes (linear, or 128-byte swizzle for the contiguous sweep)
@@ -249,7 +249,7 @@ bool qcs_pipeline_supports(const qcs_register *reg, const qft::sweep_plan &p)
     return smem <= reg->smem_optin;
 }
 
-int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_plan &plan)
+int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &plan)
 {
     encode_fn_t encode = get_encode();
     if (!encode) {
@@ -268,7 +268,7 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_plan &plan)
         const int g = plan.d.g_hi - plan.d.g_lo;
         dims[0] = 2ull << plan.d.g_lo;                       // doubles below g_lo
         dims[1] = 1ull << g;
-        dims[2] = 1ull << (reg->n_local - (unsigned) plan.d.g_hi);
+        dims[2] = 1ull << (tg.n_bits - (unsigned) plan.d.g_hi);
         strides[0] = 16ull << plan.d.g_lo;
         strides[1] = 16ull << plan.d.g_hi;
         box[0] = 2u << plan.d.a;
@@ -279,7 +279,7 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_plan &plan)
         P.d.sw = 28;                                         // no XOR
     } else {
         dims[0] = 16;                                        // 128 B rows
-        dims[1] = reg->N_local >> 3;
+        dims[1] = (1ull << tg.n_bits) >> 3;
         dims[2] = 1;
         strides[0] = 128;
         strides[1] = 128ull * dims[1];
@@ -290,7 +290,7 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_plan &plan)
         P.lo_gap = -1;
         P.d.sw = 3;
     }
-    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, reg->amp, dims, strides, box, estr,
+    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, tg.amp, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
@@ -302,7 +302,7 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_plan &plan)
     QCS_CUDA(cudaFuncSetAttribute(k_qft_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     uint64_t grid = (uint64_t) reg->sm_count;
     if (grid > plan.n_tiles) grid = plan.n_tiles;
-    qcs_launch_begin(reg, QCS_K_TILE_SWEEP, 32.0 * (double) reg->N_local);
-    k_qft_sweep_tma<<<(unsigned) grid, kThreads, smem, reg->stream>>>(tmap, P);
+    qcs_launch_begin(reg, QCS_K_TILE_SWEEP, 32.0 * (double) (plan.n_tiles << kTileBits));
+    k_qft_sweep_tma<<<(unsigned) grid, kThreads, smem, tg.stream>>>(tmap, P);
     return qcs_launch_end(reg, QCS_K_TILE_SWEEP, "k_qft_sweep_tma");
 }

@@ -1,0 +1,137 @@
+"""Multi-GPU parity worker: run under torch.distributed.run, one rank per GPU.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/dist_worker.py
+
+Every sharded result is gathered to rank 0 and compared there with a
+single-GPU register running the same calls (which the single-GPU tests pin to
+the oracle).  Prints DIST_OK on success."""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import quantumcomputer_b200 as q  # noqa: E402
+
+TOL = 1e-12
+
+
+def gather_state(reg, rank, world):
+    local = torch.from_numpy(reg.get_state().view(np.float64).copy()).cuda()
+    parts = [torch.empty_like(local) for _ in range(world)] if rank == 0 else None
+    dist.gather(local, parts, dst=0)
+    if rank == 0:
+        return torch.cat(parts).cpu().numpy().view(np.complex128)
+    return None
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ids = [q.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    failures = []
+
+    def check(name, got, want, exact=False):
+        if rank != 0:
+            return
+        if exact:
+            ok = bool(np.all(got.view(np.float64) == want.view(np.float64)))
+            err = 0.0 if ok else float(np.linalg.norm(got - want) / np.linalg.norm(want))
+        else:
+            err = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+            ok = err <= TOL
+        print(f"[dist] {name}: {'ok' if ok else 'FAIL'} (err {err:.2e})", flush=True)
+        if not ok:
+            failures.append(name)
+
+    for (L, M) in [(18, 0), (12, 5), (21, 0)]:
+        n = L + M
+        sh = q.Register(L, M, device=local_rank, rank=rank, world_size=world, comm_id=ids[0])
+        single = q.Register(L, M, device=local_rank) if rank == 0 else None
+
+        def both(fn):
+            fn(sh)
+            if single is not None:
+                fn(single)
+
+        def prep(r):
+            r.fill_synthetic(77 + n)
+        both(prep)
+        s = sh.norm2()
+        both(lambda r: r.scale(1.0 / math.sqrt(s)))
+        if rank == 0:
+            assert abs(single.norm2() - sh.norm2()) < 1e-13
+
+        # gate by gate, including Hadamards on the global qubits (pairwise exchange)
+        both(lambda r: r.set_option(q.OPT_FUSION, 0))
+        def gates(r):
+            r.hadamard_gate(n - 1)
+            r.c_phase_shift_gate(n - 1, 2, 0.37)
+            r.hadamard_gate(3)
+            r.c_phase_shift_gate(n - 2, n - 1, -1.1)
+            if world > 2:
+                r.hadamard_gate(n - 2)
+            if M:
+                r.c_amodc_gate(21, 4, n - 1)
+                r.c_amodc_gate(21, 5, M)
+        both(gates)
+        got = gather_state(sh, rank, world)
+        check(f"n={n} M={M} gate-by-gate", got, single.get_state() if rank == 0 else None, exact=True)
+
+        # fused inverse / forward QFT across the global qubits
+        both(lambda r: r.set_option(q.OPT_FUSION, 1))
+        both(lambda r: r.inverse_QFT())
+        got = gather_state(sh, rank, world)
+        check(f"n={n} M={M} fused inverse_QFT", got, single.get_state() if rank == 0 else None)
+        both(lambda r: r.QFT())
+        got = gather_state(sh, rank, world)
+        check(f"n={n} M={M} fused QFT", got, single.get_state() if rank == 0 else None)
+
+        # measurement: same index everywhere, bit-exact with the single-GPU scan
+        for rr in (0.0, 0.31, 0.77, 0.999999, 1.5):
+            if rank == 0:
+                keep = single.get_state().copy()
+            a = sh.measure_state(rr)
+            if rank == 0:
+                b = single.measure_state(rr)
+                print(f"[dist] n={n} measure r={rr}: {a} vs {b}", flush=True)
+                if a != b:
+                    failures.append(f"measure {rr}")
+                single.set_state(keep)
+            # restore the sharded state from the single-GPU copy
+            obj = [keep if rank == 0 else None]
+            dist.broadcast_object_list(obj, src=0)
+            nl = sh.local_states
+            sh.set_state(obj[0][rank * nl:(rank + 1) * nl])
+
+        if M:
+            both(lambda r: r.reset_register())
+            both(lambda r: r.quantum_computation(21, 2, q.POW_MODULAR))
+            got = gather_state(sh, rank, world)
+            check(f"n={n} M={M} fused quantum_computation", got, single.get_state() if rank == 0 else None)
+        sh.close()
+        if single is not None:
+            single.close()
+
+    flag = torch.tensor([len(failures)], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if int(flag.item()):
+        if rank == 0:
+            print("DIST_FAIL", failures, flush=True)
+        sys.exit(1)
+    if rank == 0:
+        print("DIST_OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()
