@@ -31,6 +31,8 @@ def gather_state(reg, rank, world):
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(100, exit=True)
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local_rank)
@@ -67,8 +69,9 @@ def main():
         both(prep)
         s = sh.norm2()
         both(lambda r: r.scale(1.0 / math.sqrt(s)))
+        s2 = sh.norm2()                     # collective: every rank calls it
         if rank == 0:
-            assert abs(single.norm2() - sh.norm2()) < 1e-13
+            assert abs(single.norm2() - s2) < 1e-13
 
         # gate by gate, including Hadamards on the global qubits (pairwise exchange)
         both(lambda r: r.set_option(q.OPT_FUSION, 0))
