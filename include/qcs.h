@@ -89,7 +89,8 @@ enum {
     QCS_K_MODEXP_SWEEP = 6,  /* fused H^L + all L a^x mod C gates                    */
     QCS_K_EXCHANGE = 7,      /* global-qubit exchange (multi-GPU)                    */
     QCS_K_SCALE = 8,         /* in-place scaling                     32*2^n B/launch */
-    QCS_K_COUNT = 9
+    QCS_K_DENSE_BLOCK = 9,   /* dense 2^k x 2^k block on the k low qubits (DMMA) 32*2^n B/launch */
+    QCS_K_COUNT = 10
 };
 
 const char *qcs_version(void);
@@ -108,7 +109,8 @@ void qcs_register_destroy(qcs_register *reg);
 /* Sharded register: this process holds shard `rank` of `world_size` = 2^p
  * equal shards; the top p qubits are global.  `comm_id` is the
  * 128-byte id produced by qcs_comm_unique_id on rank 0 and distributed by the
- * launcher (torch.distributed, MPI, a file ...).                            */
+ * launcher (torch.distributed, MPI, a file ...).  One id per sharded register:
+ * an id cannot be reused for a second communicator.                        */
 #define QCS_COMM_ID_BYTES 128
 int qcs_comm_unique_id(void *id_out);
 int qcs_register_create_sharded(qcs_register **out, int L_size, int M_size, int device,
@@ -179,6 +181,13 @@ int qcs_get_state(qcs_register *reg, unsigned long long first, unsigned long lon
                   double *interleaved_out);
 int qcs_set_state(qcs_register *reg, unsigned long long first, unsigned long long count,
                   const double *interleaved_in);
+
+/* Fused dense block: an arbitrary 2^k x 2^k complex matrix U (row-major,
+ * interleaved re/im, k = 3 or 4) applied to qubits 0..k-1 of every basis state,
+ * i.e. what a run of gates on those qubits multiplies out to (generalises
+ * HADAMARD_BASE_MATRIX / C_PHASE_SHIFT_BASE_MATRIX, Q:210-225).  FP64 tensor
+ * cores (DMMA, mma.sync.m8n8k4.f64). */
+int qcs_apply_dense_block(qcs_register *reg, unsigned k, const double *u_interleaved);
 
 /* synthetic benchmark state: amp[i] = (u(2i), u(2i+1)),
  * u(k) = (mix64(seed + k) >> 11) * 2^-53 - 0.5, generated on the device */

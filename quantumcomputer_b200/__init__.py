@@ -18,7 +18,7 @@ NO_ERROR, INSUFFICIENT_MEMORY, BAD_ARGUMENTS, PERIOD_NOT_FOUND, UNKNOWN_ERROR = 
 POW_VERBATIM, POW_MODULAR = 0, 1
 OPT_FUSION, OPT_PROFILE, OPT_TILE_BITS, OPT_MEASURE_SEQUENTIAL, OPT_PIPELINE = 1, 2, 3, 4, 5
 KERNEL_CLASSES = ["hadamard", "cphase", "amodc", "fill", "reduce", "tile_sweep",
-                  "modexp_sweep", "exchange", "scale"]
+                  "modexp_sweep", "exchange", "scale", "dense_block"]
 
 
 class QcsError(RuntimeError):
@@ -208,6 +208,12 @@ class Register:
         """Host -> device copy without the trailing synchronise (pinned source)."""
         _check(self._l.qcs_set_state(self._h, first, float64_array.size // 2,
                                      float64_array.ctypes.data), "set_state")
+
+    def apply_dense_block(self, k, U):
+        """U: (2^k, 2^k) complex matrix applied to qubits 0..k-1 (k = 3 or 4), DMMA kernel."""
+        u = np.ascontiguousarray(np.asarray(U, dtype=np.complex128)).view(np.float64)
+        assert u.size == 2 * (1 << k) ** 2
+        _check(self._l.qcs_apply_dense_block(self._h, k, u.ctypes.data), "apply_dense_block")
 
     def fill_synthetic(self, seed):
         _check(self._l.qcs_fill_synthetic(self._h, seed), "fill_synthetic")

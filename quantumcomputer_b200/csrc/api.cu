@@ -85,7 +85,7 @@ extern "C" const char *qcs_error_string(int code)
 extern "C" const char *qcs_kernel_class_name(int k)
 {
     static const char *names[QCS_K_COUNT] = {"hadamard", "cphase", "amodc", "fill", "reduce",
-                                             "tile_sweep", "modexp_sweep", "exchange", "scale"};
+                                             "tile_sweep", "modexp_sweep", "exchange", "scale", "dense_block"};
     return (k >= 0 && k < QCS_K_COUNT) ? names[k] : "?";
 }
 

@@ -37,9 +37,13 @@ def main():
     local_rank = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ids = [q.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
     failures = []
+
+    def fresh_id():
+        # one NCCL unique id per communicator (per sharded register)
+        ids = [q.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        return ids[0]
 
     def check(name, got, want, exact=False):
         if rank != 0:
@@ -56,7 +60,7 @@ def main():
 
     for (L, M) in [(18, 0), (12, 5), (21, 0)]:
         n = L + M
-        sh = q.Register(L, M, device=local_rank, rank=rank, world_size=world, comm_id=ids[0])
+        sh = q.Register(L, M, device=local_rank, rank=rank, world_size=world, comm_id=fresh_id())
         single = q.Register(L, M, device=local_rank) if rank == 0 else None
 
         def both(fn):

@@ -177,3 +177,36 @@ def test_quantum_computation_on_arbitrary_input_state(qcs, L, M, Cn, a, mode):
         assert rel_l2(fused.get_state(), exact.get_state()) <= TOL
         prof = fused.profile()
         assert prof["modexp_sweep"][0] == 1 and prof["amodc"][0] == 0
+
+
+@pytest.mark.parametrize("k,n", [(3, 6), (4, 7), (3, 14), (4, 16), (4, 22)])
+def test_dense_block_dmma(qcs, oracle_built, k, n):
+    """qcs_apply_dense_block (FP64 tensor cores) == the gates it fuses: the k-qubit inverse
+    QFT on qubits 0..k-1 multiplied out into one 2^k x 2^k matrix, and a random unitary."""
+    R = 1 << k
+    # matrix of inverse_QFT on a k-qubit register, column by column, from the oracle
+    U = np.zeros((R, R), dtype=np.complex128)
+    for j in range(R):
+        o = oracle_built.Restatement(k, 0)
+        e = np.zeros(R, dtype=np.complex128)
+        e[j] = 1.0
+        o.set_state(e)
+        o.inverse_QFT()
+        U[:, j] = o.get_state()
+    rng = np.random.default_rng(k * 100 + n)
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    v /= np.linalg.norm(v)
+    with qcs.Register(n, 0) as dense, qcs.Register(n, 0) as gates:
+        gates.set_option(qcs.OPT_FUSION, 0)
+        dense.set_state(v)
+        gates.set_state(v)
+        dense.apply_dense_block(k, U)
+        gates.inverse_QFT(0, k)
+        assert rel_l2(dense.get_state(), gates.get_state()) <= TOL
+        assert dense.profile()["dense_block"][0] == 1
+        # random unitary vs numpy
+        q_, _ = np.linalg.qr(rng.normal(size=(R, R)) + 1j * rng.normal(size=(R, R)))
+        dense.set_state(v)
+        dense.apply_dense_block(k, q_)
+        want = (v.reshape(-1, R) @ q_.T).reshape(-1)
+        assert rel_l2(dense.get_state(), want) <= TOL
