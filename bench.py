@@ -206,6 +206,8 @@ def run_ours(args):
     reg.set_option(q.OPT_FUSION, 0 if args.no_fusion else 1)
     if args.tile_bits:
         reg.set_option(q.OPT_TILE_BITS, args.tile_bits)
+    if args.prefetch >= 0:
+        reg.set_option(q.OPT_PREFETCH_TILES, args.prefetch)
 
     def barrier():
         reg.synchronize()
@@ -320,6 +322,7 @@ def main():
     ap.add_argument("--qubits", type=int, default=0, help="override n (default 30 + log2(gpus))")
     ap.add_argument("--no-fusion", action="store_true", help="gate-by-gate reference-order kernels")
     ap.add_argument("--tile-bits", type=int, default=0)
+    ap.add_argument("--prefetch", type=int, default=-1, help="L2 prefetch distance in tiles (-1: library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")

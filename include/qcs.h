@@ -75,7 +75,10 @@ enum {
     QCS_OPT_MEASURE_SEQUENTIAL = 4,
     /* 1 (default): fused sweeps use the TMA + mbarrier pipelined kernel where it
      * applies (tile = 2^11 amplitudes); 0: the direct global<->register kernel. */
-    QCS_OPT_PIPELINE = 5
+    QCS_OPT_PIPELINE = 5,
+    /* how many tiles ahead of its TMA load the pipelined sweep prefetches into L2
+     * (0 = off, the default: measured slower on B200, see profiles/README.md) */
+    QCS_OPT_PREFETCH_TILES = 6
 };
 
 /* kernel classes reported by qcs_profile_get */

@@ -171,6 +171,7 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->opt_tile_bits = 0;
     reg->opt_measure_sequential = 0;
     reg->opt_pipeline = 1;
+    reg->opt_prefetch_tiles = 0;     // measured: L2 prefetch slows the sweep down (profiles/README.md)
     reg->d_meas = nullptr;
     reg->launches_total = 0;
     memset(reg->launches, 0, sizeof reg->launches);
@@ -266,6 +267,10 @@ extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
             return QCS_NO_ERROR;
         case QCS_OPT_MEASURE_SEQUENTIAL: reg->opt_measure_sequential = value != 0; return QCS_NO_ERROR;
         case QCS_OPT_PIPELINE: reg->opt_pipeline = value != 0; return QCS_NO_ERROR;
+        case QCS_OPT_PREFETCH_TILES:
+            if (value < 0 || value > 64) return QCS_BAD_ARGUMENTS;
+            reg->opt_prefetch_tiles = (int) value;
+            return QCS_NO_ERROR;
         default: return QCS_BAD_ARGUMENTS;
     }
 }
@@ -279,6 +284,7 @@ extern "C" long long qcs_get_option(const qcs_register *reg, int option)
         case QCS_OPT_TILE_BITS: return reg->opt_tile_bits;
         case QCS_OPT_MEASURE_SEQUENTIAL: return reg->opt_measure_sequential;
         case QCS_OPT_PIPELINE: return reg->opt_pipeline;
+        case QCS_OPT_PREFETCH_TILES: return reg->opt_prefetch_tiles;
         default: return -1;
     }
 }

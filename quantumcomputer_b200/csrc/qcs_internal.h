@@ -41,6 +41,7 @@ struct qcs_register {
     int opt_fusion;
     int opt_profile;
     int opt_tile_bits;
+    int opt_prefetch_tiles;       // L2 prefetch distance of the pipelined sweep (tiles)
     int opt_pipeline;             // 1: TMA/mbarrier pipelined sweep kernel where it applies
     int opt_measure_sequential;   // 1: always use the single-CTA sequential scan
 

@@ -46,6 +46,7 @@ struct pipe_params {
     sweep_desc d;
     uint64_t n_tiles;
     int lo_gap;             // g_lo - a (strided) or -1 (contiguous final sweep)
+    int prefetch;           // tiles ahead of the load that are prefetched into L2 (0: off)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -83,6 +84,11 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
             "r"(smem_u32(dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2)
 {
@@ -154,11 +160,21 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
     if (warp == 0) {
         // ---------------- producer ----------------
         if (lane == 0) {
+            int c0, c1, c2;
+            // the smem ring holds ~2 tiles in flight per SM; an L2 prefetch a few tiles
+            // ahead deepens the HBM pipeline without costing shared memory
+            for (uint64_t k = 0; k < (uint64_t) P.prefetch && k < my_tiles; k++) {
+                tile_coords(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
+                tma_prefetch_3d(&tmap, c0, c1, c2);
+            }
             for (uint64_t k = 0; k < my_tiles; k++) {
                 const int s = (int) (k % kStages);
                 const uint32_t round = (uint32_t) (k / kStages);
+                if (P.prefetch && k + P.prefetch < my_tiles) {
+                    tile_coords(P, P.d.tile_first + blockIdx.x + (k + P.prefetch) * gridDim.x, c0, c1, c2);
+                    tma_prefetch_3d(&tmap, c0, c1, c2);
+                }
                 mbar_wait(&empty[s], (round & 1u) ^ 1u);
-                int c0, c1, c2;
                 tile_coords(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
                 mbar_expect_tx(&full[s], kTileBytes);
                 tma_load_3d(stage_buf + (size_t) s * (1u << kTileBits), &tmap, &full[s], c0, c1, c2);
@@ -259,6 +275,7 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
     pipe_params P;
     P.d = plan.d;
     P.n_tiles = plan.n_tiles;
+    P.prefetch = reg->opt_prefetch_tiles;
     CUtensorMap tmap;
     cuuint64_t dims[3], strides[2];
     cuuint32_t box[3], estr[3] = {1, 1, 1};
