@@ -23,6 +23,13 @@ struct sweep_step {
     int col_off;    // offset of the step's column-twiddle table (in double2)
 };
 
+// a diagonal two-qubit phase gate (c_phase_shift_gate) in fused form: multiply by
+// (c + i s) every amplitude whose GLOBAL index has all bits of `mask` set
+struct diag_gate {
+    unsigned long long mask;
+    double c, s;
+};
+
 struct sweep_desc {
     int a, g_lo, g_hi, t;   // tile = physical bits [0,a) U [g_lo,g_hi); t = a + g_hi - g_lo
     int lo;                 // lowest qubit of the transform (the reference's M_size)
@@ -33,6 +40,9 @@ struct sweep_desc {
     int hadamard_only;      // 1: the stages are bare Hadamards (no phase gates): Walsh-Hadamard sweep
     unsigned long long y_const;   // added to the per-tile y: register bits held by the rank (sharded layouts)
     unsigned long long tile_first; // first tile of this launch (sub-range launches that overlap an exchange)
+    unsigned long long index_or;   // global index bits held by the rank (for the diagonal masks)
+    int n_diag;                    // diagonal gates applied at the end of the sweep
+    const diag_gate *diag;         // device pointer
     double scale;           // (1/sqrt 2)^(stages in this sweep), applied in the last step
     sweep_step step[kMaxSteps];
 };
@@ -123,7 +133,7 @@ __device__ __forceinline__ constexpr int bitrev(int k)
 template <int R>
 __device__ __forceinline__ void external_twiddle(double2 (&x)[R], double2 w)
 {
-    double2 p[R];
+    double2 p[R < 2 ? 2 : R];
     p[1] = w;
 #pragma unroll
     for (int k = 2; k < R; k++) p[k] = (k & 1) ? cmul(p[k - 1], w) : csqr(p[k >> 1]);
@@ -158,7 +168,8 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
                                          const double2 *__restrict__ wcol, double2 wb, const tile_geom G,
                                          const sweep_step S, int t, uint64_t base, bool from_global,
                                          bool to_global, bool apply_scale, double scale,
-                                         unsigned tid, unsigned nthreads)
+                                         unsigned tid, unsigned nthreads, const diag_gate *diag = nullptr,
+                                         int n_diag = 0, uint64_t index_or = 0)
 {
     const unsigned n_cols = 1u << (t - S.r);
     const unsigned low_mask = (1u << S.s) - 1u;
@@ -194,6 +205,20 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
         if (apply_scale) {
 #pragma unroll
             for (int d = 0; d < R; d++) { x[d].x *= scale; x[d].y *= scale; }
+            // diagonal gates of the layer: the elements are in registers and their
+            // full basis-state index is known
+            if (n_diag > 0) {
+                const uint64_t i0 = index_or | base | G.spread(e_base);
+                const uint64_t dstride = 1ull << G.phys(S.s);
+                for (int gi = 0; gi < n_diag; gi++) {
+                    const diag_gate dg = diag[gi];
+#pragma unroll
+                    for (int d = 0; d < R; d++) {
+                        const uint64_t idx = i0 | ((uint64_t) d * dstride);
+                        if ((idx & dg.mask) == dg.mask) x[d] = cmul(x[d], make_double2(dg.c, dg.s));
+                    }
+                }
+            }
         }
         if (to_global) {
             if (S.s == 0 && R >= 2) {
@@ -214,13 +239,15 @@ template <bool INV, bool TW = true>
 __device__ __forceinline__ void dispatch_step(double2 *amp, double2 *tile, const double2 *wcol, double2 wb,
                                               const tile_geom G, const sweep_step S, int t, uint64_t base,
                                               bool from_global, bool to_global, bool apply_scale, double scale,
-                                              unsigned tid, unsigned nthreads)
+                                              unsigned tid, unsigned nthreads, const diag_gate *diag = nullptr,
+                                              int n_diag = 0, uint64_t index_or = 0)
 {
     switch (S.r) {
-        case 4: run_step<16, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
-        case 3: run_step<8, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
-        case 2: run_step<4, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
-        default: run_step<2, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads); break;
+        case 4: run_step<16, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
+        case 3: run_step<8, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
+        case 2: run_step<4, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
+        case 0: run_step<1, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
+        default: run_step<2, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
     }
 }
 
@@ -327,6 +354,9 @@ inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int 
         d.hadamard_only = 0;
         d.y_const = 0;
         d.tile_first = 0;
+        d.index_or = 0;
+        d.n_diag = 0;
+        d.diag = nullptr;
         p.stages = rw.s_hi - rw.s_lo;
         d.scale = pow(0.70710678118654752440, (double) p.stages);
         if (p.stages % 2 == 0) d.scale = ldexp(1.0, -p.stages / 2);      // exact power of two

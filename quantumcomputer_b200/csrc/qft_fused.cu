@@ -82,7 +82,7 @@ k_qft_sweep(double2 *__restrict__ amp, uint64_t n_tiles, const sweep_desc P)
             const sweep_step S = P.step[k];
             const bool first = k == 0, last = k == P.n_steps - 1;
             const double2 wb = wbase[parity * kMaxSteps + k];
-            if (P.hadamard_only) dispatch_step<true, false>(amp, tile, wcol + S.col_off, wb, G, S, P.t, base, first, last, last, P.scale, threadIdx.x, NT);
+            if (P.hadamard_only) dispatch_step<true, false>(amp, tile, wcol + S.col_off, wb, G, S, P.t, base, first, last, last, P.scale, threadIdx.x, NT, P.diag, P.n_diag, P.index_or);
             else if (inv) dispatch_step<true>(amp, tile, wcol + S.col_off, wb, G, S, P.t, base, first, last, last, P.scale, threadIdx.x, NT);
             else dispatch_step<false>(amp, tile, wcol + S.col_off, wb, G, S, P.t, base, first, last, last, P.scale, threadIdx.x, NT);
             if (!last) __syncthreads();

@@ -221,7 +221,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
                 const sweep_step S = P.d.step[st];
                 const bool last = st == P.d.n_steps - 1;
                 const double2 wb = my_wbase[st];
-                if (P.d.hadamard_only) dispatch_step<true, false>(nullptr, tile, wcol + S.col_off, wb, G, S, kTileBits, 0, false, false, last, P.d.scale, tig, kGroupThreads);
+                if (P.d.hadamard_only) dispatch_step<true, false>(nullptr, tile, wcol + S.col_off, wb, G, S, kTileBits, base, false, false, last, P.d.scale, tig, kGroupThreads, P.d.diag, P.d.n_diag, P.d.index_or);
                 else if (inv) dispatch_step<true>(nullptr, tile, wcol + S.col_off, wb, G, S, kTileBits, 0, false, false, last, P.d.scale, tig, kGroupThreads);
                 else dispatch_step<false>(nullptr, tile, wcol + S.col_off, wb, G, S, kTileBits, 0, false, false, last, P.d.scale, tig, kGroupThreads);
                 if (last) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
