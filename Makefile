@@ -24,7 +24,7 @@ all: lib host oracle
 
 lib: $(LIB)
 
-$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/qcs_internal.h include/qcs.h
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/qcs_internal.h $(CSRC)/qft_common.cuh include/qcs.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
 

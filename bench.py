@@ -25,6 +25,7 @@ if ROOT not in sys.path:
 
 SEED = 1234
 CLASS_BYTES_NOTE = {
+    "diag_multi": "32*2^n B per launch (read+write every amplitude, any number of diagonal gates)",
     "hadamard": "32*2^n B per launch (read+write every amplitude)",
     "cphase": "8*2^n B per launch (read+write the |11> quarter)",
     "tile_sweep": "32*2^n B per launch (read+write every amplitude once per sweep)",
@@ -200,14 +201,45 @@ def run_ours(args):
         comm_id = ids[0]
 
     p = int(math.log2(world))
-    n = args.qubits if args.qubits else 30 + p
-    gates = qft_gate_count(n)
+    if args.workload == "layered":
+        # BASELINE configs[3]: random Hadamard / controlled-phase layered circuit, n = 33 on one GPU
+        from quantumcomputer_b200.workloads import apply_gates, layered_circuit
+        n = args.qubits if args.qubits else 33 + p
+        circuit = layered_circuit(n, args.layers)
+        gates = len(circuit)
+        workload = (f"layered circuit (BASELINE configs[3]): {args.layers} layers of H on every qubit + C-phase on "
+                    f"(q, (q+1+d) mod n), n={n}, {gates} gates per step, issued gate by gate through "
+                    f"qcs_hadamard_gate / qcs_c_phase_shift_gate inside qcs_fuse_begin/end")
+    else:
+        n = args.qubits if args.qubits else 30 + p
+        circuit = None
+        gates = qft_gate_count(n)
+        workload = (f"inverse_QFT over all n={n} qubits of a synthetic random state "
+                    f"(BASELINE configs[2]; {gates} gates per step)")
     reg = q.Register(n, 0, device=local_rank, rank=rank, world_size=world, comm_id=comm_id)
     reg.set_option(q.OPT_FUSION, 0 if args.no_fusion else 1)
     if args.tile_bits:
         reg.set_option(q.OPT_TILE_BITS, args.tile_bits)
     if args.prefetch >= 0:
         reg.set_option(q.OPT_PREFETCH_TILES, args.prefetch)
+    if args.pipe_shape >= 0:
+        reg.set_option(q.OPT_PIPE_SHAPE, args.pipe_shape)
+    if args.direct_store >= 0:
+        reg.set_option(q.OPT_DIRECT_STORE, args.direct_store)
+    if args.min_run_bits > 0:
+        reg.set_option(q.OPT_MIN_RUN_BITS, args.min_run_bits)
+
+    if circuit is not None:
+        args.no_cpu_baseline = True                  # the CPU arm times the headline (iqft) workload
+        if 16 * reg.local_states > 32 * 2 ** 30:
+            args.no_e2e = True                       # no 128 GiB pinned host mirror of an n = 33 state
+
+    def one_step():
+        if circuit is None:
+            reg.inverse_QFT()
+        else:
+            with reg.fused():
+                apply_gates(reg, circuit)
 
     def barrier():
         reg.synchronize()
@@ -228,7 +260,7 @@ def run_ours(args):
     norm_in = reg.norm2()
 
     for _ in range(args.warmup):
-        reg.inverse_QFT()
+        one_step()
     barrier()
 
     # ---- device-resident throughput ("value")
@@ -239,7 +271,7 @@ def run_ours(args):
     barrier()
     reg.timer_start()
     for _ in range(args.steps):
-        reg.inverse_QFT()
+        one_step()
     ms = reg.timer_stop()
     barrier()
     clocks = sampler.stop()
@@ -261,7 +293,7 @@ def run_ours(args):
         for step_i in range(e2e_steps):
             reg.timer_start()
             reg.set_state_async(pinned.array)               # H2D from pinned memory
-            reg.inverse_QFT()
+            one_step()
             # the step's result, as in find_period (qc_shor.c:923-928): the measured index (8 bytes D2H)
             result = reg.measure_state(((step_i * 2654435761 + 12345) % 2 ** 32) / 2.0 ** 32)
             t_ms += reg.timer_stop()
@@ -289,15 +321,19 @@ def run_ours(args):
                          "GBps": round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] > 0 else None}
                      for k, v in prof.items() if v[0]}
         line = {
-            "metric": "qft_gates_per_sec", "value": gates * args.steps / (ms * 1e-3), "unit": "gates/s",
+            "metric": "qft_gates_per_sec" if circuit is None else "layered_circuit_gates_per_sec",
+            "value": gates * args.steps / (ms * 1e-3), "unit": "gates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"inverse_QFT over all n={n} qubits of a synthetic random state "
-                                   f"(BASELINE configs[2]; {gates} gates per step)",
+            "config": {"workload": workload,
                        "qubits": n, "gates_per_step": gates, "state_bytes_per_gpu": int(16 * reg.local_states),
                        "fusion": int(reg.get_option(q.OPT_FUSION)), "parallelism": f"top {p} qubits global",
-                       "l2": "state (16 GiB per GPU) is far larger than the 126 MB L2; no flush needed",
+                       "pipe_shape": int(reg.get_option(q.OPT_PIPE_SHAPE)),
+                       "direct_store": int(reg.get_option(q.OPT_DIRECT_STORE)),
+                       "min_run_bits": int(reg.get_option(q.OPT_MIN_RUN_BITS)),
+                       "l2": f"state ({16 * reg.local_states / 2 ** 30:.0f} GiB per GPU) is far larger than the "
+                             f"126 MB L2; no flush needed",
                        "norm_before": norm_in, "norm_after": norm_out},
             "roofline": roofline, "kernels": per_class,
             "gpu_launches": int(launches), "clocks": clocks,
@@ -323,6 +359,12 @@ def main():
     ap.add_argument("--no-fusion", action="store_true", help="gate-by-gate reference-order kernels")
     ap.add_argument("--tile-bits", type=int, default=0)
     ap.add_argument("--prefetch", type=int, default=-1, help="L2 prefetch distance in tiles (-1: library default)")
+    ap.add_argument("--workload", choices=["iqft", "layered"], default="iqft",
+                    help="iqft: BASELINE configs[2] (default, the headline metric); layered: configs[3]")
+    ap.add_argument("--layers", type=int, default=8)
+    ap.add_argument("--pipe-shape", type=int, default=-1)
+    ap.add_argument("--direct-store", type=int, default=-1)
+    ap.add_argument("--min-run-bits", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -78,7 +78,16 @@ enum {
     QCS_OPT_PIPELINE = 5,
     /* how many tiles ahead of its TMA load the pipelined sweep prefetches into L2
      * (0 = off, the default: measured slower on B200, see profiles/README.md) */
-    QCS_OPT_PREFETCH_TILES = 6
+    QCS_OPT_PREFETCH_TILES = 6,
+    /* which instantiated shape of the pipelined sweep runs (tile size, ring depth, consumer
+     * groups; csrc/qft_pipeline.cu kShapes).  Tuning knob; -1 = library default. */
+    QCS_OPT_PIPE_SHAPE = 7,
+    /* 1: the last step of a pipelined sweep stores its registers straight to global memory
+     * instead of going back through shared memory and a TMA store. */
+    QCS_OPT_DIRECT_STORE = 8,
+    /* log2 of the shortest contiguous run of amplitudes a strided tile may use (3 = 128 B,
+     * 4 = 256 B ...): shorter runs leave more tile bits for stages, i.e. fewer sweeps. */
+    QCS_OPT_MIN_RUN_BITS = 9
 };
 
 /* kernel classes reported by qcs_profile_get */
@@ -93,7 +102,8 @@ enum {
     QCS_K_EXCHANGE = 7,      /* global-qubit exchange (multi-GPU)                    */
     QCS_K_SCALE = 8,         /* in-place scaling                     32*2^n B/launch */
     QCS_K_DENSE_BLOCK = 9,   /* dense 2^k x 2^k block on the k low qubits (DMMA) 32*2^n B/launch */
-    QCS_K_COUNT = 10
+    QCS_K_DIAG = 10,         /* several diagonal gates in one pass (gate stream) 32*2^n B/launch */
+    QCS_K_COUNT = 11
 };
 
 const char *qcs_version(void);
@@ -184,6 +194,23 @@ int qcs_get_state(qcs_register *reg, unsigned long long first, unsigned long lon
                   double *interleaved_out);
 int qcs_set_state(qcs_register *reg, unsigned long long first, unsigned long long count,
                   const double *interleaved_in);
+
+/* Deferred gate stream.  Between qcs_fuse_begin and qcs_fuse_end,
+ * qcs_hadamard_gate and qcs_c_phase_shift_gate record their gate instead of
+ * launching it; qcs_fuse_end schedules the recorded run into as few passes over
+ * the state as the gates' commutation rules allow (Hadamards on a run of qubits
+ * = one Walsh-Hadamard tile sweep; diagonal gates ride along in the sweeps'
+ * registers) and launches them.  This is what replaces "one operate_matrix
+ * pass per gate" (Q:370-420) for arbitrary H / C-phase circuits such as the
+ * layered circuit of BASELINE configs[3].  Any other call on the register
+ * flushes the recorded gates first, so results never depend on when the flush
+ * happens.  With QCS_OPT_FUSION = 0 nothing is recorded: every gate runs at
+ * once through the reference-order kernels.  Amplitudes agree with gate-by-gate
+ * application to <= 1e-12 relative L2. */
+int qcs_fuse_begin(qcs_register *reg);
+int qcs_fuse_end(qcs_register *reg);
+/* gates recorded and not yet launched */
+unsigned long long qcs_fuse_pending(const qcs_register *reg);
 
 /* Fused dense block: an arbitrary 2^k x 2^k complex matrix U (row-major,
  * interleaved re/im, k = 3 or 4) applied to qubits 0..k-1 of every basis state,

@@ -17,8 +17,9 @@ from . import _lib
 NO_ERROR, INSUFFICIENT_MEMORY, BAD_ARGUMENTS, PERIOD_NOT_FOUND, UNKNOWN_ERROR = range(5)
 POW_VERBATIM, POW_MODULAR = 0, 1
 OPT_FUSION, OPT_PROFILE, OPT_TILE_BITS, OPT_MEASURE_SEQUENTIAL, OPT_PIPELINE, OPT_PREFETCH_TILES = 1, 2, 3, 4, 5, 6
+OPT_PIPE_SHAPE, OPT_DIRECT_STORE, OPT_MIN_RUN_BITS = 7, 8, 9
 KERNEL_CLASSES = ["hadamard", "cphase", "amodc", "fill", "reduce", "tile_sweep",
-                  "modexp_sweep", "exchange", "scale", "dense_block"]
+                  "modexp_sweep", "exchange", "scale", "dense_block", "diag_multi"]
 
 
 class QcsError(RuntimeError):
@@ -208,6 +209,30 @@ class Register:
         """Host -> device copy without the trailing synchronise (pinned source)."""
         _check(self._l.qcs_set_state(self._h, first, float64_array.size // 2,
                                      float64_array.ctypes.data), "set_state")
+
+    # ---- deferred gate stream
+    def fuse_begin(self):
+        _check(self._l.qcs_fuse_begin(self._h), "fuse_begin")
+
+    def fuse_end(self):
+        _check(self._l.qcs_fuse_end(self._h), "fuse_end")
+
+    @property
+    def fuse_pending(self):
+        return int(self._l.qcs_fuse_pending(self._h))
+
+    def fused(self):
+        """``with reg.fused(): ...`` records H / C-phase gates and launches them fused on exit."""
+        reg = self
+
+        class _Ctx:
+            def __enter__(self):
+                reg.fuse_begin()
+                return reg
+
+            def __exit__(self, *exc):
+                reg.fuse_end()
+        return _Ctx()
 
     def apply_dense_block(self, k, U):
         """U: (2^k, 2^k) complex matrix applied to qubits 0..k-1 (k = 3 or 4), DMMA kernel."""

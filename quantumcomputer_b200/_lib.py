@@ -47,6 +47,9 @@ SIGNATURES = [
     ("qcs_nonzero_states", C.c_int, [_vp, _ull, C.POINTER(_ull), _dp, C.POINTER(_ull)]),
     ("qcs_get_state", C.c_int, [_vp, _ull, _ull, _vp]),
     ("qcs_set_state", C.c_int, [_vp, _ull, _ull, _vp]),
+    ("qcs_fuse_begin", C.c_int, [_vp]),
+    ("qcs_fuse_end", C.c_int, [_vp]),
+    ("qcs_fuse_pending", _ull, [_vp]),
     ("qcs_apply_dense_block", C.c_int, [_vp, _u, _vp]),
     ("qcs_fill_synthetic", C.c_int, [_vp, _ull]),
     ("qcs_scale", C.c_int, [_vp, C.c_double]),

@@ -85,7 +85,8 @@ extern "C" const char *qcs_error_string(int code)
 extern "C" const char *qcs_kernel_class_name(int k)
 {
     static const char *names[QCS_K_COUNT] = {"hadamard", "cphase", "amodc", "fill", "reduce",
-                                             "tile_sweep", "modexp_sweep", "exchange", "scale", "dense_block"};
+                                             "tile_sweep", "modexp_sweep", "exchange", "scale", "dense_block",
+                                             "diag_multi"};
     return (k >= 0 && k < QCS_K_COUNT) ? names[k] : "?";
 }
 
@@ -126,6 +127,20 @@ extern "C" int qcs_host_free(void *ptr)
     QCS_CUDA(cudaFreeHost(ptr));
     return QCS_NO_ERROR;
 }
+
+// every entry point that is not a recordable gate first launches what the gate
+// stream has recorded (circuit.cu), so deferral is never observable
+#define QCS_ENTER(reg)                                              \
+    do {                                                            \
+        if (!(reg)) return QCS_BAD_ARGUMENTS;                       \
+        QCS_CUDA(cudaSetDevice((reg)->device));                     \
+        if (!(reg)->queue.empty()) QCS_TRY(qcs_fuse_flush(reg));    \
+    } while (0)
+#define QCS_ENTER_GATE(reg)                         \
+    do {                                            \
+        if (!(reg)) return QCS_BAD_ARGUMENTS;       \
+        QCS_CUDA(cudaSetDevice((reg)->device));     \
+    } while (0)
 
 // ---------------------------------------------------------------------------
 // register life-cycle
@@ -171,8 +186,14 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->opt_tile_bits = 0;
     reg->opt_measure_sequential = 0;
     reg->opt_pipeline = 1;
+    reg->opt_pipe_shape = -1;
+    reg->opt_direct_store = 0;
+    reg->opt_min_run_bits = 4;
     reg->opt_prefetch_tiles = 0;     // measured: L2 prefetch slows the sweep down (profiles/README.md)
     reg->d_meas = nullptr;
+    reg->fusing = 0;
+    reg->d_diag = nullptr;
+    reg->d_diag_cap = 0;
     reg->launches_total = 0;
     memset(reg->launches, 0, sizeof reg->launches);
     memset(reg->alg_bytes, 0, sizeof reg->alg_bytes);
@@ -239,6 +260,7 @@ extern "C" void qcs_register_destroy(qcs_register *reg)
     if (reg->d_partials) cudaFree(reg->d_partials);
     if (reg->d_small) cudaFree(reg->d_small);
     if (reg->d_meas) cudaFree(reg->d_meas);
+    if (reg->d_diag) cudaFree(reg->d_diag);
     if (reg->h_small) cudaFreeHost(reg->h_small);
     if (reg->stream) cudaStreamDestroy(reg->stream);
     delete reg;
@@ -254,7 +276,7 @@ extern "C" int qcs_world_size(const qcs_register *reg) { return reg ? reg->world
 
 extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
 {
-    if (!reg) return QCS_BAD_ARGUMENTS;
+    QCS_ENTER(reg);      // recorded gates are launched under the options they were recorded with
     switch (option) {
         case QCS_OPT_FUSION: reg->opt_fusion = value != 0; return QCS_NO_ERROR;
         case QCS_OPT_PROFILE:
@@ -267,6 +289,15 @@ extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
             return QCS_NO_ERROR;
         case QCS_OPT_MEASURE_SEQUENTIAL: reg->opt_measure_sequential = value != 0; return QCS_NO_ERROR;
         case QCS_OPT_PIPELINE: reg->opt_pipeline = value != 0; return QCS_NO_ERROR;
+        case QCS_OPT_PIPE_SHAPE:
+            if (value < -1 || value > 16) return QCS_BAD_ARGUMENTS;
+            reg->opt_pipe_shape = (int) value;
+            return QCS_NO_ERROR;
+        case QCS_OPT_DIRECT_STORE: reg->opt_direct_store = value != 0; return QCS_NO_ERROR;
+        case QCS_OPT_MIN_RUN_BITS:
+            if (value < 1 || value > 7) return QCS_BAD_ARGUMENTS;
+            reg->opt_min_run_bits = (int) value;
+            return QCS_NO_ERROR;
         case QCS_OPT_PREFETCH_TILES:
             if (value < 0 || value > 64) return QCS_BAD_ARGUMENTS;
             reg->opt_prefetch_tiles = (int) value;
@@ -284,6 +315,9 @@ extern "C" long long qcs_get_option(const qcs_register *reg, int option)
         case QCS_OPT_TILE_BITS: return reg->opt_tile_bits;
         case QCS_OPT_MEASURE_SEQUENTIAL: return reg->opt_measure_sequential;
         case QCS_OPT_PIPELINE: return reg->opt_pipeline;
+        case QCS_OPT_PIPE_SHAPE: return reg->opt_pipe_shape;
+        case QCS_OPT_DIRECT_STORE: return reg->opt_direct_store;
+        case QCS_OPT_MIN_RUN_BITS: return reg->opt_min_run_bits;
         case QCS_OPT_PREFETCH_TILES: return reg->opt_prefetch_tiles;
         default: return -1;
     }
@@ -291,17 +325,10 @@ extern "C" long long qcs_get_option(const qcs_register *reg, int option)
 
 extern "C" int qcs_synchronize(qcs_register *reg)
 {
-    if (!reg) return QCS_BAD_ARGUMENTS;
-    QCS_CUDA(cudaSetDevice(reg->device));
+    QCS_ENTER(reg);
     QCS_CUDA(cudaStreamSynchronize(reg->stream));
     return QCS_NO_ERROR;
 }
-
-#define QCS_ENTER(reg)                              \
-    do {                                            \
-        if (!(reg)) return QCS_BAD_ARGUMENTS;       \
-        QCS_CUDA(cudaSetDevice((reg)->device));     \
-    } while (0)
 
 // ---------------------------------------------------------------------------
 // single gates
@@ -321,7 +348,12 @@ static int hadamard_any(qcs_register *reg, unsigned q)
 
 extern "C" int qcs_hadamard_gate(qcs_register *reg, unsigned qubit_num)
 {
-    QCS_ENTER(reg);
+    QCS_ENTER_GATE(reg);
+    if (reg->fusing && reg->opt_fusion) {
+        if (qubit_num >= reg->n) return QCS_BAD_ARGUMENTS;
+        reg->queue.push_back({0, qubit_num, qubit_num, 0.0, 0.0});
+        return QCS_NO_ERROR;
+    }
     return hadamard_any(reg, qubit_num);
 }
 
@@ -342,8 +374,13 @@ static int cphase_any(qcs_register *reg, unsigned c, unsigned q, double co, doub
 
 extern "C" int qcs_c_phase_shift_gate(qcs_register *reg, unsigned c_qubit_num, unsigned qubit_num, double theta)
 {
-    QCS_ENTER(reg);
+    QCS_ENTER_GATE(reg);
     // gsl_complex_polar(1.0, theta), qc_shor.c:526: host libm like the reference
+    if (reg->fusing && reg->opt_fusion) {
+        if (c_qubit_num >= reg->n || qubit_num >= reg->n) return QCS_BAD_ARGUMENTS;
+        reg->queue.push_back({1, c_qubit_num, qubit_num, 1.0 * cos(theta), 1.0 * sin(theta)});
+        return QCS_NO_ERROR;
+    }
     return cphase_any(reg, c_qubit_num, qubit_num, 1.0 * cos(theta), 1.0 * sin(theta));
 }
 

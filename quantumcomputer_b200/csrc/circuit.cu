@@ -1,0 +1,300 @@
+// circuit.cu -- deferred gate stream: hadamard_gate / c_phase_shift_gate calls
+// recorded between qcs_fuse_begin and qcs_fuse_end are scheduled into as few
+// passes over HBM as their commutation rules allow, then launched.
+//
+// The reference applies every gate as one full pass over the state
+// (operate_matrix, qc_shor.c:370-420).  Two facts let a run of gates share a
+// pass:
+//   * Hadamards on different qubits commute, so a set of them is a
+//     Walsh-Hadamard transform on those index bits: contiguous runs of qubits
+//     become the tile sweeps of qft_fused.cu / qft_pipeline.cu with the
+//     twiddles compiled out;
+//   * controlled phase gates are diagonal (qc_shor.c:220-225): they commute
+//     with each other and with a Hadamard on any qubit they do not touch.  A
+//     diagonal gate may therefore be applied at the end of ANY pass between the
+//     last earlier Hadamard on one of its qubits and the next later one; it is
+//     attached to the least loaded tile sweep in that window, where the
+//     amplitudes are in registers and their full index is known.
+//
+// The stream is cut into groups  { set of H qubits } -> { diagonal gates }  by a
+// single scan in program order; nothing is reordered across a gate it does not
+// commute with.  Amplitudes agree with gate-by-gate application to ~1e-15
+// relative (bar 1e-12); with QCS_OPT_FUSION = 0 qcs_fuse_begin records nothing
+// and every gate runs immediately through the reference-order kernels.
+#include "qft_common.cuh"
+
+#include <string.h>
+
+namespace {
+
+using qft::diag_gate;
+using qft::sweep_plan;
+
+constexpr int kThreads = 256;
+constexpr int kMaxDiagPerSweep = 48;   // beyond this a sweep turns FP64-bound: spill to a diagonal pass
+
+// one pass over the shard applying a list of diagonal gates: 32 B per amplitude
+// for any number of gates (each gate alone would cost 8 B per amplitude)
+__global__ void __launch_bounds__(kThreads)
+k_diag_multi(double2 *__restrict__ amp, uint64_t n_pairs, const diag_gate *__restrict__ gates, int n_gates)
+{
+    extern __shared__ diag_gate sg[];
+    for (int i = threadIdx.x; i < n_gates; i += kThreads) sg[i] = gates[i];
+    __syncthreads();
+    const uint64_t stride = (uint64_t) gridDim.x * kThreads;
+    for (uint64_t p = (uint64_t) blockIdx.x * kThreads + threadIdx.x; p < n_pairs; p += stride) {
+        double2 x0, x1;
+        x0 = qft::ld256_lo(amp + 2 * p, x1);
+        const uint64_t i0 = 2 * p, i1 = 2 * p + 1;
+        for (int g = 0; g < n_gates; g++) {
+            const diag_gate dg = sg[g];
+            const double2 ph = make_double2(dg.c, dg.s);
+            if ((i0 & dg.mask) == dg.mask) x0 = qft::cmul(x0, ph);
+            if ((i1 & dg.mask) == dg.mask) x1 = qft::cmul(x1, ph);
+        }
+        qft::st256(amp + 2 * p, x0, x1);
+    }
+}
+
+struct pass {
+    int type;                   // 0: tile sweep, 1: single local Hadamard kernel, 2: global Hadamard(s)
+    int group;
+    uint64_t hmask;             // qubits this pass applies H to
+    sweep_plan plan;            // type 0
+    unsigned q;                 // type 1
+    bool top_stages;            // type 2: all global qubits at once through the qubit-swap pipeline
+    std::vector<diag_gate> in_sweep;    // applied in the last step of the sweep (type 0)
+    std::vector<int> after;             // recorded gates applied by standalone kernels after the pass
+};
+
+int ensure_diag_capacity(qcs_register *reg, size_t gates)
+{
+    if (gates <= reg->d_diag_cap) return QCS_NO_ERROR;
+    // the old array may still be read by sweeps in flight on the stream
+    QCS_CUDA(cudaStreamSynchronize(reg->stream));
+    if (reg->d_diag) QCS_CUDA(cudaFree(reg->d_diag));
+    reg->d_diag = nullptr;
+    reg->d_diag_cap = 0;
+    size_t cap = 256;
+    while (cap < gates) cap *= 2;
+    QCS_CUDA(cudaMalloc(&reg->d_diag, cap * sizeof(diag_gate)));
+    reg->d_diag_cap = cap;
+    return QCS_NO_ERROR;
+}
+
+// the part of a recorded diagonal gate that lives in this shard: global qubits
+// contribute the rank's (constant) bit.  false: the gate is the identity here.
+bool localise(const qcs_register *reg, const qcs_pending_gate &g, diag_gate &out)
+{
+    uint64_t mask = 0;
+    const unsigned both[2] = {g.q0, g.q1};
+    for (int k = 0; k < 2; k++) {
+        const unsigned b = both[k];
+        if (b < reg->n_local) mask |= 1ull << b;
+        else if (!(((unsigned) reg->rank >> (b - reg->n_local)) & 1u)) return false;
+    }
+    out.mask = mask;
+    out.c = g.c;
+    out.s = g.s;
+    return true;
+}
+
+int launch_diag_list(qcs_register *reg, const std::vector<qcs_pending_gate> &queue, const std::vector<int> &list,
+                     diag_gate *d_slot, std::vector<diag_gate> &host_stage)
+{
+    if (list.empty()) return QCS_NO_ERROR;
+    if (list.size() <= 3) {
+        // 8 B per amplitude each: cheaper than one 32 B pass, and reference-order arithmetic
+        for (int gi : list) {
+            const qcs_pending_gate &g = queue[(size_t) gi];
+            diag_gate dg;
+            if (!localise(reg, g, dg)) continue;
+            unsigned bits[2];
+            int nb = 0;
+            for (unsigned b = 0; b < reg->n_local; b++)
+                if ((dg.mask >> b) & 1ull) bits[nb++] = b;
+            QCS_TRY(qcs_k_phase_masked(reg, nb, nb > 0 ? bits[0] : 0, nb > 1 ? bits[1] : 0, dg.c, dg.s));
+        }
+        return QCS_NO_ERROR;
+    }
+    host_stage.clear();
+    for (int gi : list) {
+        diag_gate dg;
+        if (localise(reg, queue[(size_t) gi], dg)) host_stage.push_back(dg);
+    }
+    if (host_stage.empty()) return QCS_NO_ERROR;
+    for (size_t at = 0; at < host_stage.size(); at += 1024) {
+        const int n = (int) std::min<size_t>(1024, host_stage.size() - at);
+        QCS_CUDA(cudaMemcpyAsync(d_slot + at, host_stage.data() + at, (size_t) n * sizeof(diag_gate),
+                                 cudaMemcpyHostToDevice, reg->stream));
+        const uint64_t n_pairs = reg->N_local >> 1;
+        uint64_t grid = (n_pairs + kThreads - 1) / kThreads;
+        const uint64_t cap = (uint64_t) reg->sm_count * 8;
+        if (grid > cap) grid = cap;
+        if (grid < 1) grid = 1;
+        qcs_launch_begin(reg, QCS_K_DIAG, 32.0 * (double) reg->N_local);
+        k_diag_multi<<<(unsigned) grid, kThreads, (size_t) n * sizeof(diag_gate), reg->stream>>>(
+            reg->amp, n_pairs, d_slot + at, n);
+        QCS_TRY(qcs_launch_end(reg, QCS_K_DIAG, "k_diag_multi"));
+    }
+    return QCS_NO_ERROR;
+}
+
+}  // namespace
+
+int qcs_fuse_flush(qcs_register *reg)
+{
+    if (reg->queue.empty()) return QCS_NO_ERROR;
+    std::vector<qcs_pending_gate> queue;
+    queue.swap(reg->queue);             // the per-gate calls below must not see a pending queue
+
+    // ---- 1. groups: {H set} then {diagonal gates}, cut in program order
+    struct group { uint64_t hset = 0, dmask = 0; std::vector<int> diag; };
+    std::vector<group> groups(1);
+    std::vector<int> group_of(queue.size(), 0);
+    for (size_t i = 0; i < queue.size(); i++) {
+        const qcs_pending_gate &g = queue[i];
+        if (g.kind == 0) {
+            const uint64_t bit = 1ull << g.q0;
+            if ((groups.back().hset | groups.back().dmask) & bit) groups.emplace_back();
+            groups.back().hset |= bit;
+        } else {
+            groups.back().dmask |= (1ull << g.q0) | (1ull << g.q1);
+            groups.back().diag.push_back((int) i);
+        }
+        group_of[i] = (int) groups.size() - 1;
+    }
+
+    // ---- 2. passes
+    std::vector<pass> passes;
+    const uint64_t local_mask = reg->n_local >= 64 ? ~0ull : ((1ull << reg->n_local) - 1ull);
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        const uint64_t hl = groups[gi].hset & local_mask, hg = groups[gi].hset & ~local_mask;
+        if (hg) {
+            // sharded register, Hadamards on global qubits: all p of them at once through the
+            // qubit-swap pipeline when that is the whole global set, else pairwise exchanges
+            pass ps;
+            ps.type = 2;
+            ps.group = (int) gi;
+            ps.hmask = hg;
+            const uint64_t all_global = ((reg->n >= 64 ? ~0ull : ((1ull << reg->n) - 1ull))) & ~local_mask;
+            ps.top_stages = hg == all_global && reg->n_local >= 2u * (unsigned) reg->p_global;
+            passes.push_back(ps);
+        }
+        unsigned b = reg->n_local;
+        while (b > 0) {
+            // contiguous runs of H qubits, top run first (the order the sweep planner works in)
+            if (!((hl >> (b - 1)) & 1ull)) { b--; continue; }
+            unsigned hi = b;
+            while (b > 0 && ((hl >> (b - 1)) & 1ull)) b--;
+            const unsigned lo = b;
+            if (hi - lo == 1) {
+                pass ps;
+                ps.type = 1;
+                ps.group = (int) gi;
+                ps.hmask = 1ull << lo;
+                ps.q = lo;
+                passes.push_back(ps);
+                continue;
+            }
+            std::vector<sweep_plan> plans;
+            QCS_TRY(qcs_plan_hadamard_sweeps(reg, lo, hi, plans));
+            for (const sweep_plan &pl : plans) {
+                pass ps;
+                ps.type = 0;
+                ps.group = (int) gi;
+                ps.plan = pl;
+                ps.hmask = 0;
+                for (int k = 0; k < pl.d.n_steps; k++)
+                    for (int r = 0; r < pl.d.step[k].r; r++) ps.hmask |= 1ull << (pl.d.step[k].low_phys + r);
+                passes.push_back(ps);
+            }
+        }
+    }
+
+    // ---- 3. place every diagonal gate
+    std::vector<int> before_all;        // no pass may precede them
+    for (size_t i = 0; i < queue.size(); i++) {
+        if (queue[i].kind != 1) continue;
+        const uint64_t bits = (1ull << queue[i].q0) | (1ull << queue[i].q1);
+        const int g = group_of[i];
+        int earliest = -1, latest = (int) passes.size() - 1;
+        for (int p = 0; p < (int) passes.size(); p++) {
+            if (!(passes[(size_t) p].hmask & bits)) continue;
+            if (passes[(size_t) p].group <= g) earliest = p;
+            else { latest = p - 1; break; }
+        }
+        int best = -1;
+        for (int p = earliest < 0 ? 0 : earliest; p <= latest; p++) {
+            const pass &ps = passes[(size_t) p];
+            if (ps.type != 0 || (int) ps.in_sweep.size() >= kMaxDiagPerSweep) continue;
+            if (best < 0 || ps.in_sweep.size() < passes[(size_t) best].in_sweep.size()) best = p;
+        }
+        if (best >= 0) {
+            diag_gate dg;
+            if (localise(reg, queue[i], dg)) passes[(size_t) best].in_sweep.push_back(dg);
+        } else if (earliest < 0) {
+            before_all.push_back((int) i);
+        } else {
+            passes[(size_t) earliest].after.push_back((int) i);
+        }
+    }
+
+    // ---- 4. launch
+    size_t need = 1024;
+    for (const pass &ps : passes) need += ps.in_sweep.size();
+    QCS_TRY(ensure_diag_capacity(reg, need));
+    diag_gate *d_all = (diag_gate *) reg->d_diag;
+    // the array may still be read by the sweeps of the previous flush: reuse is stream-ordered
+    // (the copies below are issued on the same stream as those sweeps)
+    std::vector<diag_gate> stage;
+    diag_gate *d_scratch = d_all;       // first 1024 slots: standalone diagonal passes
+    size_t at = 1024;
+    {
+        std::vector<diag_gate> all;
+        for (const pass &ps : passes) all.insert(all.end(), ps.in_sweep.begin(), ps.in_sweep.end());
+        if (!all.empty())
+            QCS_CUDA(cudaMemcpyAsync(d_all + at, all.data(), all.size() * sizeof(diag_gate), cudaMemcpyHostToDevice,
+                                     reg->stream));
+    }
+    QCS_TRY(launch_diag_list(reg, queue, before_all, d_scratch, stage));
+    for (pass &ps : passes) {
+        if (ps.type == 0) {
+            ps.plan.d.n_diag = (int) ps.in_sweep.size();
+            ps.plan.d.diag = ps.in_sweep.empty() ? nullptr : d_all + at;
+            at += ps.in_sweep.size();
+            QCS_TRY(qcs_launch_sweep_plan(reg, ps.plan));
+        } else if (ps.type == 1) {
+            QCS_TRY(qcs_k_hadamard_local(reg, ps.q));
+        } else if (ps.top_stages) {
+            QCS_TRY(qcs_dist_top_stages(reg, 0, true, true));
+        } else {
+            for (unsigned q = reg->n_local; q < reg->n; q++)
+                if ((ps.hmask >> q) & 1ull) QCS_TRY(qcs_dist_hadamard_global(reg, q));
+        }
+        QCS_TRY(launch_diag_list(reg, queue, ps.after, d_scratch, stage));
+    }
+    return QCS_NO_ERROR;
+}
+
+extern "C" int qcs_fuse_begin(qcs_register *reg)
+{
+    if (!reg) return QCS_BAD_ARGUMENTS;
+    if (reg->fusing) return QCS_BAD_ARGUMENTS;
+    reg->fusing = 1;
+    return QCS_NO_ERROR;
+}
+
+extern "C" int qcs_fuse_end(qcs_register *reg)
+{
+    if (!reg) return QCS_BAD_ARGUMENTS;
+    if (!reg->fusing) return QCS_BAD_ARGUMENTS;
+    reg->fusing = 0;
+    QCS_CUDA(cudaSetDevice(reg->device));
+    return qcs_fuse_flush(reg);
+}
+
+extern "C" unsigned long long qcs_fuse_pending(const qcs_register *reg)
+{
+    return reg ? (unsigned long long) reg->queue.size() : 0ull;
+}

@@ -19,6 +19,13 @@ struct qcs_profile_slot {
     int kind;
 };
 
+// a gate recorded between qcs_fuse_begin and qcs_fuse_end (circuit.cu)
+struct qcs_pending_gate {
+    int kind;               // 0: hadamard_gate(q0), 1: c_phase_shift_gate(q0, q1, theta)
+    unsigned q0, q1;
+    double c, s;            // cos(theta), sin(theta) as the reference forms them (qc_shor.c:526)
+};
+
 struct qcs_register {
     int L_size, M_size;
     unsigned n;             // total qubits
@@ -43,7 +50,16 @@ struct qcs_register {
     int opt_tile_bits;
     int opt_prefetch_tiles;       // L2 prefetch distance of the pipelined sweep (tiles)
     int opt_pipeline;             // 1: TMA/mbarrier pipelined sweep kernel where it applies
+    int opt_pipe_shape;           // which instantiated pipeline shape (qft_pipeline.cu kShapes)
+    int opt_direct_store;         // 1: last step of a pipelined sweep stores registers -> global
+    int opt_min_run_bits;         // log2 of the shortest contiguous run (amplitudes) a strided tile may use
     int opt_measure_sequential;   // 1: always use the single-CTA sequential scan
+
+    // deferred gate stream (qcs_fuse_begin .. qcs_fuse_end)
+    int fusing;
+    std::vector<qcs_pending_gate> queue;
+    void *d_diag;                 // device array of qft::diag_gate for the sweeps in flight
+    size_t d_diag_cap;            // in gates
 
     // accounting
     unsigned long long launches_total;
@@ -114,6 +130,10 @@ int qcs_fused_top_sweep(qcs_register *reg, double2 *buf, unsigned c, unsigned p,
                         unsigned long long y_const, bool inverse, bool hadamard_only, cudaStream_t stream);
 // H on the L register, then all L controlled a^(2^k) mod C gates in one block-local sweep
 int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, unsigned n_gates);
+
+// ---- deferred gate stream: circuit.cu ------------------------------------------
+// schedule and launch every recorded gate (no-op when the queue is empty)
+int qcs_fuse_flush(qcs_register *reg);
 
 // ---- multi-GPU: dist.cu ---------------------------------------------------
 int qcs_dist_init(qcs_register *reg, const void *comm_id);

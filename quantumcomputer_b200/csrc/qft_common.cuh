@@ -133,7 +133,7 @@ __device__ __forceinline__ constexpr int bitrev(int k)
 template <int R>
 __device__ __forceinline__ void external_twiddle(double2 (&x)[R], double2 w)
 {
-    double2 p[R < 2 ? 2 : R];
+    double2 p[R];
     p[1] = w;
 #pragma unroll
     for (int k = 2; k < R; k++) p[k] = (k & 1) ? cmul(p[k - 1], w) : csqr(p[k >> 1]);
@@ -246,7 +246,6 @@ __device__ __forceinline__ void dispatch_step(double2 *amp, double2 *tile, const
         case 4: run_step<16, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
         case 3: run_step<8, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
         case 2: run_step<4, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
-        case 0: run_step<1, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
         default: run_step<2, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
     }
 }
@@ -325,15 +324,25 @@ inline void split_even(int total, int cap, std::vector<int> &out)
     for (int i = 0; i < m; i++) out.push_back(total / m + (i < total % m ? 1 : 0));
 }
 
-// sweeps of the inverse transform on qubits [lo, hi), top stages first
-inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int a_req, std::vector<sweep_plan> &plans)
+// sweeps of the inverse transform on qubits [lo, hi), top stages first.  Strided tiles keep
+// the low `a` index bits (a contiguous run of 2^a amplitudes) for coalescing and spend the
+// other t - a bits on stages: `a` is the largest value in [a_min, a_pref] ... that still gives
+// the fewest sweeps (a longer run never costs a sweep).
+inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int a_min, std::vector<sweep_plan> &plans)
 {
     plans.clear();
     const int t = std::min<int>(T, (int) n_local);
-    const int a = (int) n_local <= t ? t : std::min(a_req, t - 1);
+    const int first_hi = std::max<int>((int) lo, t);
+    int a = t;
+    if ((int) n_local > t) {
+        a_min = std::max(1, std::min(a_min, t - 1));
+        const int rest = std::max(0, (int) hi - first_hi);
+        auto sweeps_with = [&](int aa) { return (rest + (t - aa) - 1) / (t - aa); };
+        a = a_min;
+        while (a + 1 <= std::min(7, t - 1) && sweeps_with(a + 1) == sweeps_with(a_min)) a++;
+    }
     int top = (int) hi;
     std::vector<int> sizes;
-    const int first_hi = std::max<int>((int) lo, t);
     if ((int) n_local > t) split_even(top - first_hi, t - a, sizes);
     struct raw { int a, g_lo, g_hi, s_lo, s_hi; };
     std::vector<raw> raws;
@@ -400,3 +409,9 @@ inline void make_forward(std::vector<sweep_plan> &plans)
 }
 
 }  // namespace qft
+
+// ---- host entry points of qft_fused.cu used by the gate-stream scheduler (circuit.cu)
+// Walsh-Hadamard tile sweeps for H on every qubit of [lo, hi) (hi <= n_local), top run first
+int qcs_plan_hadamard_sweeps(const qcs_register *reg, unsigned lo, unsigned hi, std::vector<qft::sweep_plan> &plans);
+// launch one planned sweep on the register's shard and stream
+int qcs_launch_sweep_plan(qcs_register *reg, const qft::sweep_plan &plan);

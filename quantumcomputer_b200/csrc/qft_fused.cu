@@ -54,7 +54,7 @@ k_qft_sweep(double2 *__restrict__ amp, uint64_t n_tiles, const sweep_desc P)
     const bool inv = P.inverse != 0;
 
     // per-column part of the external twiddle: fixed for the whole kernel
-    for (int k = 0; k < P.n_steps; k++) {
+    for (int k = 0; k < (P.hadamard_only ? 0 : P.n_steps); k++) {
         const sweep_step S = P.step[k];
         const unsigned n_cols = 1u << (P.t - S.r);
         for (unsigned c = threadIdx.x; c < n_cols; c += NT) {
@@ -107,10 +107,17 @@ int launch_sweep(qcs_register *reg, const sweep_target &tg, const sweep_plan &p,
 
 }  // namespace
 
+int qcs_pipeline_tile_bits(const qcs_register *reg);
 bool qcs_pipeline_supports(const qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &p);
 int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &plan);
 
 static int launch_plan_inner(qcs_register *reg, const sweep_target &tg, const sweep_plan &p);
+
+static int default_tile_bits(const qcs_register *reg)
+{
+    if (reg->opt_tile_bits) return reg->opt_tile_bits;
+    return reg->opt_pipeline ? qcs_pipeline_tile_bits(reg) : 11;
+}
 
 static int launch_plan(qcs_register *reg, const sweep_target &tg, const sweep_plan &p)
 {
@@ -136,9 +143,9 @@ static int run_sweeps(qcs_register *reg, unsigned lo, unsigned hi, bool inverse,
         fprintf(stderr, "qcs: fused sweeps over global qubits are handled by the distributed schedule\n");
         return QCS_BAD_ARGUMENTS;
     }
-    const int T = reg->opt_tile_bits ? reg->opt_tile_bits : 11;
+    const int T = default_tile_bits(reg);
     std::vector<sweep_plan> plans;
-    plan_inverse(reg->n_local, lo, hi, T, 4, plans);
+    plan_inverse(reg->n_local, lo, hi, T, reg->opt_min_run_bits, plans);
     if (!inverse) make_forward(plans);
     const sweep_target tg = {reg->amp, reg->n_local, reg->stream};
     for (sweep_plan &p : plans) {
@@ -146,6 +153,23 @@ static int run_sweeps(qcs_register *reg, unsigned lo, unsigned hi, bool inverse,
         QCS_TRY(launch_plan(reg, tg, p));
     }
     return QCS_NO_ERROR;
+}
+
+int qcs_plan_hadamard_sweeps(const qcs_register *reg, unsigned lo, unsigned hi, std::vector<sweep_plan> &plans)
+{
+    if (lo >= hi || hi > reg->n_local) return QCS_BAD_ARGUMENTS;
+    plan_inverse(reg->n_local, lo, hi, default_tile_bits(reg), reg->opt_min_run_bits, plans);
+    for (sweep_plan &p : plans) {
+        p.d.hadamard_only = 1;
+        p.d.wcol_total = 0;             // no twiddle tables
+    }
+    return QCS_NO_ERROR;
+}
+
+int qcs_launch_sweep_plan(qcs_register *reg, const sweep_plan &plan)
+{
+    const sweep_target tg = {reg->amp, reg->n_local, reg->stream};
+    return launch_plan(reg, tg, plan);
 }
 
 // One sweep over the top `p` index bits of `buf` (2^(c+p) amplitudes laid out
@@ -157,7 +181,7 @@ int qcs_fused_top_sweep(qcs_register *reg, double2 *buf, unsigned c, unsigned p,
 {
     if (p < 1 || p > 4) return QCS_BAD_ARGUMENTS;
     const unsigned nb = c + p;
-    int T = reg->opt_tile_bits ? reg->opt_tile_bits : 11;
+    int T = default_tile_bits(reg);
     if ((unsigned) T > nb) T = (int) nb;
     sweep_plan pl;
     sweep_desc &d = pl.d;

@@ -35,18 +35,18 @@ namespace {
 
 using namespace qft;
 
-constexpr int kStages = 6;
-constexpr int kGroups = 3;
-constexpr int kGroupThreads = 128;
-constexpr int kThreads = 64 + kGroups * kGroupThreads;     // 448
-constexpr int kTileBits = 11;                               // 2048 amplitudes = 32 KiB per stage
-constexpr uint32_t kTileBytes = 16u << kTileBits;
-
+// pipeline shapes (template parameters of the kernel): log2 tile size, ring depth,
+// consumer groups and threads per group
 struct pipe_params {
     sweep_desc d;
     uint64_t n_tiles;
     int lo_gap;             // g_lo - a (strided) or -1 (contiguous final sweep)
     int prefetch;           // tiles ahead of the load that are prefetched into L2 (0: off)
+    int n_boxes;            // TMA boxes per tile (a box has at most 256 rows)
+    int box_rows;
+    uint32_t box_bytes;
+    int direct_store;       // 1: the last step stores registers -> global, no TMA store
+    double2 *amp;           // direct_store target
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -96,11 +96,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void 
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
-__device__ __forceinline__ void group_barrier(int group)
+__device__ __forceinline__ void group_barrier(int group, int threads)
 {
-    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kGroupThreads) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(threads) : "memory");
 }
 
+template <int TB>
 __device__ __forceinline__ void tile_coords(const pipe_params &P, uint64_t tix, int &c0, int &c1, int &c2)
 {
     if (P.lo_gap >= 0) {
@@ -109,21 +110,25 @@ __device__ __forceinline__ void tile_coords(const pipe_params &P, uint64_t tix, 
         c2 = (int) (tix >> P.lo_gap);
     } else {
         c0 = 0;
-        c1 = (int) (tix << (kTileBits - 3));                                // rows of 8 amplitudes
+        c1 = (int) (tix << (TB - 3));                                       // rows of 8 amplitudes
         c2 = 0;
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int TB, int STAGES, int GROUPS, int GT>
+__global__ void __launch_bounds__(64 + GROUPS * GT, 1)
 k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
 {
+    constexpr int kThreads = 64 + GROUPS * GT;
+    constexpr uint32_t kTileBytes = 16u << TB;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // kStages tiles; the 128-byte swizzle of the final sweep needs 1024-byte alignment
+    // STAGES tiles; the 128-byte swizzle of the final sweep needs 1024-byte alignment
     double2 *stage_buf = (double2 *) (smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-    double2 *wcol = stage_buf + (size_t) kStages * (1u << kTileBits);
-    double2 *wbase = wcol + P.d.wcol_total;                                 // [kGroups][kMaxSteps]
-    uint64_t *bars = (uint64_t *) (wbase + kGroups * kMaxSteps);
-    uint64_t *full = bars, *computed = bars + kStages, *empty = bars + 2 * kStages;
+    double2 *wcol = stage_buf + (size_t) STAGES * (1u << TB);
+    double2 *wbase = wcol + P.d.wcol_total;                                 // [GROUPS][kMaxSteps]
+    uint64_t *bars = (uint64_t *) (wbase + GROUPS * kMaxSteps);
+    uint64_t *full = bars, *computed = bars + STAGES, *empty = bars + 2 * STAGES;
+    diag_gate *sdiag = (diag_gate *) (bars + 3 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     tile_geom G;
@@ -133,7 +138,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
     const bool inv = P.d.inverse != 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) {
+        for (int s = 0; s < STAGES; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&computed[s], 1);
             mbar_init(&empty[s], 1);
@@ -142,16 +147,19 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     }
     // per-column part of the external twiddle: fixed for the whole kernel
-    for (int k = 0; k < P.d.n_steps; k++) {
-        const sweep_step S = P.d.step[k];
-        const unsigned n_cols = 1u << (kTileBits - S.r);
-        for (unsigned c = threadIdx.x; c < n_cols; c += kThreads) {
-            const unsigned e_base = ((c >> S.s) << (S.s + S.r)) | (c & ((1u << S.s) - 1u));
-            uint64_t y = 0;
-            if (S.low_phys > P.d.lo) y = (G.spread(e_base) & ((1ull << S.low_phys) - 1ull)) >> P.d.lo;
-            wcol[S.col_off + c] = unit_phase(y, S.j, inv);
+    if (!P.d.hadamard_only) {
+        for (int k = 0; k < P.d.n_steps; k++) {
+            const sweep_step S = P.d.step[k];
+            const unsigned n_cols = 1u << (TB - S.r);
+            for (unsigned c = threadIdx.x; c < n_cols; c += kThreads) {
+                const unsigned e_base = ((c >> S.s) << (S.s + S.r)) | (c & ((1u << S.s) - 1u));
+                uint64_t y = 0;
+                if (S.low_phys > P.d.lo) y = (G.spread(e_base) & ((1ull << S.low_phys) - 1ull)) >> P.d.lo;
+                wcol[S.col_off + c] = unit_phase(y, S.j, inv);
+            }
         }
     }
+    for (int i = threadIdx.x; i < P.d.n_diag; i += kThreads) sdiag[i] = P.d.diag[i];
     __syncthreads();
 
     // this CTA's tiles: tix = blockIdx.x + k * gridDim.x, k = 0 .. my_tiles-1
@@ -161,35 +169,38 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
         // ---------------- producer ----------------
         if (lane == 0) {
             int c0, c1, c2;
-            // the smem ring holds ~2 tiles in flight per SM; an L2 prefetch a few tiles
-            // ahead deepens the HBM pipeline without costing shared memory
+            // optional L2 prefetch a few tiles ahead of the shared-memory ring
             for (uint64_t k = 0; k < (uint64_t) P.prefetch && k < my_tiles; k++) {
-                tile_coords(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
-                tma_prefetch_3d(&tmap, c0, c1, c2);
+                tile_coords<TB>(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
+                for (int b = 0; b < P.n_boxes; b++) tma_prefetch_3d(&tmap, c0, c1 + b * P.box_rows, c2);
             }
             for (uint64_t k = 0; k < my_tiles; k++) {
-                const int s = (int) (k % kStages);
-                const uint32_t round = (uint32_t) (k / kStages);
+                const int s = (int) (k % STAGES);
+                const uint32_t round = (uint32_t) (k / STAGES);
                 if (P.prefetch && k + P.prefetch < my_tiles) {
-                    tile_coords(P, P.d.tile_first + blockIdx.x + (k + P.prefetch) * gridDim.x, c0, c1, c2);
-                    tma_prefetch_3d(&tmap, c0, c1, c2);
+                    tile_coords<TB>(P, P.d.tile_first + blockIdx.x + (k + P.prefetch) * gridDim.x, c0, c1, c2);
+                    for (int b = 0; b < P.n_boxes; b++) tma_prefetch_3d(&tmap, c0, c1 + b * P.box_rows, c2);
                 }
                 mbar_wait(&empty[s], (round & 1u) ^ 1u);
-                tile_coords(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
+                tile_coords<TB>(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
                 mbar_expect_tx(&full[s], kTileBytes);
-                tma_load_3d(stage_buf + (size_t) s * (1u << kTileBits), &tmap, &full[s], c0, c1, c2);
+                unsigned char *dst = (unsigned char *) (stage_buf + (size_t) s * (1u << TB));
+                for (int b = 0; b < P.n_boxes; b++)
+                    tma_load_3d(dst + (size_t) b * P.box_bytes, &tmap, &full[s], c0, c1 + b * P.box_rows, c2);
             }
         }
     } else if (warp == 1) {
         // ---------------- store issuer ----------------
-        if (lane == 0) {
+        if (lane == 0 && !P.direct_store) {
             for (uint64_t k = 0; k < my_tiles; k++) {
-                const int s = (int) (k % kStages);
-                const uint32_t round = (uint32_t) (k / kStages);
+                const int s = (int) (k % STAGES);
+                const uint32_t round = (uint32_t) (k / STAGES);
                 mbar_wait(&computed[s], round & 1u);
                 int c0, c1, c2;
-                tile_coords(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
-                tma_store_3d(&tmap, stage_buf + (size_t) s * (1u << kTileBits), c0, c1, c2);
+                tile_coords<TB>(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
+                const unsigned char *src = (const unsigned char *) (stage_buf + (size_t) s * (1u << TB));
+                for (int b = 0; b < P.n_boxes; b++)
+                    tma_store_3d(&tmap, src + (size_t) b * P.box_bytes, c0, c1 + b * P.box_rows, c2);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 mbar_arrive(&empty[s]);
@@ -198,36 +209,40 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
         }
     } else {
         // ---------------- consumers ----------------
-        const int group = (warp - 2) / (kGroupThreads / 32);
-        const unsigned tig = threadIdx.x - 64 - group * kGroupThreads;
+        const int group = (warp - 2) / (GT / 32);
+        const unsigned tig = threadIdx.x - 64 - group * GT;
         double2 *my_wbase = wbase + group * kMaxSteps;
         const int lo_gap = P.lo_gap;
-        for (uint64_t k = group; k < my_tiles; k += kGroups) {
-            const int s = (int) (k % kStages);
-            const uint32_t round = (uint32_t) (k / kStages);
+        const bool direct = P.direct_store != 0;
+        for (uint64_t k = group; k < my_tiles; k += GROUPS) {
+            const int s = (int) (k % STAGES);
+            const uint32_t round = (uint32_t) (k / STAGES);
             const uint64_t tix = P.d.tile_first + blockIdx.x + k * gridDim.x;
             const uint64_t base = lo_gap >= 0 ? (((tix >> lo_gap) << P.d.g_hi) | ((tix & ((1ull << lo_gap) - 1ull)) << P.d.a))
-                                              : (tix << kTileBits);
-            if (tig < (unsigned) P.d.n_steps) {
+                                              : (tix << TB);
+            if (!P.d.hadamard_only && tig < (unsigned) P.d.n_steps) {
                 const sweep_step S = P.d.step[tig];
                 uint64_t y = 0;
                 if (S.low_phys > P.d.lo) y = (base & ((1ull << S.low_phys) - 1ull)) >> P.d.lo;
                 my_wbase[tig] = unit_phase(y + P.d.y_const, S.j, inv);
             }
-            group_barrier(group);
-            double2 *tile = stage_buf + (size_t) s * (1u << kTileBits);
+            group_barrier(group, GT);
+            double2 *tile = stage_buf + (size_t) s * (1u << TB);
             mbar_wait(&full[s], round & 1u);
             for (int st = 0; st < P.d.n_steps; st++) {
                 const sweep_step S = P.d.step[st];
                 const bool last = st == P.d.n_steps - 1;
+                const bool to_global = last && direct;
                 const double2 wb = my_wbase[st];
-                if (P.d.hadamard_only) dispatch_step<true, false>(nullptr, tile, wcol + S.col_off, wb, G, S, kTileBits, base, false, false, last, P.d.scale, tig, kGroupThreads, P.d.diag, P.d.n_diag, P.d.index_or);
-                else if (inv) dispatch_step<true>(nullptr, tile, wcol + S.col_off, wb, G, S, kTileBits, 0, false, false, last, P.d.scale, tig, kGroupThreads);
-                else dispatch_step<false>(nullptr, tile, wcol + S.col_off, wb, G, S, kTileBits, 0, false, false, last, P.d.scale, tig, kGroupThreads);
-                if (last) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
-                group_barrier(group);
+                if (P.d.hadamard_only) dispatch_step<true, false>(P.amp, tile, wcol + S.col_off, wb, G, S, TB, base, false, to_global, last, P.d.scale, tig, GT, sdiag, P.d.n_diag, P.d.index_or);
+                else if (inv) dispatch_step<true>(P.amp, tile, wcol + S.col_off, wb, G, S, TB, base, false, to_global, last, P.d.scale, tig, GT);
+                else dispatch_step<false>(P.amp, tile, wcol + S.col_off, wb, G, S, TB, base, false, to_global, last, P.d.scale, tig, GT);
+                if (last && !direct) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
+                group_barrier(group, GT);
             }
-            if (tig == 0) mbar_arrive(&computed[s]);
+            // direct store: the tile left through the registers, the stage is free as soon as
+            // every thread of the group has read it
+            if (tig == 0) mbar_arrive(direct ? &empty[s] : &computed[s]);
         }
     }
 }
@@ -251,18 +266,62 @@ encode_fn_t get_encode()
 
 }  // namespace
 
+// ---------------------------------------------------------------------------
+// host side: the kernel shapes that are instantiated and how a plan maps to one
+// ---------------------------------------------------------------------------
+namespace {
+
+struct pipe_shape { int tb, stages, groups, gt; };
+constexpr pipe_shape kShapes[] = {
+    {11, 6, 3, 128},    // 0: three groups of 128, each owning every third tile
+    {11, 6, 1, 384},    // 1: all consumers on one tile at a time
+    {11, 6, 2, 192},    // 2
+    {12, 3, 1, 384},    // 3: 64 KiB tiles: one sweep fewer at n = 30
+    {12, 3, 2, 192},    // 4
+    {11, 6, 1, 256},    // 5
+    {12, 3, 1, 256},    // 6
+};
+constexpr int kNumShapes = (int) (sizeof kShapes / sizeof kShapes[0]);
+
+size_t pipe_smem(const pipe_shape &sh, const qft::sweep_desc &d)
+{
+    return (size_t) sh.stages * ((size_t) 16 << sh.tb) + 16 * (size_t) d.wcol_total + 16 * (size_t) sh.groups * kMaxSteps +
+           8 * 3 * (size_t) sh.stages + sizeof(diag_gate) * (size_t) d.n_diag + 1024;
+}
+
+template <int TB, int STAGES, int GROUPS, int GT>
+int launch_shape(qcs_register *reg, const CUtensorMap &tmap, const pipe_params &P, size_t smem, cudaStream_t stream)
+{
+    auto kern = k_qft_sweep_tma<TB, STAGES, GROUPS, GT>;
+    QCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    uint64_t grid = (uint64_t) reg->sm_count;
+    if (grid > P.n_tiles) grid = P.n_tiles;
+    qcs_launch_begin(reg, QCS_K_TILE_SWEEP, 32.0 * (double) (P.n_tiles << TB));
+    kern<<<(unsigned) grid, 64 + GROUPS * GT, smem, stream>>>(tmap, P);
+    return qcs_launch_end(reg, QCS_K_TILE_SWEEP, "k_qft_sweep_tma");
+}
+
+}  // namespace
+
+int qcs_pipeline_tile_bits(const qcs_register *reg)
+{
+    const int v = reg->opt_pipe_shape >= 0 && reg->opt_pipe_shape < kNumShapes ? reg->opt_pipe_shape : 0;
+    return kShapes[v].tb;
+}
+
 // true when the pipelined kernel can run this sweep
 bool qcs_pipeline_supports(const qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &p)
 {
-    if (p.d.t != kTileBits || tg.n_bits < 14) return false;
+    const pipe_shape sh = kShapes[reg->opt_pipe_shape >= 0 && reg->opt_pipe_shape < kNumShapes ? reg->opt_pipe_shape : 0];
+    if (p.d.t != sh.tb || tg.n_bits < (unsigned) sh.tb + 3) return false;
     const bool strided = p.d.g_lo > p.d.a;
-    if (strided && (p.d.a < 1 || p.d.a > 7 || p.d.g_hi - p.d.g_lo > 8 || p.d.g_lo + 1 > 31)) return false;
-    // the layout TMA writes (linear, or 128-byte swizzle for the contiguous sweep)
-    // must make every step's shared-memory access conflict-free
-    if (conflict_cost(p.d, strided ? 28 : 3, true) != 0) return false;
-    const size_t smem = (size_t) kStages * kTileBytes + 16 * (size_t) p.d.wcol_total + 16 * kGroups * kMaxSteps +
-                        8 * 3 * kStages + 1024;
-    return smem <= reg->smem_optin;
+    // a TMA box row is 2^(a+1) doubles (32 B .. 2 KiB); coordinates are 32-bit
+    if (strided && (p.d.a < 1 || p.d.a > 7 || p.d.g_lo + 1 > 31)) return false;
+    // the linear layout TMA writes for a strided tile must make every step conflict-free; the
+    // contiguous sweep takes the 128-byte hardware swizzle (conflict-free for every step except a
+    // radix-16 step on bits 0..3, which is 2-way conflicted)
+    if (strided && conflict_cost(p.d, 28, true) != 0) return false;
+    return pipe_smem(sh, p.d) <= reg->smem_optin;
 }
 
 int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &plan)
@@ -272,41 +331,49 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
         fprintf(stderr, "qcs: cuTensorMapEncodeTiled is unavailable\n");
         return QCS_UNKNOWN_ERROR;
     }
+    const int shape_id = reg->opt_pipe_shape >= 0 && reg->opt_pipe_shape < kNumShapes ? reg->opt_pipe_shape : 0;
+    const pipe_shape sh = kShapes[shape_id];
     pipe_params P;
     P.d = plan.d;
     P.n_tiles = plan.n_tiles;
     P.prefetch = reg->opt_prefetch_tiles;
+    P.direct_store = reg->opt_direct_store ? 1 : 0;
+    P.amp = tg.amp;
     CUtensorMap tmap;
     cuuint64_t dims[3], strides[2];
     cuuint32_t box[3], estr[3] = {1, 1, 1};
     CUtensorMapSwizzle swz;
     const bool strided = plan.d.g_lo > plan.d.a;
+    unsigned rows;
     if (strided) {
         const int g = plan.d.g_hi - plan.d.g_lo;
+        rows = 1u << g;
         dims[0] = 2ull << plan.d.g_lo;                       // doubles below g_lo
-        dims[1] = 1ull << g;
+        dims[1] = rows;
         dims[2] = 1ull << (tg.n_bits - (unsigned) plan.d.g_hi);
         strides[0] = 16ull << plan.d.g_lo;
         strides[1] = 16ull << plan.d.g_hi;
         box[0] = 2u << plan.d.a;
-        box[1] = 1u << g;
-        box[2] = 1;
         swz = CU_TENSOR_MAP_SWIZZLE_NONE;
         P.lo_gap = plan.d.g_lo - plan.d.a;
         P.d.sw = 28;                                         // no XOR
     } else {
+        rows = 1u << (sh.tb - 3);
         dims[0] = 16;                                        // 128 B rows
         dims[1] = (1ull << tg.n_bits) >> 3;
         dims[2] = 1;
         strides[0] = 128;
         strides[1] = 128ull * dims[1];
         box[0] = 16;
-        box[1] = 1u << (kTileBits - 3);
-        box[2] = 1;
         swz = CU_TENSOR_MAP_SWIZZLE_128B;
         P.lo_gap = -1;
         P.d.sw = 3;
     }
+    P.box_rows = rows < 256u ? (int) rows : 256;             // a box dimension is at most 256
+    P.n_boxes = (int) (rows / (unsigned) P.box_rows);
+    P.box_bytes = (uint32_t) (((size_t) 16 << sh.tb) / (size_t) P.n_boxes);
+    box[1] = (cuuint32_t) P.box_rows;
+    box[2] = 1;
     CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, tg.amp, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -314,12 +381,14 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
         fprintf(stderr, "qcs: cuTensorMapEncodeTiled failed (%d)\n", (int) cr);
         return QCS_UNKNOWN_ERROR;
     }
-    const size_t smem = (size_t) kStages * kTileBytes + 16 * (size_t) P.d.wcol_total + 16 * kGroups * kMaxSteps +
-                        8 * 3 * kStages + 1024;
-    QCS_CUDA(cudaFuncSetAttribute(k_qft_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    uint64_t grid = (uint64_t) reg->sm_count;
-    if (grid > plan.n_tiles) grid = plan.n_tiles;
-    qcs_launch_begin(reg, QCS_K_TILE_SWEEP, 32.0 * (double) (plan.n_tiles << kTileBits));
-    k_qft_sweep_tma<<<(unsigned) grid, kThreads, smem, tg.stream>>>(tmap, P);
-    return qcs_launch_end(reg, QCS_K_TILE_SWEEP, "k_qft_sweep_tma");
+    const size_t smem = pipe_smem(sh, P.d);
+    switch (shape_id) {
+        case 1: return launch_shape<11, 6, 1, 384>(reg, tmap, P, smem, tg.stream);
+        case 2: return launch_shape<11, 6, 2, 192>(reg, tmap, P, smem, tg.stream);
+        case 3: return launch_shape<12, 3, 1, 384>(reg, tmap, P, smem, tg.stream);
+        case 4: return launch_shape<12, 3, 2, 192>(reg, tmap, P, smem, tg.stream);
+        case 5: return launch_shape<11, 6, 1, 256>(reg, tmap, P, smem, tg.stream);
+        case 6: return launch_shape<12, 3, 1, 256>(reg, tmap, P, smem, tg.stream);
+        default: return launch_shape<11, 6, 3, 128>(reg, tmap, P, smem, tg.stream);
+    }
 }

@@ -46,6 +46,19 @@ def test_mt19937_kat3(host):
     assert host.qcsh_rng_uniform(g) == 0.92961608665063977      # KAT-1's r
 
 
+def test_workload_generator_uses_the_same_stream():
+    """quantumcomputer_b200.workloads draws the layered circuit's angles from the same MT19937."""
+    from quantumcomputer_b200.workloads import layered_circuit, mt19937_uniforms
+    gold = load_golden("scalars.json")["mt19937"]
+    for key, seed in (("seed5489_first_uniform", 5489), ("seed0_first_uniform", 0), ("seed4357_first_uniform", 4357)):
+        assert [u.hex() for u in mt19937_uniforms(seed, len(gold[key]))] == gold[key]
+    assert mt19937_uniforms(12345, 1)[0] == 0.92961608665063977
+    assert len(mt19937_uniforms(7, 1500)) == 1500          # crosses two state regenerations
+    gates = layered_circuit(33, 8)
+    assert len(gates) == 528 and gates[0] == ("h", 0) and gates[33][:3] == ("cp", 0, 1)
+    assert gates[66 * 7 + 33 + 32][:3] == ("cp", 32, (32 + 1 + 7) % 33)
+
+
 def test_gcd_and_read_omega(host):
     g = load_golden("scalars.json")
     for e in g["gcd"]:
