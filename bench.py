@@ -224,8 +224,6 @@ def run_ours(args):
         reg.set_option(q.OPT_PREFETCH_TILES, args.prefetch)
     if args.pipe_shape >= 0:
         reg.set_option(q.OPT_PIPE_SHAPE, args.pipe_shape)
-    if args.direct_store >= 0:
-        reg.set_option(q.OPT_DIRECT_STORE, args.direct_store)
     if args.min_run_bits > 0:
         reg.set_option(q.OPT_MIN_RUN_BITS, args.min_run_bits)
 
@@ -330,7 +328,6 @@ def run_ours(args):
                        "qubits": n, "gates_per_step": gates, "state_bytes_per_gpu": int(16 * reg.local_states),
                        "fusion": int(reg.get_option(q.OPT_FUSION)), "parallelism": f"top {p} qubits global",
                        "pipe_shape": int(reg.get_option(q.OPT_PIPE_SHAPE)),
-                       "direct_store": int(reg.get_option(q.OPT_DIRECT_STORE)),
                        "min_run_bits": int(reg.get_option(q.OPT_MIN_RUN_BITS)),
                        "l2": f"state ({16 * reg.local_states / 2 ** 30:.0f} GiB per GPU) is far larger than the "
                              f"126 MB L2; no flush needed",
@@ -363,7 +360,6 @@ def main():
                     help="iqft: BASELINE configs[2] (default, the headline metric); layered: configs[3]")
     ap.add_argument("--layers", type=int, default=8)
     ap.add_argument("--pipe-shape", type=int, default=-1)
-    ap.add_argument("--direct-store", type=int, default=-1)
     ap.add_argument("--min-run-bits", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -74,7 +74,7 @@ enum {
      * sequential rounding exactly (same index, see csrc/measure.cu). */
     QCS_OPT_MEASURE_SEQUENTIAL = 4,
     /* 1 (default): fused sweeps use the TMA + mbarrier pipelined kernel where it
-     * applies (tile = 2^11 amplitudes); 0: the direct global<->register kernel. */
+     * applies (tile = 2^12 amplitudes by default); 0: the direct global<->register kernel. */
     QCS_OPT_PIPELINE = 5,
     /* how many tiles ahead of its TMA load the pipelined sweep prefetches into L2
      * (0 = off, the default: measured slower on B200, see profiles/README.md) */
@@ -82,12 +82,10 @@ enum {
     /* which instantiated shape of the pipelined sweep runs (tile size, ring depth, consumer
      * groups; csrc/qft_pipeline.cu kShapes).  Tuning knob; -1 = library default. */
     QCS_OPT_PIPE_SHAPE = 7,
-    /* 1: the last step of a pipelined sweep stores its registers straight to global memory
-     * instead of going back through shared memory and a TMA store. */
-    QCS_OPT_DIRECT_STORE = 8,
     /* log2 of the shortest contiguous run of amplitudes a strided tile may use (3 = 128 B,
-     * 4 = 256 B ...): shorter runs leave more tile bits for stages, i.e. fewer sweeps. */
-    QCS_OPT_MIN_RUN_BITS = 9
+     * the default; 4 = 256 B ...): shorter runs leave more tile bits for stages, i.e. fewer
+     * sweeps. */
+    QCS_OPT_MIN_RUN_BITS = 8
 };
 
 /* kernel classes reported by qcs_profile_get */

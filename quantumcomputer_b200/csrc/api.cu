@@ -187,8 +187,7 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->opt_measure_sequential = 0;
     reg->opt_pipeline = 1;
     reg->opt_pipe_shape = -1;
-    reg->opt_direct_store = 0;
-    reg->opt_min_run_bits = 4;
+    reg->opt_min_run_bits = 3;
     reg->opt_prefetch_tiles = 0;     // measured: L2 prefetch slows the sweep down (profiles/README.md)
     reg->d_meas = nullptr;
     reg->fusing = 0;
@@ -293,7 +292,6 @@ extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
             if (value < -1 || value > 16) return QCS_BAD_ARGUMENTS;
             reg->opt_pipe_shape = (int) value;
             return QCS_NO_ERROR;
-        case QCS_OPT_DIRECT_STORE: reg->opt_direct_store = value != 0; return QCS_NO_ERROR;
         case QCS_OPT_MIN_RUN_BITS:
             if (value < 1 || value > 7) return QCS_BAD_ARGUMENTS;
             reg->opt_min_run_bits = (int) value;
@@ -316,7 +314,6 @@ extern "C" long long qcs_get_option(const qcs_register *reg, int option)
         case QCS_OPT_MEASURE_SEQUENTIAL: return reg->opt_measure_sequential;
         case QCS_OPT_PIPELINE: return reg->opt_pipeline;
         case QCS_OPT_PIPE_SHAPE: return reg->opt_pipe_shape;
-        case QCS_OPT_DIRECT_STORE: return reg->opt_direct_store;
         case QCS_OPT_MIN_RUN_BITS: return reg->opt_min_run_bits;
         case QCS_OPT_PREFETCH_TILES: return reg->opt_prefetch_tiles;
         default: return -1;

@@ -51,7 +51,6 @@ struct qcs_register {
     int opt_prefetch_tiles;       // L2 prefetch distance of the pipelined sweep (tiles)
     int opt_pipeline;             // 1: TMA/mbarrier pipelined sweep kernel where it applies
     int opt_pipe_shape;           // which instantiated pipeline shape (qft_pipeline.cu kShapes)
-    int opt_direct_store;         // 1: last step of a pipelined sweep stores registers -> global
     int opt_min_run_bits;         // log2 of the shortest contiguous run (amplitudes) a strided tile may use
     int opt_measure_sequential;   // 1: always use the single-CTA sequential scan
 

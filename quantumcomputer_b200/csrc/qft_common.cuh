@@ -21,6 +21,7 @@ struct sweep_step {
     int j;          // stage index of the step's top bit (physical bit - lo)
     int low_phys;   // physical position of the step's lowest bit
     int col_off;    // offset of the step's column-twiddle table (in double2)
+    int notw;       // 1: no register bit lies below the step (y == 0): the external twiddle is 1
 };
 
 // a diagonal two-qubit phase gate (c_phase_shift_gate) in fused form: multiply by
@@ -43,7 +44,9 @@ struct sweep_desc {
     unsigned long long index_or;   // global index bits held by the rank (for the diagonal masks)
     int n_diag;                    // diagonal gates applied at the end of the sweep
     const diag_gate *diag;         // device pointer
-    double scale;           // (1/sqrt 2)^(stages in this sweep), applied in the last step
+    double scale;           // applied in the last step (1.0: nothing to do); the planner puts the
+                            // whole (1/sqrt 2)^stages of a transform on its last sweep, where it
+                            // is an exact power of two whenever the stage count is even
     sweep_step step[kMaxSteps];
 };
 
@@ -191,20 +194,27 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
             for (int d = 0; d < R; d++) x[d] = tile[G.swz(e_base + ((unsigned) d << S.s))];
         }
         if (TW) {
-            const double2 w = cmul(wb, wcol[c]);
-            if (INV) {
-                dif_inverse<R, true>(x);
-                external_twiddle<R>(x, w);
+            if (S.notw) {
+                if (INV) dif_inverse<R, true>(x);
+                else dit_forward<R, true>(x);
             } else {
-                external_twiddle<R>(x, w);
-                dit_forward<R, true>(x);
+                const double2 w = cmul(wb, wcol[c]);
+                if (INV) {
+                    dif_inverse<R, true>(x);
+                    external_twiddle<R>(x, w);
+                } else {
+                    external_twiddle<R>(x, w);
+                    dit_forward<R, true>(x);
+                }
             }
         } else {
             dif_inverse<R, false>(x);       // H on r qubits in any order: a Walsh-Hadamard butterfly
         }
         if (apply_scale) {
+            if (scale != 1.0) {
 #pragma unroll
-            for (int d = 0; d < R; d++) { x[d].x *= scale; x[d].y *= scale; }
+                for (int d = 0; d < R; d++) { x[d].x *= scale; x[d].y *= scale; }
+            }
             // diagonal gates of the layer: the elements are in registers and their
             // full basis-state index is known
             if (n_diag > 0) {
@@ -367,8 +377,7 @@ inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int 
         d.n_diag = 0;
         d.diag = nullptr;
         p.stages = rw.s_hi - rw.s_lo;
-        d.scale = pow(0.70710678118654752440, (double) p.stages);
-        if (p.stages % 2 == 0) d.scale = ldexp(1.0, -p.stages / 2);      // exact power of two
+        d.scale = 1.0;
         std::vector<int> rs;
         split_even(p.stages, 4, rs);
         d.n_steps = (int) rs.size();
@@ -379,6 +388,7 @@ inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int 
             S.low_phys = l - S.r;
             S.s = S.low_phys < d.a ? S.low_phys : d.a + (S.low_phys - d.g_lo);
             S.j = (l - 1) - (int) lo;
+            S.notw = S.low_phys <= (int) lo ? 1 : 0;
             S.col_off = off;
             off += 1 << (d.t - S.r);
             l -= S.r;
@@ -387,6 +397,11 @@ inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int 
         d.sw = choose_swizzle(d);
         p.n_tiles = 1ull << (n_local - (unsigned) d.t);
         plans.push_back(p);
+    }
+    // one scaling for the whole transform, on its last sweep
+    if (!plans.empty()) {
+        const int total = (int) hi - (int) lo;
+        plans.back().d.scale = total % 2 == 0 ? ldexp(1.0, -total / 2) : ldexp(0.70710678118654752440, -(total - 1) / 2);
     }
 }
 

@@ -203,6 +203,7 @@ int qcs_fused_top_sweep(qcs_register *reg, double2 *buf, unsigned c, unsigned p,
     d.step[0].low_phys = (int) c;
     d.step[0].j = (int) (reg->n - 1) - (int) lo;
     d.step[0].col_off = 0;
+    d.step[0].notw = 0;
     d.wcol_total = 1 << (d.t - (int) p);
     d.sw = 28;
     pl.n_tiles = 1ull << (nb - (unsigned) T);

@@ -45,8 +45,6 @@ struct pipe_params {
     int n_boxes;            // TMA boxes per tile (a box has at most 256 rows)
     int box_rows;
     uint32_t box_bytes;
-    int direct_store;       // 1: the last step stores registers -> global, no TMA store
-    double2 *amp;           // direct_store target
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -119,6 +117,7 @@ template <int TB, int STAGES, int GROUPS, int GT>
 __global__ void __launch_bounds__(64 + GROUPS * GT, 1)
 k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
 {
+    static_assert(STAGES % GROUPS == 0, "a ring stage must always be consumed by the same group");
     constexpr int kThreads = 64 + GROUPS * GT;
     constexpr uint32_t kTileBytes = 16u << TB;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -191,7 +190,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
         }
     } else if (warp == 1) {
         // ---------------- store issuer ----------------
-        if (lane == 0 && !P.direct_store) {
+        if (lane == 0) {
             for (uint64_t k = 0; k < my_tiles; k++) {
                 const int s = (int) (k % STAGES);
                 const uint32_t round = (uint32_t) (k / STAGES);
@@ -213,7 +212,6 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
         const unsigned tig = threadIdx.x - 64 - group * GT;
         double2 *my_wbase = wbase + group * kMaxSteps;
         const int lo_gap = P.lo_gap;
-        const bool direct = P.direct_store != 0;
         for (uint64_t k = group; k < my_tiles; k += GROUPS) {
             const int s = (int) (k % STAGES);
             const uint32_t round = (uint32_t) (k / STAGES);
@@ -232,17 +230,14 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
             for (int st = 0; st < P.d.n_steps; st++) {
                 const sweep_step S = P.d.step[st];
                 const bool last = st == P.d.n_steps - 1;
-                const bool to_global = last && direct;
                 const double2 wb = my_wbase[st];
-                if (P.d.hadamard_only) dispatch_step<true, false>(P.amp, tile, wcol + S.col_off, wb, G, S, TB, base, false, to_global, last, P.d.scale, tig, GT, sdiag, P.d.n_diag, P.d.index_or);
-                else if (inv) dispatch_step<true>(P.amp, tile, wcol + S.col_off, wb, G, S, TB, base, false, to_global, last, P.d.scale, tig, GT);
-                else dispatch_step<false>(P.amp, tile, wcol + S.col_off, wb, G, S, TB, base, false, to_global, last, P.d.scale, tig, GT);
-                if (last && !direct) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
+                if (P.d.hadamard_only) dispatch_step<true, false>(nullptr, tile, wcol + S.col_off, wb, G, S, TB, base, false, false, last, P.d.scale, tig, GT, sdiag, P.d.n_diag, P.d.index_or);
+                else if (inv) dispatch_step<true>(nullptr, tile, wcol + S.col_off, wb, G, S, TB, base, false, false, last, P.d.scale, tig, GT);
+                else dispatch_step<false>(nullptr, tile, wcol + S.col_off, wb, G, S, TB, base, false, false, last, P.d.scale, tig, GT);
+                if (last) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
                 group_barrier(group, GT);
             }
-            // direct store: the tile left through the registers, the stage is free as soon as
-            // every thread of the group has read it
-            if (tig == 0) mbar_arrive(direct ? &empty[s] : &computed[s]);
+            if (tig == 0) mbar_arrive(&computed[s]);
         }
     }
 }
@@ -272,14 +267,16 @@ encode_fn_t get_encode()
 namespace {
 
 struct pipe_shape { int tb, stages, groups, gt; };
+// A stage of the ring must always be consumed by the same group (STAGES % GROUPS == 0): a
+// group is in order, so it can never wait on a `full` barrier two phases ahead of the barrier's
+// current phase -- which a parity wait cannot tell from "already complete".
 constexpr pipe_shape kShapes[] = {
-    {11, 6, 3, 128},    // 0: three groups of 128, each owning every third tile
-    {11, 6, 1, 384},    // 1: all consumers on one tile at a time
-    {11, 6, 2, 192},    // 2
-    {12, 3, 1, 384},    // 3: 64 KiB tiles: one sweep fewer at n = 30
-    {12, 3, 2, 192},    // 4
-    {11, 6, 1, 256},    // 5
-    {12, 3, 1, 256},    // 6
+    {12, 3, 3, 128},    // 0: 64 KiB tiles, one group per stage: one sweep fewer at n = 30
+    {11, 6, 3, 128},    // 1: 32 KiB tiles, three groups of 128, each owning two stages
+    {11, 6, 6, 64},     // 2: 32 KiB tiles, six groups of 64
+    {12, 3, 1, 256},    // 3
+    {12, 3, 3, 64},     // 4
+    {11, 6, 2, 128},    // 5
 };
 constexpr int kNumShapes = (int) (sizeof kShapes / sizeof kShapes[0]);
 
@@ -337,8 +334,6 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
     P.d = plan.d;
     P.n_tiles = plan.n_tiles;
     P.prefetch = reg->opt_prefetch_tiles;
-    P.direct_store = reg->opt_direct_store ? 1 : 0;
-    P.amp = tg.amp;
     CUtensorMap tmap;
     cuuint64_t dims[3], strides[2];
     cuuint32_t box[3], estr[3] = {1, 1, 1};
@@ -383,12 +378,11 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
     }
     const size_t smem = pipe_smem(sh, P.d);
     switch (shape_id) {
-        case 1: return launch_shape<11, 6, 1, 384>(reg, tmap, P, smem, tg.stream);
-        case 2: return launch_shape<11, 6, 2, 192>(reg, tmap, P, smem, tg.stream);
-        case 3: return launch_shape<12, 3, 1, 384>(reg, tmap, P, smem, tg.stream);
-        case 4: return launch_shape<12, 3, 2, 192>(reg, tmap, P, smem, tg.stream);
-        case 5: return launch_shape<11, 6, 1, 256>(reg, tmap, P, smem, tg.stream);
-        case 6: return launch_shape<12, 3, 1, 256>(reg, tmap, P, smem, tg.stream);
-        default: return launch_shape<11, 6, 3, 128>(reg, tmap, P, smem, tg.stream);
+        case 1: return launch_shape<11, 6, 3, 128>(reg, tmap, P, smem, tg.stream);
+        case 2: return launch_shape<11, 6, 6, 64>(reg, tmap, P, smem, tg.stream);
+        case 3: return launch_shape<12, 3, 1, 256>(reg, tmap, P, smem, tg.stream);
+        case 4: return launch_shape<12, 3, 3, 64>(reg, tmap, P, smem, tg.stream);
+        case 5: return launch_shape<11, 6, 2, 128>(reg, tmap, P, smem, tg.stream);
+        default: return launch_shape<12, 3, 3, 128>(reg, tmap, P, smem, tg.stream);
     }
 }

@@ -3,6 +3,7 @@
 per configuration.  Run on the GPU box; prints one JSON line per configuration."""
 import json
 import math
+import subprocess
 import sys
 
 import numpy as np
@@ -13,7 +14,19 @@ import quantumcomputer_b200 as q
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 shapes = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2, 3, 4, 5, 6]
+directs = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0]
+runs = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [3]
 N = 1 << n
+if len(shapes) > 1:
+    # one process per shape under a timeout: an experimental shape that hangs must not take
+    # the whole matrix (or the GPU box) with it
+    for sh in shapes:
+        try:
+            subprocess.run([sys.executable, __file__, str(n), str(reps), str(sh), ",".join(map(str, directs)),
+                            ",".join(map(str, runs))], timeout=90)
+        except subprocess.TimeoutExpired:
+            print(json.dumps({"n": n, "shape": sh, "error": "timeout"}), flush=True)
+    sys.exit(0)
 
 
 def bitrev(j):
@@ -22,10 +35,9 @@ def bitrev(j):
 
 with q.Register(n, 0) as reg:
     for shape in shapes:
-        for direct in (0, 1):
-            for run_bits in (3, 4):
+        for direct in directs:
+            for run_bits in runs:
                 reg.set_option(q.OPT_PIPE_SHAPE, shape)
-                reg.set_option(q.OPT_DIRECT_STORE, direct)
                 reg.set_option(q.OPT_MIN_RUN_BITS, run_bits)
                 # correctness: inverse_QFT |k> = e^{2 pi i jk/N}/sqrt(N) at bit-reversed j
                 k = 0x1C0FFEE1 % N
