@@ -30,6 +30,7 @@
 #include "qft_common.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -45,7 +46,27 @@ struct pipe_params {
     int n_boxes;            // TMA boxes per tile (a box has at most 256 rows)
     int box_rows;
     uint32_t box_bytes;
+    unsigned long long *timing;   // -DQCS_PIPE_TIMING builds only: per-CTA cycle counters
 };
+
+// Role timing (where do the producer, the store issuer and the consumer groups spend their
+// cycles) is compiled in only with -DQCS_PIPE_TIMING and switched on by the environment
+// variable of the same name; production builds carry none of it.
+#ifdef QCS_PIPE_TIMING
+#define QCS_TICK(P) ((P).timing ? clock64() : 0)
+#define QCS_TIMING_ADD(P, slot, cycles)                                                      \
+    do {                                                                                     \
+        if ((P).timing) (P).timing[blockIdx.x * 16 + (slot)] += (unsigned long long) (cycles); \
+    } while (0)
+#define QCS_TIMING_SET(P, slot, value)                                              \
+    do {                                                                            \
+        if ((P).timing) (P).timing[blockIdx.x * 16 + (slot)] = (unsigned long long) (value); \
+    } while (0)
+#else
+#define QCS_TICK(P) 0ll
+#define QCS_TIMING_ADD(P, slot, cycles) do { (void) (cycles); } while (0)
+#define QCS_TIMING_SET(P, slot, value) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
@@ -180,7 +201,9 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
                     tile_coords<TB>(P, P.d.tile_first + blockIdx.x + (k + P.prefetch) * gridDim.x, c0, c1, c2);
                     for (int b = 0; b < P.n_boxes; b++) tma_prefetch_3d(&tmap, c0, c1 + b * P.box_rows, c2);
                 }
+                const long long t0 = QCS_TICK(P);
                 mbar_wait(&empty[s], (round & 1u) ^ 1u);
+                QCS_TIMING_ADD(P, 0, QCS_TICK(P) - t0);
                 tile_coords<TB>(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
                 mbar_expect_tx(&full[s], kTileBytes);
                 unsigned char *dst = (unsigned char *) (stage_buf + (size_t) s * (1u << TB));
@@ -194,7 +217,9 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
             for (uint64_t k = 0; k < my_tiles; k++) {
                 const int s = (int) (k % STAGES);
                 const uint32_t round = (uint32_t) (k / STAGES);
+                const long long t0 = QCS_TICK(P);
                 mbar_wait(&computed[s], round & 1u);
+                const long long t1 = QCS_TICK(P);
                 int c0, c1, c2;
                 tile_coords<TB>(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
                 const unsigned char *src = (const unsigned char *) (stage_buf + (size_t) s * (1u << TB));
@@ -202,6 +227,8 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
                     tma_store_3d(&tmap, src + (size_t) b * P.box_bytes, c0, c1 + b * P.box_rows, c2);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                QCS_TIMING_ADD(P, 1, t1 - t0);               // waiting for a computed tile
+                QCS_TIMING_ADD(P, 2, QCS_TICK(P) - t1);      // the store reading shared memory
                 mbar_arrive(&empty[s]);
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -226,7 +253,9 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
             }
             group_barrier(group, GT);
             double2 *tile = stage_buf + (size_t) s * (1u << TB);
+            const long long t0 = QCS_TICK(P);
             mbar_wait(&full[s], round & 1u);
+            const long long t1 = QCS_TICK(P);
             for (int st = 0; st < P.d.n_steps; st++) {
                 const sweep_step S = P.d.step[st];
                 const bool last = st == P.d.n_steps - 1;
@@ -237,8 +266,13 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
                 if (last) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
                 group_barrier(group, GT);
             }
-            if (tig == 0) mbar_arrive(&computed[s]);
+            if (tig == 0) {
+                mbar_arrive(&computed[s]);
+                QCS_TIMING_ADD(P, 4 + 2 * group, t1 - t0);              // waiting for the load
+                QCS_TIMING_ADD(P, 5 + 2 * group, QCS_TICK(P) - t1);     // the steps
+            }
         }
+        if (tig == 0 && group == 0) QCS_TIMING_SET(P, 3, my_tiles);
     }
 }
 
@@ -299,6 +333,9 @@ int launch_shape(qcs_register *reg, const CUtensorMap &tmap, const pipe_params &
 }
 
 }  // namespace
+
+static int launch_by_shape(qcs_register *reg, int shape_id, const CUtensorMap &tmap, const pipe_params &P, size_t smem,
+                           cudaStream_t stream);
 
 int qcs_pipeline_tile_bits(const qcs_register *reg)
 {
@@ -377,12 +414,45 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
         return QCS_UNKNOWN_ERROR;
     }
     const size_t smem = pipe_smem(sh, P.d);
+    // -DQCS_PIPE_TIMING builds: QCS_PIPE_TIMING=1 prints where the roles of the pipeline spend their cycles
+#ifdef QCS_PIPE_TIMING
+    static const bool timing_on = getenv("QCS_PIPE_TIMING") != nullptr;
+#else
+    const bool timing_on = false;
+#endif
+    P.timing = nullptr;
+    if (timing_on) {
+        QCS_CUDA(cudaMalloc((void **) &P.timing, 16 * 8 * (size_t) reg->sm_count));
+        QCS_CUDA(cudaMemsetAsync(P.timing, 0, 16 * 8 * (size_t) reg->sm_count, tg.stream));
+    }
+    const int rc = launch_by_shape(reg, shape_id, tmap, P, smem, tg.stream);
+    if (timing_on && rc == QCS_NO_ERROR) {
+        std::vector<unsigned long long> h(16 * (size_t) reg->sm_count);
+        QCS_CUDA(cudaMemcpyAsync(h.data(), P.timing, h.size() * 8, cudaMemcpyDeviceToHost, tg.stream));
+        QCS_CUDA(cudaStreamSynchronize(tg.stream));
+        double sum[16] = {0};
+        for (size_t i = 0; i < h.size(); i++) sum[i % 16] += (double) h[i];
+        const double tiles = sum[3] > 0 ? sum[3] : 1;
+        fprintf(stderr, "qcs pipe timing (cycles per tile, avg over CTAs) shape %d a=%d g=[%d,%d) steps=%d: producer wait empty %.0f | "
+                "store wait computed %.0f, store read %.0f |", shape_id, plan.d.a, plan.d.g_lo, plan.d.g_hi, plan.d.n_steps,
+                sum[0] / tiles, sum[1] / tiles, sum[2] / tiles);
+        for (int g = 0; g < sh.groups && g < 6; g++)
+            fprintf(stderr, " g%d wait load %.0f steps %.0f;", g, sum[4 + 2 * g] / tiles * sh.groups, sum[5 + 2 * g] / tiles * sh.groups);
+        fprintf(stderr, "\n");
+        cudaFree(P.timing);
+    }
+    return rc;
+}
+
+static int launch_by_shape(qcs_register *reg, int shape_id, const CUtensorMap &tmap, const pipe_params &P, size_t smem,
+                           cudaStream_t stream)
+{
     switch (shape_id) {
-        case 1: return launch_shape<11, 6, 3, 128>(reg, tmap, P, smem, tg.stream);
-        case 2: return launch_shape<11, 6, 6, 64>(reg, tmap, P, smem, tg.stream);
-        case 3: return launch_shape<12, 3, 1, 256>(reg, tmap, P, smem, tg.stream);
-        case 4: return launch_shape<12, 3, 3, 64>(reg, tmap, P, smem, tg.stream);
-        case 5: return launch_shape<11, 6, 2, 128>(reg, tmap, P, smem, tg.stream);
-        default: return launch_shape<12, 3, 3, 128>(reg, tmap, P, smem, tg.stream);
+        case 1: return launch_shape<11, 6, 3, 128>(reg, tmap, P, smem, stream);
+        case 2: return launch_shape<11, 6, 6, 64>(reg, tmap, P, smem, stream);
+        case 3: return launch_shape<12, 3, 1, 256>(reg, tmap, P, smem, stream);
+        case 4: return launch_shape<12, 3, 3, 64>(reg, tmap, P, smem, stream);
+        case 5: return launch_shape<11, 6, 2, 128>(reg, tmap, P, smem, stream);
+        default: return launch_shape<12, 3, 3, 128>(reg, tmap, P, smem, stream);
     }
 }
