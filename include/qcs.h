@@ -134,6 +134,11 @@ unsigned long long qcs_num_states(const qcs_register *reg);        /* 2^n, all s
 unsigned long long qcs_local_states(const qcs_register *reg);      /* this shard      */
 int qcs_rank(const qcs_register *reg);
 int qcs_world_size(const qcs_register *reg);
+/* 1 when the shards of a sharded register are mapped into one virtual address range on every
+ * rank (CUDA virtual memory management + NVLink peer access, csrc/peer.cu): sweeps over global
+ * qubits then read and write the peers' shards directly instead of exchanging through staging
+ * buffers.  0: private shards, NCCL send/recv exchange (csrc/dist.cu). */
+int qcs_peer_memory(const qcs_register *reg);
 
 int qcs_set_option(qcs_register *reg, int option, long long value);
 long long qcs_get_option(const qcs_register *reg, int option);

@@ -131,6 +131,11 @@ class Register:
     def local_states(self):
         return self._l.qcs_local_states(self._h)
 
+    @property
+    def peer_memory(self):
+        """True when the shards of a sharded register are stitched into one address range."""
+        return bool(self._l.qcs_peer_memory(self._h))
+
     def set_option(self, opt, value):
         _check(self._l.qcs_set_option(self._h, opt, value), "qcs_set_option")
 

@@ -30,6 +30,7 @@ SIGNATURES = [
     ("qcs_local_states", _ull, [_vp]),
     ("qcs_rank", C.c_int, [_vp]),
     ("qcs_world_size", C.c_int, [_vp]),
+    ("qcs_peer_memory", C.c_int, [_vp]),
     ("qcs_set_option", C.c_int, [_vp, C.c_int, _ll]),
     ("qcs_get_option", _ll, [_vp, C.c_int]),
     ("qcs_synchronize", C.c_int, [_vp]),

@@ -181,6 +181,8 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->world = world;
     reg->p_global = p;
     reg->dist = nullptr;
+    reg->peer = nullptr;
+    reg->amp_all = nullptr;
     reg->opt_fusion = 1;
     reg->opt_profile = 0;
     reg->opt_tile_bits = 0;
@@ -212,7 +214,6 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
         reg->sm_count = prop.multiProcessorCount;
         reg->smem_optin = prop.sharedMemPerBlockOptin;
         if ((e = cudaStreamCreateWithFlags(&reg->stream, cudaStreamNonBlocking)) != cudaSuccess) break;
-        if ((e = cudaMalloc((void **) &reg->amp, reg->N_local * sizeof(double2))) != cudaSuccess) break;
         reg->partials_cap = (size_t) reg->sm_count * 16;
         if ((e = cudaMalloc((void **) &reg->d_partials, reg->partials_cap * sizeof(double))) != cudaSuccess) break;
         if ((e = cudaMalloc(&reg->d_small, 4096)) != cudaSuccess) break;
@@ -228,6 +229,22 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     if (world > 1) {
         rc = qcs_dist_init(reg, comm_id);
         if (rc != QCS_NO_ERROR) { qcs_register_destroy(reg); return rc; }
+        // one address range over all shards (peer.cu); every rank must have it or none
+        const bool mine = qcs_peer_try_alloc(reg, comm_id);
+        std::vector<double> flags((size_t) world);
+        rc = qcs_dist_allgather_double(reg, mine ? 1.0 : 0.0, flags.data());
+        if (rc != QCS_NO_ERROR) { qcs_register_destroy(reg); return rc; }
+        bool all = true;
+        for (double f : flags) all = all && f != 0.0;
+        if (!all && mine) qcs_peer_free(reg);
+    }
+    if (!reg->amp) {
+        e = cudaMalloc((void **) &reg->amp, reg->N_local * sizeof(double2));
+        if (e != cudaSuccess) {
+            rc = qcs_map_cuda_error(e, "register allocation", __FILE__, __LINE__);
+            qcs_register_destroy(reg);
+            return rc;
+        }
     }
     *out = reg;
     return QCS_NO_ERROR;
@@ -250,12 +267,14 @@ extern "C" void qcs_register_destroy(qcs_register *reg)
     if (!reg) return;
     cudaSetDevice(reg->device);
     if (reg->stream) cudaStreamSynchronize(reg->stream);
+    if (reg->peer && reg->dist) qcs_dist_barrier(reg);   // no rank unmaps while a peer may still touch its shard
     if (reg->dist) qcs_dist_destroy(reg);
     for (auto &s : reg->pending) { cudaEventDestroy(s.begin); cudaEventDestroy(s.end); }
     for (auto &s : reg->free_slots) { cudaEventDestroy(s.begin); cudaEventDestroy(s.end); }
     if (reg->timer_begin) cudaEventDestroy(reg->timer_begin);
     if (reg->timer_end) cudaEventDestroy(reg->timer_end);
-    if (reg->amp) cudaFree(reg->amp);
+    if (reg->peer) qcs_peer_free(reg);
+    else if (reg->amp) cudaFree(reg->amp);
     if (reg->d_partials) cudaFree(reg->d_partials);
     if (reg->d_small) cudaFree(reg->d_small);
     if (reg->d_meas) cudaFree(reg->d_meas);
@@ -272,6 +291,7 @@ extern "C" unsigned long long qcs_num_states(const qcs_register *reg) { return r
 extern "C" unsigned long long qcs_local_states(const qcs_register *reg) { return reg ? reg->N_local : 0; }
 extern "C" int qcs_rank(const qcs_register *reg) { return reg ? reg->rank : -1; }
 extern "C" int qcs_world_size(const qcs_register *reg) { return reg ? reg->world : 0; }
+extern "C" int qcs_peer_memory(const qcs_register *reg) { return reg && reg->peer ? 1 : 0; }
 
 extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
 {
@@ -443,8 +463,10 @@ static int qft_any(qcs_register *reg, unsigned lo, unsigned hi, bool inverse)
     if (lo == hi) return QCS_NO_ERROR;
     if (!reg->opt_fusion) return qft_gate_by_gate(reg, lo, hi, inverse);
     if (hi <= reg->n_local) return qcs_fused_qft(reg, lo, hi, inverse);
-    // sharded register, transform reaches the global qubits: their stages run as
-    // exchange + sweep + exchange (dist.cu), the local ones as ordinary sweeps
+    // sharded register, transform reaches the global qubits.  With peer memory the sweeps whose
+    // tile holds global qubits run on the stitched array (qft_fused.cu); without it their stages
+    // run as exchange + sweep + exchange (dist.cu), the local ones as ordinary sweeps
+    if (reg->peer && hi == reg->n && reg->n_local >= 15) return qcs_fused_sweeps_sharded(reg, lo, hi, inverse, false);
     const unsigned q = reg->n_local - (unsigned) reg->p_global;
     if (hi != reg->n || lo > q || reg->n_local < 2u * (unsigned) reg->p_global)
         return qft_gate_by_gate(reg, lo, hi, inverse);       // odd shapes: pairwise exchanges, gate by gate

@@ -22,6 +22,7 @@ struct nccl_api {
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -47,6 +48,7 @@ int load_nccl()
     QCS_SYM(Send, "ncclSend")
     QCS_SYM(Recv, "ncclRecv")
     QCS_SYM(AllGather, "ncclAllGather")
+    QCS_SYM(AllReduce, "ncclAllReduce")
     QCS_SYM(GroupStart, "ncclGroupStart")
     QCS_SYM(GroupEnd, "ncclGroupEnd")
     QCS_SYM(GetErrorString, "ncclGetErrorString")
@@ -142,6 +144,7 @@ int qcs_dist_init(qcs_register *reg, const void *comm_id)
     }
     QCS_CUDA(cudaEventCreateWithFlags(&d->ready, cudaEventDisableTiming));
     QCS_CUDA(cudaMalloc((void **) &d->d_gather, (size_t) (reg->world + 1) * sizeof(double)));
+    QCS_CUDA(cudaMemset(d->d_gather, 0, (size_t) (reg->world + 1) * sizeof(double)));
     QCS_CUDA(cudaHostAlloc((void **) &d->h_gather, (size_t) (reg->world + 1) * sizeof(double), cudaHostAllocDefault));
     return QCS_NO_ERROR;
 }
@@ -191,6 +194,18 @@ int qcs_dist_barrier(qcs_register *reg)
     if (reg->world == 1) return QCS_NO_ERROR;
     std::vector<double> all((size_t) reg->world);
     return qcs_dist_allgather_double(reg, 0.0, all.data());
+}
+
+int qcs_dist_stream_barrier(qcs_register *reg)
+{
+    qcs_dist *d = reg->dist;
+    if (!d) return QCS_NO_ERROR;
+    // a one-element all-reduce: its kernel on a rank completes only after every rank has
+    // reached it, i.e. after everything queued before it on every rank's stream
+    reg->launches_total++;
+    reg->launches[QCS_K_EXCHANGE]++;
+    QCS_NCCL(g_nccl.AllReduce(d->d_gather, d->d_gather, 1, ncclDouble, ncclSum, d->comm, reg->stream));
+    return QCS_NO_ERROR;
 }
 
 // Hadamard on a global qubit: pairwise exchange with rank ^ 2^(q - n_local),

@@ -13,6 +13,7 @@
 #include "../../include/qcs.h"
 
 struct qcs_dist;   // multi-GPU state (dist.cu)
+struct qcs_peer;   // stitched peer-memory mapping of all shards (peer.cu)
 
 struct qcs_profile_slot {
     cudaEvent_t begin, end;
@@ -75,6 +76,11 @@ struct qcs_register {
     // sharding: rank holds amplitudes whose top log2(world) index bits == rank
     int rank, world, p_global;
     qcs_dist *dist;
+    // peer memory: when non-null, amp_all[i] addresses basis state i of the WHOLE register on
+    // every rank (shard k is mapped at k * N_local; remote shards travel over NVLink) and
+    // amp == amp_all + rank * N_local
+    qcs_peer *peer;
+    double2 *amp_all;
 };
 
 // ---- error plumbing -------------------------------------------------------
@@ -124,6 +130,9 @@ int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limi
 
 // ---- fused sweeps: qft_fused.cu / modexp_fused.cu ---------------------------
 int qcs_fused_qft(qcs_register *reg, unsigned lo, unsigned hi, bool inverse);
+// the same on a sharded register with peer memory: qubits up to n, sweeps whose tile holds
+// global qubits run on the stitched array, every rank taking its share of the tiles
+int qcs_fused_sweeps_sharded(qcs_register *reg, unsigned lo, unsigned hi, bool inverse, bool hadamard_only);
 int qcs_fused_hadamards(qcs_register *reg, unsigned lo, unsigned hi);
 int qcs_fused_top_sweep(qcs_register *reg, double2 *buf, unsigned c, unsigned p, unsigned lo,
                         unsigned long long y_const, bool inverse, bool hadamard_only, cudaStream_t stream);
@@ -143,3 +152,10 @@ int qcs_dist_hadamard_global(qcs_register *reg, unsigned q);
 int qcs_dist_top_stages(qcs_register *reg, unsigned lo, bool inverse, bool hadamard_only);
 int qcs_dist_allgather_double(qcs_register *reg, double mine, double *all_host);
 int qcs_dist_barrier(qcs_register *reg);
+// cross-rank barrier ordered on the register's stream (no host synchronisation): work queued
+// after it on any rank starts only when the work queued before it has finished on every rank
+int qcs_dist_stream_barrier(qcs_register *reg);
+
+// ---- peer memory: peer.cu ----------------------------------------------------
+bool qcs_peer_try_alloc(qcs_register *reg, const void *comm_id);
+void qcs_peer_free(qcs_register *reg);

@@ -58,9 +58,12 @@ def main():
         if not ok:
             failures.append(name)
 
-    for (L, M) in [(18, 0), (12, 5), (21, 0)]:
+    for (L, M) in [(18, 0), (12, 5), (21, 0), (20, 5)]:
         n = L + M
         sh = q.Register(L, M, device=local_rank, rank=rank, world_size=world, comm_id=fresh_id())
+        if rank == 0:
+            print(f"[dist] n={n} M={M}: peer memory {'on' if sh.peer_memory else 'off'} "
+                  f"(shard {16 * sh.local_states / 2 ** 20:.1f} MiB)", flush=True)
         single = q.Register(L, M, device=local_rank) if rank == 0 else None
 
         def both(fn):
