@@ -36,6 +36,24 @@ def qft_gate_count(n):
     return n + n * (n - 1) // 2
 
 
+def profiled_traffic(n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the tile-sweep kernel from the
+    committed `ncu --set full` capture of the same workload (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_qft_sweep_tma_t12_n30.csv")
+    if n != 30 or not os.path.exists(path):
+        return None, None
+    try:
+        import csv
+        with open(path) as f:
+            rows = list(csv.reader(f))
+        hdr = rows[0]
+        rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        per = [float(r[rd]) + float(r[wr]) for r in rows[2:] if len(r) > wr]
+        return 1e9 * sum(per) / len(per), os.path.relpath(path, ROOT)
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -309,9 +327,10 @@ def run_ours(args):
         d_launches, d_ms, d_bytes = prof[dom]
         achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
         kernel_ms = sum(v[1] for v in prof.values())
+        traffic, traffic_src = profiled_traffic(n) if (dom == "tile_sweep" and circuit is None and world == 1) else (None, None)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "peak_source": peak_src + " (of measured)",
-                    "traffic": None, "launches": d_launches, "avg_launch_ms": d_ms / d_launches,
+                    "traffic": traffic, "traffic_source": traffic_src, "launches": d_launches, "avg_launch_ms": d_ms / d_launches,
                     "algorithmic_bytes_per_launch": d_bytes / d_launches,
                     "share_of_kernel_time": d_ms / kernel_ms if kernel_ms else None,
                     "bytes_model": CLASS_BYTES_NOTE.get(dom, "")}

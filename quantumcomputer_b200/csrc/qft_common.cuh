@@ -215,18 +215,22 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
 #pragma unroll
                 for (int d = 0; d < R; d++) { x[d].x *= scale; x[d].y *= scale; }
             }
-            // diagonal gates of the layer: the elements are in registers and their
-            // full basis-state index is known
+            // diagonal gates riding along (circuit.cu): the elements are in registers and their
+            // full basis-state index is known.  The mask bits outside the step's digit are the
+            // same for all R elements of the thread and are tested once per gate.
             if (n_diag > 0) {
                 const uint64_t i0 = index_or | base | G.spread(e_base);
-                const uint64_t dstride = 1ull << G.phys(S.s);
+                const int dshift = G.phys(S.s);
+                const uint64_t digit_bits = (uint64_t) (R - 1) << dshift;
                 for (int gi = 0; gi < n_diag; gi++) {
                     const diag_gate dg = diag[gi];
+                    const uint64_t rest = dg.mask & ~digit_bits;
+                    if ((i0 & rest) != rest) continue;
+                    const unsigned dm = (unsigned) ((dg.mask & digit_bits) >> dshift);
+                    const double2 ph = make_double2(dg.c, dg.s);
 #pragma unroll
-                    for (int d = 0; d < R; d++) {
-                        const uint64_t idx = i0 | ((uint64_t) d * dstride);
-                        if ((idx & dg.mask) == dg.mask) x[d] = cmul(x[d], make_double2(dg.c, dg.s));
-                    }
+                    for (int d = 0; d < R; d++)
+                        if (((unsigned) d & dm) == dm) x[d] = cmul(x[d], ph);
                 }
             }
         }
@@ -362,7 +366,7 @@ inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int 
     }
     if (top > (int) lo) raws.push_back({t, t, t, (int) lo, top});
     for (const raw &rw : raws) {
-        sweep_plan p;
+        sweep_plan p = {};
         sweep_desc &d = p.d;
         d.a = rw.a;
         d.g_lo = rw.g_lo;

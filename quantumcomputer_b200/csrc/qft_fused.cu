@@ -183,7 +183,7 @@ int qcs_fused_top_sweep(qcs_register *reg, double2 *buf, unsigned c, unsigned p,
     const unsigned nb = c + p;
     int T = default_tile_bits(reg);
     if ((unsigned) T > nb) T = (int) nb;
-    sweep_plan pl;
+    sweep_plan pl = {};              // no diagonal gates, no rank bits
     sweep_desc &d = pl.d;
     d.t = T;
     d.a = T - (int) p;
