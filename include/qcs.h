@@ -85,7 +85,11 @@ enum {
     /* log2 of the shortest contiguous run of amplitudes a strided tile may use (3 = 128 B,
      * the default; 4 = 256 B ...): shorter runs leave more tile bits for stages, i.e. fewer
      * sweeps. */
-    QCS_OPT_MIN_RUN_BITS = 8
+    QCS_OPT_MIN_RUN_BITS = 8,
+    /* sharded registers with peer memory: log2 of the contiguous run (amplitudes per TMA row) of
+     * the one sweep that covers the global qubits.  That sweep is NVLink-bound, so it prefers
+     * long rows to many stage bits. */
+    QCS_OPT_GLOBAL_RUN_BITS = 9
 };
 
 /* kernel classes reported by qcs_profile_get */

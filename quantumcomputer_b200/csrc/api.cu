@@ -190,6 +190,7 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->opt_pipeline = 1;
     reg->opt_pipe_shape = -1;
     reg->opt_min_run_bits = 3;
+    reg->opt_global_run_bits = 7;
     reg->opt_prefetch_tiles = 0;     // measured: L2 prefetch slows the sweep down (profiles/README.md)
     reg->d_meas = nullptr;
     reg->fusing = 0;
@@ -316,6 +317,10 @@ extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
             if (value < 1 || value > 7) return QCS_BAD_ARGUMENTS;
             reg->opt_min_run_bits = (int) value;
             return QCS_NO_ERROR;
+        case QCS_OPT_GLOBAL_RUN_BITS:
+            if (value < 1 || value > 7) return QCS_BAD_ARGUMENTS;
+            reg->opt_global_run_bits = (int) value;
+            return QCS_NO_ERROR;
         case QCS_OPT_PREFETCH_TILES:
             if (value < 0 || value > 64) return QCS_BAD_ARGUMENTS;
             reg->opt_prefetch_tiles = (int) value;
@@ -335,6 +340,7 @@ extern "C" long long qcs_get_option(const qcs_register *reg, int option)
         case QCS_OPT_PIPELINE: return reg->opt_pipeline;
         case QCS_OPT_PIPE_SHAPE: return reg->opt_pipe_shape;
         case QCS_OPT_MIN_RUN_BITS: return reg->opt_min_run_bits;
+        case QCS_OPT_GLOBAL_RUN_BITS: return reg->opt_global_run_bits;
         case QCS_OPT_PREFETCH_TILES: return reg->opt_prefetch_tiles;
         default: return -1;
     }
@@ -466,7 +472,8 @@ static int qft_any(qcs_register *reg, unsigned lo, unsigned hi, bool inverse)
     // sharded register, transform reaches the global qubits.  With peer memory the sweeps whose
     // tile holds global qubits run on the stitched array (qft_fused.cu); without it their stages
     // run as exchange + sweep + exchange (dist.cu), the local ones as ordinary sweeps
-    if (reg->peer && hi == reg->n && reg->n_local >= 15) return qcs_fused_sweeps_sharded(reg, lo, hi, inverse, false);
+    if (reg->peer && hi == reg->n && reg->n_local >= 15 && lo + 12 <= reg->n_local)
+        return qcs_fused_sweeps_sharded(reg, lo, hi, inverse, false);
     const unsigned q = reg->n_local - (unsigned) reg->p_global;
     if (hi != reg->n || lo > q || reg->n_local < 2u * (unsigned) reg->p_global)
         return qft_gate_by_gate(reg, lo, hi, inverse);       // odd shapes: pairwise exchanges, gate by gate

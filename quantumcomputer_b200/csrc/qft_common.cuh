@@ -342,11 +342,15 @@ inline void split_even(int total, int cap, std::vector<int> &out)
 // the low `a` index bits (a contiguous run of 2^a amplitudes) for coalescing and spend the
 // other t - a bits on stages: `a` is the largest value in [a_min, a_pref] ... that still gives
 // the fewest sweeps (a longer run never costs a sweep).
-inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int a_min, std::vector<sweep_plan> &plans)
+// stage_lo >= lo (default lo): plan only the stages [stage_lo, hi); the twiddles still refer to
+// the register's lowest qubit `lo`.
+inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int a_min, std::vector<sweep_plan> &plans,
+                         int stage_lo = -1)
 {
     plans.clear();
+    if (stage_lo < (int) lo) stage_lo = (int) lo;
     const int t = std::min<int>(T, (int) n_local);
-    const int first_hi = std::max<int>((int) lo, t);
+    const int first_hi = std::max<int>(stage_lo, t);
     int a = t;
     if ((int) n_local > t) {
         a_min = std::max(1, std::min(a_min, t - 1));
@@ -364,7 +368,7 @@ inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int 
         raws.push_back({t - g, top - g, top, top - g, top});     // low run widened so the tile has exactly t bits
         top -= g;
     }
-    if (top > (int) lo) raws.push_back({t, t, t, (int) lo, top});
+    if (top > stage_lo) raws.push_back({t, t, t, stage_lo, top});
     for (const raw &rw : raws) {
         sweep_plan p = {};
         sweep_desc &d = p.d;
@@ -404,7 +408,7 @@ inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int 
     }
     // one scaling for the whole transform, on its last sweep
     if (!plans.empty()) {
-        const int total = (int) hi - (int) lo;
+        const int total = (int) hi - stage_lo;
         plans.back().d.scale = total % 2 == 0 ? ldexp(1.0, -total / 2) : ldexp(0.70710678118654752440, -(total - 1) / 2);
     }
 }

@@ -217,51 +217,67 @@ int qcs_fused_qft(qcs_register *reg, unsigned lo, unsigned hi, bool inverse)
     return run_sweeps(reg, lo, hi, inverse, false);
 }
 
-// Sharded register with peer memory (peer.cu): the transform on qubits [lo, hi), hi <= n, is
-// planned on the WHOLE register exactly as on one GPU.  Every rank runs every sweep on its
-// 1/world share of the tiles:
-//   * a sweep whose tile holds a global qubit addresses the stitched array amp_all; the rows of
-//     a tile that live on other ranks are fetched (and written back) over NVLink by the TMA
-//     engine while the consumer groups work on tiles that already arrived -- the exchange is
-//     part of the sweep.  A stream-ordered barrier separates it from the sweeps around it
-//     (peers read what this rank wrote before, and write what it reads next);
-//   * a sweep on local qubits touches only this rank's shard: the rank's tiles are exactly the
-//     tiles of its shard, no barrier, no communication.
-// NVLink traffic: each rank reads and writes (world-1)/world of a shard per global sweep.
+// Sharded register with peer memory (peer.cu), transform on qubits [lo, hi) reaching the
+// global qubits (hi > n_local):
+//   * the top stages -- the global qubits and as many local ones as fit beside a long
+//     contiguous run -- are ONE tile sweep on the stitched array amp_all.  Every rank runs it on
+//     its 1/world share of the tiles; the rows of a tile that live on other ranks are fetched
+//     (and written back) over NVLink by the TMA engine while the consumer groups work on tiles
+//     that already arrived: the exchange is part of the sweep.  A stream-ordered barrier
+//     separates it from the work around it;
+//   * the remaining stages are ordinary sweeps on the rank's own shard: no communication.
+// NVLink traffic: each rank reads and writes (world-1)/world of a shard, once.
 int qcs_fused_sweeps_sharded(qcs_register *reg, unsigned lo, unsigned hi, bool inverse, bool hadamard_only)
 {
     if (!reg->peer || !reg->amp_all || lo >= hi || hi > reg->n) return QCS_BAD_ARGUMENTS;
     const int T = default_tile_bits(reg);
-    if ((int) reg->n_local < T) return QCS_BAD_ARGUMENTS;
-    std::vector<sweep_plan> plans;
-    plan_inverse(reg->n, lo, hi, T, reg->opt_min_run_bits, plans);
-    if (!inverse) make_forward(plans);
-    bool dirty = true;      // other ranks may still be working on what a global sweep reads
-    for (sweep_plan &p : plans) {
-        p.d.hadamard_only = hadamard_only ? 1 : 0;
-        if (hadamard_only) p.d.wcol_total = 0;
-        const bool global = p.d.g_hi > (int) reg->n_local;
-        const uint64_t share = p.n_tiles >> reg->p_global;
-        if (share == 0) return QCS_BAD_ARGUMENTS;
-        if (global) {
+    if ((int) reg->n_local < T + 3 || hi <= reg->n_local) return QCS_BAD_ARGUMENTS;
+    // The sweep over the global qubits is bound by NVLink, not by HBM: it keeps long contiguous
+    // runs (2^a amplitudes per TMA row) and takes along only as many local stage bits as fit.
+    int a_glob = reg->opt_global_run_bits;
+    if (a_glob > T - reg->p_global) a_glob = T - reg->p_global;
+    if (a_glob < 1) return QCS_BAD_ARGUMENTS;
+    int split = (int) hi - (T - a_glob);                    // global sweep: stages [split, hi)
+    if (split < (int) lo) split = (int) lo;
+    if (split > (int) reg->n_local) return QCS_BAD_ARGUMENTS;
+    std::vector<sweep_plan> global_plans, local_plans;
+    plan_inverse(reg->n, lo, hi, T, a_glob, global_plans, split);
+    if (split > (int) lo) plan_inverse(reg->n_local, lo, (unsigned) split, T, reg->opt_min_run_bits, local_plans);
+    if (!inverse) {
+        make_forward(global_plans);
+        make_forward(local_plans);
+    }
+    auto run_global = [&]() -> int {
+        for (sweep_plan &p : global_plans) {
+            p.d.hadamard_only = hadamard_only ? 1 : 0;
+            if (hadamard_only) p.d.wcol_total = 0;
+            const uint64_t share = p.n_tiles >> reg->p_global;
+            if (share == 0) return QCS_BAD_ARGUMENTS;
+            // peers read what this rank wrote before the sweep and write what it reads after it
             QCS_TRY(qcs_dist_stream_barrier(reg));
             p.d.tile_first = (uint64_t) reg->rank * share;
             p.n_tiles = share;
             const sweep_target tg = {reg->amp_all, reg->n, reg->stream};
             QCS_TRY(launch_plan(reg, tg, p));
             QCS_TRY(qcs_dist_stream_barrier(reg));
-            dirty = false;
-        } else {
-            // the plan's tiles with this rank's value of the global bits are the tiles of its shard
-            p.d.tile_first = 0;
-            p.n_tiles = share;
-            const sweep_target tg = {reg->amp, reg->n_local, reg->stream};
-            QCS_TRY(launch_plan(reg, tg, p));
-            dirty = true;
         }
+        return QCS_NO_ERROR;
+    };
+    auto run_local = [&]() -> int {
+        const sweep_target tg = {reg->amp, reg->n_local, reg->stream};
+        for (sweep_plan &p : local_plans) {
+            p.d.hadamard_only = hadamard_only ? 1 : 0;
+            if (hadamard_only) p.d.wcol_total = 0;
+            QCS_TRY(launch_plan(reg, tg, p));
+        }
+        return QCS_NO_ERROR;
+    };
+    if (inverse) {
+        QCS_TRY(run_global());
+        return run_local();
     }
-    (void) dirty;
-    return QCS_NO_ERROR;
+    QCS_TRY(run_local());
+    return run_global();
 }
 
 // Hadamard on every qubit of [lo, hi) (the first loop of quantum_computation,
