@@ -105,7 +105,10 @@ enum {
     QCS_K_SCALE = 8,         /* in-place scaling                     32*2^n B/launch */
     QCS_K_DENSE_BLOCK = 9,   /* dense 2^k x 2^k block on the k low qubits (DMMA) 32*2^n B/launch */
     QCS_K_DIAG = 10,         /* several diagonal gates in one pass (gate stream) 32*2^n B/launch */
-    QCS_K_COUNT = 11
+    QCS_K_GLOBAL_SWEEP = 11, /* tile sweep over the global qubits on peer memory (multi-GPU); bytes =
+                              * NVLink traffic per direction, 2*(P-1)/P * 16*2^n_local B/launch */
+    QCS_K_GATE_1Q = 12,      /* arbitrary (controlled) single-qubit gate  32*2^n B/launch (16*2^n controlled) */
+    QCS_K_COUNT = 13
 };
 
 const char *qcs_version(void);
@@ -186,6 +189,12 @@ int qcs_quantum_computation(qcs_register *reg, unsigned C, unsigned a, int pow_m
  * with the reference's sequential summation semantics (bit-exact index). */
 int qcs_measure_state(qcs_register *reg, double r, unsigned long long *state_num);
 
+/* Sampling without collapse (not in the reference, which reruns the whole computation per
+ * sample; Q:294-301 mentions the option): state_nums[k] = the index qcs_measure_state would
+ * return for r[k], the state is left untouched. */
+int qcs_sample_states(qcs_register *reg, unsigned long long n_shots, const double *r,
+                      unsigned long long *state_nums);
+
 /* check_normalisation, T:28-37: sum of |amp|^2 (deterministic parallel order) */
 int qcs_norm2(qcs_register *reg, double *sum_of_sq);
 
@@ -201,6 +210,20 @@ int qcs_get_state(qcs_register *reg, unsigned long long first, unsigned long lon
                   double *interleaved_out);
 int qcs_set_state(qcs_register *reg, unsigned long long first, unsigned long long count,
                   const double *interleaved_in);
+
+/* Arbitrary single-qubit gate: the 2x2 complex matrix u (row-major, interleaved re/im, 8
+ * doubles) on qubit_num -- what HADAMARD_BASE_MATRIX (Q:210-213) is one instance of -- and its
+ * controlled form (u applied where bit c_qubit_num is 1), the generalisation of
+ * C_PHASE_SHIFT_BASE_MATRIX (Q:220-225).  Same pair-stride pass as qcs_hadamard_gate. */
+int qcs_apply_gate(qcs_register *reg, unsigned qubit_num, const double *u_interleaved);
+int qcs_apply_controlled_gate(qcs_register *reg, unsigned c_qubit_num, unsigned qubit_num,
+                              const double *u_interleaved);
+
+/* State dump / load: 64-byte header + this shard's amplitudes as raw little-endian interleaved
+ * doubles, the layout of gsl_vector_complex.data (Q:385-386).  A sharded register writes /
+ * reads "<path>.rank<k>" on every rank.  The file must match the register's L, M and sharding. */
+int qcs_save_state(qcs_register *reg, const char *path);
+int qcs_load_state(qcs_register *reg, const char *path);
 
 /* Deferred gate stream.  Between qcs_fuse_begin and qcs_fuse_end,
  * qcs_hadamard_gate and qcs_c_phase_shift_gate record their gate instead of

@@ -19,7 +19,7 @@ POW_VERBATIM, POW_MODULAR = 0, 1
 OPT_FUSION, OPT_PROFILE, OPT_TILE_BITS, OPT_MEASURE_SEQUENTIAL, OPT_PIPELINE, OPT_PREFETCH_TILES = 1, 2, 3, 4, 5, 6
 OPT_PIPE_SHAPE, OPT_MIN_RUN_BITS, OPT_GLOBAL_RUN_BITS = 7, 8, 9
 KERNEL_CLASSES = ["hadamard", "cphase", "amodc", "fill", "reduce", "tile_sweep",
-                  "modexp_sweep", "exchange", "scale", "dense_block", "diag_multi"]
+                  "modexp_sweep", "exchange", "scale", "dense_block", "diag_multi", "global_sweep", "gate_1q"]
 
 
 class QcsError(RuntimeError):
@@ -178,6 +178,28 @@ class Register:
         out = C.c_ulonglong(0)
         _check(self._l.qcs_measure_state(self._h, r, C.byref(out)), "measure_state")
         return int(out.value)
+
+    def sample_states(self, rs):
+        """Indices measure_state would return for each variate in rs, without collapsing."""
+        r = np.ascontiguousarray(np.asarray(rs, dtype=np.float64))
+        out = np.zeros(r.size, dtype=np.uint64)
+        _check(self._l.qcs_sample_states(self._h, r.size, r.ctypes.data, out.ctypes.data), "sample_states")
+        return [int(v) for v in out]
+
+    def apply_gate(self, qubit_num, U):
+        u = np.ascontiguousarray(np.asarray(U, dtype=np.complex128).reshape(2, 2)).view(np.float64)
+        _check(self._l.qcs_apply_gate(self._h, qubit_num, u.ctypes.data), "apply_gate")
+
+    def apply_controlled_gate(self, c_qubit_num, qubit_num, U):
+        u = np.ascontiguousarray(np.asarray(U, dtype=np.complex128).reshape(2, 2)).view(np.float64)
+        _check(self._l.qcs_apply_controlled_gate(self._h, c_qubit_num, qubit_num, u.ctypes.data),
+               "apply_controlled_gate")
+
+    def save_state(self, path):
+        _check(self._l.qcs_save_state(self._h, str(path).encode()), "save_state")
+
+    def load_state(self, path):
+        _check(self._l.qcs_load_state(self._h, str(path).encode()), "load_state")
 
     def norm2(self):
         out = C.c_double(0.0)

@@ -48,6 +48,11 @@ SIGNATURES = [
     ("qcs_nonzero_states", C.c_int, [_vp, _ull, C.POINTER(_ull), _dp, C.POINTER(_ull)]),
     ("qcs_get_state", C.c_int, [_vp, _ull, _ull, _vp]),
     ("qcs_set_state", C.c_int, [_vp, _ull, _ull, _vp]),
+    ("qcs_sample_states", C.c_int, [_vp, _ull, _vp, _vp]),
+    ("qcs_apply_gate", C.c_int, [_vp, _u, _vp]),
+    ("qcs_apply_controlled_gate", C.c_int, [_vp, _u, _u, _vp]),
+    ("qcs_save_state", C.c_int, [_vp, C.c_char_p]),
+    ("qcs_load_state", C.c_int, [_vp, C.c_char_p]),
     ("qcs_fuse_begin", C.c_int, [_vp]),
     ("qcs_fuse_end", C.c_int, [_vp]),
     ("qcs_fuse_pending", _ull, [_vp]),

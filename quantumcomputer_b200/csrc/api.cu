@@ -86,7 +86,7 @@ extern "C" const char *qcs_kernel_class_name(int k)
 {
     static const char *names[QCS_K_COUNT] = {"hadamard", "cphase", "amodc", "fill", "reduce",
                                              "tile_sweep", "modexp_sweep", "exchange", "scale", "dense_block",
-                                             "diag_multi"};
+                                             "diag_multi", "global_sweep", "gate_1q"};
     return (k >= 0 && k < QCS_K_COUNT) ? names[k] : "?";
 }
 
@@ -552,10 +552,9 @@ extern "C" int qcs_norm2(qcs_register *reg, double *sum_of_sq)
     return QCS_NO_ERROR;
 }
 
-extern "C" int qcs_measure_state(qcs_register *reg, double r, unsigned long long *state_num)
+// the index measure_state would return for this r (qc_shor.c:283-292), without the collapse
+static int locate_state(qcs_register *reg, double r, uint64_t *out_index)
 {
-    QCS_ENTER(reg);
-    if (!state_num) return QCS_BAD_ARGUMENTS;
     // qc_shor.c:283: the scan covers indices 0 .. N-2; N-1 is the fall-through
     int found = 0;
     uint64_t index = 0;
@@ -567,7 +566,6 @@ extern "C" int qcs_measure_state(qcs_register *reg, double r, unsigned long long
     } else {
         // the running sum is handed from rank to rank in index order
         for (int turn = 0; turn < reg->world; turn++) {
-            double state[3] = {cum, (double) found, 0.0};
             if (turn == reg->rank && !found) {
                 const uint64_t limit = reg->rank == reg->world - 1 ? reg->N_local - 1 : reg->N_local;
                 QCS_TRY(qcs_k_measure_scan(reg, cum, r, limit, &found, &index, &cum));
@@ -582,15 +580,40 @@ extern "C" int qcs_measure_state(qcs_register *reg, double r, unsigned long long
             // indices < 2^53 are exact in a double
             QCS_TRY(qcs_dist_allgather_double(reg, (double) global_index, all.data()));
             global_index = (uint64_t) all[(size_t) turn];
-            (void) state;
             if (found) break;
         }
     }
+    *out_index = global_index;
+    return QCS_NO_ERROR;
+}
+
+extern "C" int qcs_measure_state(qcs_register *reg, double r, unsigned long long *state_num)
+{
+    QCS_ENTER(reg);
+    if (!state_num) return QCS_BAD_ARGUMENTS;
+    uint64_t global_index = 0;
+    QCS_TRY(locate_state(reg, r, &global_index));
     // collapse, qc_shor.c:302-303
     const uint64_t owner = global_index >> reg->n_local;
     QCS_TRY(qcs_k_collapse(reg, global_index & (reg->N_local - 1), owner == (uint64_t) reg->rank));
     QCS_CUDA(cudaStreamSynchronize(reg->stream));
     *state_num = global_index;
+    return QCS_NO_ERROR;
+}
+
+// Sampling without collapse (qc_shor.c:294-301 notes the option): for every
+// variate r[k] the index measure_state would have returned, the state left untouched, so the
+// reference's "rerun the whole computation per sample" loop becomes one state preparation.
+extern "C" int qcs_sample_states(qcs_register *reg, unsigned long long n_shots, const double *r,
+                                 unsigned long long *state_nums)
+{
+    QCS_ENTER(reg);
+    if (n_shots && (!r || !state_nums)) return QCS_BAD_ARGUMENTS;
+    for (unsigned long long k = 0; k < n_shots; k++) {
+        uint64_t idx = 0;
+        QCS_TRY(locate_state(reg, r[k], &idx));
+        state_nums[k] = idx;
+    }
     return QCS_NO_ERROR;
 }
 

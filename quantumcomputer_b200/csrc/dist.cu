@@ -95,6 +95,22 @@ k_hadamard_global_combine(double2 *__restrict__ mine, const double2 *__restrict_
     }
 }
 
+// the same for an arbitrary 2x2 gate (gates_general.cu): new = A * mine + B * theirs with
+// (A, B) = (U00, U01) on the rank whose target bit is 0 and (U11, U10) on the other one;
+// ctrl_mask != 0 restricts the update to local indices with that bit set
+__global__ void __launch_bounds__(256)
+k_gate_global_combine(double2 *__restrict__ mine, const double2 *__restrict__ theirs, uint64_t count, uint64_t first_index,
+                      double2 A, double2 B, uint64_t ctrl_mask)
+{
+    const uint64_t stride = (uint64_t) gridDim.x * 256;
+    for (uint64_t i = (uint64_t) blockIdx.x * 256 + threadIdx.x; i < count; i += stride) {
+        if (ctrl_mask && !((first_index + i) & ctrl_mask)) continue;
+        const double2 a = mine[i], b = theirs[i];
+        mine[i] = make_double2(A.x * a.x - A.y * a.y + B.x * b.x - B.y * b.y,
+                               A.x * a.y + A.y * a.x + B.x * b.y + B.y * b.x);
+    }
+}
+
 }  // namespace
 
 struct qcs_dist {
@@ -248,6 +264,57 @@ int qcs_dist_hadamard_global(qcs_register *reg, unsigned q)
     return QCS_NO_ERROR;
 }
 
+
+// Arbitrary 2x2 gate on a global target qubit, optionally controlled (c < 0: no control), for
+// registers without peer memory: the same chunked pairwise exchange as the Hadamard above.
+int qcs_dist_gate_global(qcs_register *reg, unsigned q, int c, const double *u)
+{
+    qcs_dist *d = reg->dist;
+    if (!d || q < reg->n_local || q >= reg->n) return QCS_BAD_ARGUMENTS;
+    const int bitpos = (int) (q - reg->n_local);
+    const int partner = reg->rank ^ (1 << bitpos);
+    const int my_bit = (reg->rank >> bitpos) & 1;
+    uint64_t ctrl_mask = 0;
+    if (c >= 0) {
+        if ((unsigned) c >= reg->n_local) {
+            // a global control is the same constant bit on both partners
+            if (!(((unsigned) reg->rank >> ((unsigned) c - reg->n_local)) & 1u)) return QCS_NO_ERROR;
+        } else {
+            ctrl_mask = 1ull << c;
+        }
+    }
+    const double2 A = my_bit ? make_double2(u[6], u[7]) : make_double2(u[0], u[1]);
+    const double2 B = my_bit ? make_double2(u[4], u[5]) : make_double2(u[2], u[3]);
+    const uint64_t chunk = d->staging_amps;
+    const uint64_t n_chunks = reg->N_local / chunk;
+    QCS_CUDA(cudaEventRecord(d->ready, reg->stream));
+    QCS_CUDA(cudaStreamWaitEvent(d->comm_stream, d->ready, 0));
+    for (uint64_t k = 0; k < n_chunks; k++) {
+        const int b = (int) (k & 1);
+        double2 *mine = reg->amp + k * chunk;
+        if (k >= 2) QCS_CUDA(cudaStreamWaitEvent(d->comm_stream, d->buf_free[b], 0));
+        reg->launches_total++;
+        reg->launches[QCS_K_EXCHANGE]++;
+        reg->alg_bytes[QCS_K_EXCHANGE] += 16.0 * (double) chunk;
+        QCS_NCCL(g_nccl.GroupStart());
+        QCS_NCCL(g_nccl.Send(mine, chunk * 2, ncclDouble, partner, d->comm, d->comm_stream));
+        QCS_NCCL(g_nccl.Recv(d->staging[b], chunk * 2, ncclDouble, partner, d->comm, d->comm_stream));
+        QCS_NCCL(g_nccl.GroupEnd());
+        QCS_CUDA(cudaEventRecord(d->recv_done[b], d->comm_stream));
+        QCS_CUDA(cudaStreamWaitEvent(reg->stream, d->recv_done[b], 0));
+        uint64_t grid = (chunk + 255) / 256;
+        const uint64_t cap = (uint64_t) reg->sm_count * 8;
+        if (grid > cap) grid = cap;
+        qcs_launch_begin(reg, QCS_K_GATE_1Q, 48.0 * (double) chunk);
+        k_gate_global_combine<<<(unsigned) grid, 256, 0, reg->stream>>>(mine, d->staging[b], chunk, k * chunk, A, B, ctrl_mask);
+        QCS_TRY(qcs_launch_end(reg, QCS_K_GATE_1Q, "k_gate_global_combine"));
+        QCS_CUDA(cudaEventRecord(d->buf_free[b], reg->stream));
+    }
+    // the partner must not overwrite amplitudes this rank is still sending: the sends above read
+    // `mine` on the comm stream while the combine of the same chunk waits for recv_done, which
+    // follows the send in the same NCCL group
+    return QCS_NO_ERROR;
+}
 
 // ---------------------------------------------------------------------------
 // Stages on the global qubits [n_local, n) -- the first p stages of the

@@ -140,6 +140,9 @@ int qcs_fused_top_sweep(qcs_register *reg, double2 *buf, unsigned c, unsigned p,
 // H on the L register, then all L controlled a^(2^k) mod C gates in one block-local sweep
 int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, unsigned n_gates);
 
+// ---- general gates: gates_general.cu ------------------------------------------
+int qcs_k_gate_1q(qcs_register *reg, unsigned q, int c /* < 0: no control */, const double *u_interleaved);
+
 // ---- deferred gate stream: circuit.cu ------------------------------------------
 // schedule and launch every recorded gate (no-op when the queue is empty)
 int qcs_fuse_flush(qcs_register *reg);
@@ -148,6 +151,8 @@ int qcs_fuse_flush(qcs_register *reg);
 int qcs_dist_init(qcs_register *reg, const void *comm_id);
 void qcs_dist_destroy(qcs_register *reg);
 int qcs_dist_hadamard_global(qcs_register *reg, unsigned q);
+// arbitrary 2x2 gate u (row-major, interleaved) on a global target qubit, control c (< 0: none)
+int qcs_dist_gate_global(qcs_register *reg, unsigned q, int c, const double *u);
 // stages of the (inverse) QFT / Hadamards on the global qubits [n_local, n): exchange in,
 // one sweep, exchange back, pipelined over slices of the shard
 int qcs_dist_top_stages(qcs_register *reg, unsigned lo, bool inverse, bool hadamard_only);

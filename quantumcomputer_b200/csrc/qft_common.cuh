@@ -280,6 +280,8 @@ struct sweep_target {
     double2 *amp;
     unsigned n_bits;        // log2 of the number of amplitudes addressed
     cudaStream_t stream;
+    int kind = QCS_K_TILE_SWEEP;    // kernel class the launch is accounted to
+    double bytes = 0.0;             // algorithmic bytes of the launch (0: 32 B per amplitude of the tiles)
 };
 
 struct sweep_plan {

@@ -100,9 +100,9 @@ int launch_sweep(qcs_register *reg, const sweep_target &tg, const sweep_plan &p,
     if (per_sm < 1) return QCS_UNKNOWN_ERROR;
     uint64_t grid = (uint64_t) reg->sm_count * (uint64_t) per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
-    qcs_launch_begin(reg, QCS_K_TILE_SWEEP, 32.0 * (double) (p.n_tiles << p.d.t));
+    qcs_launch_begin(reg, tg.kind, tg.bytes > 0.0 ? tg.bytes : 32.0 * (double) (p.n_tiles << p.d.t));
     kern<<<(unsigned) grid, NT, smem, tg.stream>>>(tg.amp, p.n_tiles, p.d);
-    return qcs_launch_end(reg, QCS_K_TILE_SWEEP, "k_qft_sweep");
+    return qcs_launch_end(reg, tg.kind, "k_qft_sweep");
 }
 
 }  // namespace
@@ -257,7 +257,11 @@ int qcs_fused_sweeps_sharded(qcs_register *reg, unsigned lo, unsigned hi, bool i
             QCS_TRY(qcs_dist_stream_barrier(reg));
             p.d.tile_first = (uint64_t) reg->rank * share;
             p.n_tiles = share;
-            const sweep_target tg = {reg->amp_all, reg->n, reg->stream};
+            // accounted as NVLink traffic per direction: this rank's remote reads plus the peers'
+            // reads of its shard one way, its remote writes plus theirs the other way
+            sweep_target tg = {reg->amp_all, reg->n, reg->stream};
+            tg.kind = QCS_K_GLOBAL_SWEEP;
+            tg.bytes = 2.0 * 16.0 * (double) (share << p.d.t) * (double) (reg->world - 1) / (double) reg->world;
             QCS_TRY(launch_plan(reg, tg, p));
             QCS_TRY(qcs_dist_stream_barrier(reg));
         }

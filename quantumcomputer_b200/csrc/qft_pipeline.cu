@@ -321,21 +321,21 @@ size_t pipe_smem(const pipe_shape &sh, const qft::sweep_desc &d)
 }
 
 template <int TB, int STAGES, int GROUPS, int GT>
-int launch_shape(qcs_register *reg, const CUtensorMap &tmap, const pipe_params &P, size_t smem, cudaStream_t stream)
+int launch_shape(qcs_register *reg, const CUtensorMap &tmap, const pipe_params &P, size_t smem, const qft::sweep_target &tg)
 {
     auto kern = k_qft_sweep_tma<TB, STAGES, GROUPS, GT>;
     QCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     uint64_t grid = (uint64_t) reg->sm_count;
     if (grid > P.n_tiles) grid = P.n_tiles;
-    qcs_launch_begin(reg, QCS_K_TILE_SWEEP, 32.0 * (double) (P.n_tiles << TB));
-    kern<<<(unsigned) grid, 64 + GROUPS * GT, smem, stream>>>(tmap, P);
-    return qcs_launch_end(reg, QCS_K_TILE_SWEEP, "k_qft_sweep_tma");
+    qcs_launch_begin(reg, tg.kind, tg.bytes > 0.0 ? tg.bytes : 32.0 * (double) (P.n_tiles << TB));
+    kern<<<(unsigned) grid, 64 + GROUPS * GT, smem, tg.stream>>>(tmap, P);
+    return qcs_launch_end(reg, tg.kind, "k_qft_sweep_tma");
 }
 
 }  // namespace
 
 static int launch_by_shape(qcs_register *reg, int shape_id, const CUtensorMap &tmap, const pipe_params &P, size_t smem,
-                           cudaStream_t stream);
+                           const qft::sweep_target &tg);
 
 int qcs_pipeline_tile_bits(const qcs_register *reg)
 {
@@ -425,7 +425,7 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
         QCS_CUDA(cudaMalloc((void **) &P.timing, 16 * 8 * (size_t) reg->sm_count));
         QCS_CUDA(cudaMemsetAsync(P.timing, 0, 16 * 8 * (size_t) reg->sm_count, tg.stream));
     }
-    const int rc = launch_by_shape(reg, shape_id, tmap, P, smem, tg.stream);
+    const int rc = launch_by_shape(reg, shape_id, tmap, P, smem, tg);
     if (timing_on && rc == QCS_NO_ERROR) {
         std::vector<unsigned long long> h(16 * (size_t) reg->sm_count);
         QCS_CUDA(cudaMemcpyAsync(h.data(), P.timing, h.size() * 8, cudaMemcpyDeviceToHost, tg.stream));
@@ -445,14 +445,14 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
 }
 
 static int launch_by_shape(qcs_register *reg, int shape_id, const CUtensorMap &tmap, const pipe_params &P, size_t smem,
-                           cudaStream_t stream)
+                           const qft::sweep_target &tg)
 {
     switch (shape_id) {
-        case 1: return launch_shape<11, 6, 3, 128>(reg, tmap, P, smem, stream);
-        case 2: return launch_shape<11, 6, 6, 64>(reg, tmap, P, smem, stream);
-        case 3: return launch_shape<12, 3, 1, 256>(reg, tmap, P, smem, stream);
-        case 4: return launch_shape<12, 3, 3, 64>(reg, tmap, P, smem, stream);
-        case 5: return launch_shape<11, 6, 2, 128>(reg, tmap, P, smem, stream);
-        default: return launch_shape<12, 3, 3, 128>(reg, tmap, P, smem, stream);
+        case 1: return launch_shape<11, 6, 3, 128>(reg, tmap, P, smem, tg);
+        case 2: return launch_shape<11, 6, 6, 64>(reg, tmap, P, smem, tg);
+        case 3: return launch_shape<12, 3, 1, 256>(reg, tmap, P, smem, tg);
+        case 4: return launch_shape<12, 3, 3, 64>(reg, tmap, P, smem, tg);
+        case 5: return launch_shape<11, 6, 2, 128>(reg, tmap, P, smem, tg);
+        default: return launch_shape<12, 3, 3, 128>(reg, tmap, P, smem, tg);
     }
 }

@@ -96,6 +96,28 @@ def main():
         got = gather_state(sh, rank, world)
         check(f"n={n} M={M} gate-by-gate", got, single.get_state() if rank == 0 else None, exact=True)
 
+        # arbitrary gates with global target / control qubits
+        U1 = np.array([[0.6, 0.8j], [0.8j, 0.6]])
+        U2 = np.array([[np.exp(0.3j), 0.0], [0.0, np.exp(-1.1j)]]) @ (np.array([[1, 1], [1, -1]]) / math.sqrt(2.0))
+        def general(r):
+            r.apply_gate(n - 1, U1)
+            r.apply_controlled_gate(1, n - 1, U2)
+            r.apply_controlled_gate(n - 1, 4, U1)
+            if world > 2:
+                r.apply_controlled_gate(n - 1, n - 2, U2)
+        both(general)
+        got = gather_state(sh, rank, world)
+        check(f"n={n} M={M} arbitrary gates", got, single.get_state() if rank == 0 else None)
+
+        # sampling without collapse
+        rs = [0.0, 0.2, 0.5, 0.93, 1.0]
+        a = sh.sample_states(rs)
+        if rank == 0:
+            b = single.sample_states(rs)
+            print(f"[dist] n={n} sample_states: {a} vs {b}", flush=True)
+            if a != b:
+                failures.append("sample_states")
+
         # fused inverse / forward QFT across the global qubits
         both(lambda r: r.set_option(q.OPT_FUSION, 1))
         both(lambda r: r.inverse_QFT())

@@ -1,0 +1,139 @@
+"""GPU tests of the rows SURVEY 8(f) ranks as "next": sampling without collapse, state
+dump / load, arbitrary (controlled) single-qubit gates.  Where the reference has a
+counterpart (Hadamard, controlled phase, measure_state) the check is against the oracle;
+otherwise against a dense numpy application of the same 2x2 matrix."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def random_state(n, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    return v / np.linalg.norm(v)
+
+
+def numpy_gate(v, n, q, U, c=None):
+    """dense application: amp'[.., b_q, ..] = sum_k U[b_q][k] amp[.., k, ..], where bit c is 1"""
+    t = v.reshape([2] * n)                        # axis 0 = qubit n-1 ... axis n-1 = qubit 0
+    ax = n - 1 - q
+    out = np.moveaxis(np.tensordot(U, np.moveaxis(t, ax, 0), axes=([1], [0])), 0, ax)
+    if c is not None:
+        sel = [slice(None)] * n
+        sel[n - 1 - c] = 0
+        out[tuple(sel)] = t[tuple(sel)]
+    return out.reshape(-1)
+
+
+def random_unitary(rng):
+    a = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+    qm, r = np.linalg.qr(a)
+    return qm * (np.diag(r) / np.abs(np.diag(r)))
+
+
+@pytest.mark.parametrize("n", [3, 9, 14, 20])
+def test_arbitrary_gate_matches_numpy(qcs, n):
+    rng = np.random.default_rng(n)
+    v = random_state(n, 100 + n)
+    with qcs.Register(n, 0) as reg:
+        reg.set_state(v)
+        want = v
+        for _ in range(6):
+            U = random_unitary(rng)
+            q = int(rng.integers(n))
+            if rng.random() < 0.5:
+                reg.apply_gate(q, U)
+                want = numpy_gate(want, n, q, U)
+            else:
+                c = int(rng.integers(n - 1))
+                c = c + 1 if c >= q else c
+                reg.apply_controlled_gate(c, q, U)
+                want = numpy_gate(want, n, q, U, c)
+        assert rel_l2(reg.get_state(), want) <= TOL
+        assert abs(reg.norm2() - 1.0) < 1e-12
+
+
+def test_gate_special_cases_agree_with_reference_gates(qcs, oracle_built):
+    """U = H and U = diag(1, e^{i theta}) controlled reproduce hadamard_gate / c_phase_shift_gate
+    (qc_shor.c:442-565) to rounding; a non-unitary U is applied as given."""
+    n = 12
+    o = oracle_built.Restatement(n, 0)
+    o.fill_synthetic(3)
+    o.scale(1.0 / math.sqrt(o.norm2()))
+    base = o.get_state().copy()
+    o.hadamard_gate(5)
+    o.c_phase_shift_gate(7, 2, 0.7)
+    o.hadamard_gate(0)
+    H = np.array([[1, 1], [1, -1]]) / math.sqrt(2.0)
+    P = np.diag([1.0, np.exp(0.7j)])
+    with qcs.Register(n, 0) as reg:
+        reg.set_state(base)
+        reg.apply_gate(5, H)
+        reg.apply_controlled_gate(7, 2, P)
+        reg.apply_gate(0, H)
+        assert rel_l2(reg.get_state(), o.get_state()) <= TOL
+        with pytest.raises(qcs.QcsError):
+            reg.apply_gate(n, H)
+        with pytest.raises(qcs.QcsError):
+            reg.apply_controlled_gate(3, 3, H)
+        reg.set_state(base)
+        reg.apply_gate(4, np.array([[2.0, 0.0], [0.0, 0.0]]))
+        assert abs(reg.norm2() - 4.0 * np.sum(np.abs(base.reshape(-1, 2, 16)[:, 0, :]) ** 2)) < 1e-12
+
+
+@pytest.mark.parametrize("L,M", [(3, 4), (10, 0), (18, 0), (20, 1)])
+def test_sampling_without_collapse_matches_measure_state(qcs, oracle_built, L, M):
+    """Every sampled index equals what measure_state returns for the same r (oracle for small
+    registers, the engine's own measure_state -- pinned to the oracle elsewhere -- for all)."""
+    n = L + M
+    rs = [0.0, 1e-9, 0.1234, 0.5, 0.77, 0.999999, 1.0, 1.5]
+    with qcs.Register(L, M) as reg:
+        reg.fill_synthetic(40 + n)
+        reg.scale(1.0 / math.sqrt(reg.norm2()))
+        state = reg.get_state().copy()
+        got = reg.sample_states(rs)
+        assert np.array_equal(reg.get_state().view(np.float64), state.view(np.float64)), "sampling must not collapse"
+        want = []
+        for r in rs:
+            reg.set_state(state)
+            want.append(reg.measure_state(r))
+        assert got == want
+        if n <= 20:
+            o = oracle_built.Restatement(L, M)
+            ow = []
+            for r in rs:
+                o.set_state(state)
+                ow.append(o.measure_state(r))
+            assert got == ow
+
+
+def test_save_and_load_state(qcs, tmp_path):
+    n = 23                                          # 128 MiB: two pieces
+    path = os.path.join(tmp_path, "state.qcs")
+    with qcs.Register(n - 2, 2) as reg:
+        reg.fill_synthetic(5)
+        reg.scale(1.0 / math.sqrt(reg.norm2()))
+        reg.inverse_QFT()
+        want = reg.get_state().copy()
+        reg.save_state(path)
+        assert os.path.getsize(path) == 64 + 16 * (1 << n)
+        # the payload is the interleaved (re, im) array of gsl_vector_complex.data
+        raw = np.fromfile(path, dtype=np.float64, offset=64)
+        assert np.array_equal(raw, want.view(np.float64))
+        reg.reset_register()
+        reg.load_state(path)
+        assert np.array_equal(reg.get_state().view(np.float64), want.view(np.float64))
+    with qcs.Register(n - 1, 1) as other:           # a different register shape refuses the file
+        with pytest.raises(qcs.QcsError) as e:
+            other.load_state(path)
+        assert e.value.code == qcs.BAD_ARGUMENTS
+    with qcs.Register(4, 0) as small:
+        with pytest.raises(qcs.QcsError):
+            small.load_state(os.path.join(tmp_path, "missing.qcs"))
