@@ -210,3 +210,58 @@ def test_dense_block_dmma(qcs, oracle_built, k, n):
         dense.apply_dense_block(k, q_)
         want = (v.reshape(-1, R) @ q_.T).reshape(-1)
         assert rel_l2(dense.get_state(), want) <= TOL
+
+
+@pytest.mark.parametrize("shape", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("L,M,run_bits", [(18, 0, 3), (19, 2, 4), (22, 0, 3)])
+def test_every_pipeline_shape_matches_oracle(qcs, oracle_built, shape, L, M, run_bits):
+    """QCS_OPT_PIPE_SHAPE: each instantiated shape of the TMA pipeline (tile size, ring depth,
+    consumer groups) against the oracle, inverse and forward."""
+    n = L + M
+    o = oracle_built.Restatement(L, M)
+    o.fill_synthetic(900 + n)
+    o.scale(1.0 / math.sqrt(o.norm2()))
+    base = o.get_state().copy()
+    o.inverse_QFT()
+    with qcs.Register(L, M) as reg:
+        reg.set_option(qcs.OPT_PIPE_SHAPE, shape)
+        reg.set_option(qcs.OPT_MIN_RUN_BITS, run_bits)
+        reg.set_state(base)
+        reg.inverse_QFT()
+        assert rel_l2(reg.get_state(), o.get_state()) <= TOL
+        reg.QFT()
+        assert rel_l2(reg.get_state(), base) <= TOL
+
+
+def test_full_size_n30_properties(qcs):
+    """BASELINE configs[2] at its full size (n = 30, 16 GiB), through size-independent properties:
+    closed form of inverse_QFT on a basis state, unitarity (norm), QFT undoing inverse_QFT on the
+    synthetic state (probed amplitudes), linearity in a global phase."""
+    n = 30
+    N = 1 << n
+    k = 0x1C0FFEE1 % N
+    probes = [0, 1, 4097, 123456789 % N, N - 1, N // 2 + 77, 0x2AAAAAAA % N]
+    with qcs.Register(n, 0) as reg:
+        reg.reset_register()
+        reg.set_state(np.array([0j, 0j]), first=0)
+        reg.set_state(np.array([1 + 0j]), first=k)
+        reg.inverse_QFT()
+        assert abs(reg.norm2() - 1.0) < 1e-12
+        for j in probes:
+            got = reg.get_state(bitrev(j, n), 1)[0]
+            want = np.exp(2j * math.pi * ((j * k) % N) / N) / math.sqrt(N)
+            assert abs(got - want) <= 1e-12 * abs(want), j
+        reg.fill_synthetic(1234)
+        reg.scale(1.0 / math.sqrt(reg.norm2()))
+        before = np.array([reg.get_state(i, 1)[0] for i in probes])
+        reg.inverse_QFT()
+        assert abs(reg.norm2() - 1.0) < 1e-12
+        mid = np.array([reg.get_state(i, 1)[0] for i in probes])
+        reg.QFT()
+        after = np.array([reg.get_state(i, 1)[0] for i in probes])
+        assert np.max(np.abs(after - before)) <= 1e-12 * np.max(np.abs(before)) * 10
+        # linearity: i * state -> i * transformed state
+        reg.apply_gate(0, np.array([[1j, 0], [0, 1j]]))
+        reg.inverse_QFT()
+        mid2 = np.array([reg.get_state(i, 1)[0] for i in probes])
+        assert np.max(np.abs(mid2 - 1j * mid)) <= 1e-12 * np.max(np.abs(mid)) * 10
