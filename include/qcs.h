@@ -89,10 +89,7 @@ enum {
     /* sharded registers with peer memory: log2 of the contiguous run (amplitudes per TMA row) of
      * the one sweep that covers the global qubits.  That sweep is NVLink-bound, so it prefers
      * long rows to many stage bits. */
-    QCS_OPT_GLOBAL_RUN_BITS = 9,
-    /* 1 (default): in the pipelined sweep the two halves of a 2^12 tile are stored and refilled
-     * separately, the first while the last step is still working on the second. */
-    QCS_OPT_SPLIT_TILES = 10
+    QCS_OPT_GLOBAL_RUN_BITS = 9
 };
 
 /* kernel classes reported by qcs_profile_get */

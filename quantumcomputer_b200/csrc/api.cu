@@ -191,7 +191,6 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->opt_pipe_shape = -1;
     reg->opt_min_run_bits = 3;
     reg->opt_global_run_bits = 7;
-    reg->opt_split_tiles = 1;
     reg->opt_prefetch_tiles = 0;     // measured: L2 prefetch slows the sweep down (profiles/README.md)
     reg->d_meas = nullptr;
     reg->fusing = 0;
@@ -318,7 +317,6 @@ extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
             if (value < 1 || value > 7) return QCS_BAD_ARGUMENTS;
             reg->opt_min_run_bits = (int) value;
             return QCS_NO_ERROR;
-        case QCS_OPT_SPLIT_TILES: reg->opt_split_tiles = value != 0; return QCS_NO_ERROR;
         case QCS_OPT_GLOBAL_RUN_BITS:
             if (value < 1 || value > 7) return QCS_BAD_ARGUMENTS;
             reg->opt_global_run_bits = (int) value;
@@ -343,7 +341,6 @@ extern "C" long long qcs_get_option(const qcs_register *reg, int option)
         case QCS_OPT_PIPE_SHAPE: return reg->opt_pipe_shape;
         case QCS_OPT_MIN_RUN_BITS: return reg->opt_min_run_bits;
         case QCS_OPT_GLOBAL_RUN_BITS: return reg->opt_global_run_bits;
-        case QCS_OPT_SPLIT_TILES: return reg->opt_split_tiles;
         case QCS_OPT_PREFETCH_TILES: return reg->opt_prefetch_tiles;
         default: return -1;
     }

@@ -52,7 +52,6 @@ struct qcs_register {
     int opt_prefetch_tiles;       // L2 prefetch distance of the pipelined sweep (tiles)
     int opt_pipeline;             // 1: TMA/mbarrier pipelined sweep kernel where it applies
     int opt_pipe_shape;           // which instantiated pipeline shape (qft_pipeline.cu kShapes)
-    int opt_split_tiles;          // 1: half tiles are stored / refilled separately in the pipelined sweep
     int opt_global_run_bits;      // log2 of the contiguous run of the sweep over the global qubits (peer memory)
     int opt_min_run_bits;         // log2 of the shortest contiguous run (amplitudes) a strided tile may use
     int opt_measure_sequential;   // 1: always use the single-CTA sequential scan

@@ -172,13 +172,11 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
                                          const sweep_step S, int t, uint64_t base, bool from_global,
                                          bool to_global, bool apply_scale, double scale,
                                          unsigned tid, unsigned nthreads, const diag_gate *diag = nullptr,
-                                         int n_diag = 0, uint64_t index_or = 0, unsigned c_begin = 0,
-                                         unsigned c_count = 0)
+                                         int n_diag = 0, uint64_t index_or = 0)
 {
-    // columns [c_begin, c_begin + c_count) of the step (c_count == 0: all of them)
-    const unsigned c_end = c_count ? c_begin + c_count : 1u << (t - S.r);
+    const unsigned n_cols = 1u << (t - S.r);
     const unsigned low_mask = (1u << S.s) - 1u;
-    for (unsigned c = c_begin + tid; c < c_end; c += nthreads) {
+    for (unsigned c = tid; c < n_cols; c += nthreads) {
         const unsigned e_base = ((c >> S.s) << (S.s + S.r)) | (c & low_mask);
         double2 *g = amp + base + G.spread(e_base);
         const uint64_t g_stride = 1ull << G.phys(S.s);
@@ -256,14 +254,13 @@ __device__ __forceinline__ void dispatch_step(double2 *amp, double2 *tile, const
                                               const tile_geom G, const sweep_step S, int t, uint64_t base,
                                               bool from_global, bool to_global, bool apply_scale, double scale,
                                               unsigned tid, unsigned nthreads, const diag_gate *diag = nullptr,
-                                              int n_diag = 0, uint64_t index_or = 0, unsigned c_begin = 0,
-                                              unsigned c_count = 0)
+                                              int n_diag = 0, uint64_t index_or = 0)
 {
     switch (S.r) {
-        case 4: run_step<16, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or, c_begin, c_count); break;
-        case 3: run_step<8, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or, c_begin, c_count); break;
-        case 2: run_step<4, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or, c_begin, c_count); break;
-        default: run_step<2, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or, c_begin, c_count); break;
+        case 4: run_step<16, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
+        case 3: run_step<8, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
+        case 2: run_step<4, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
+        default: run_step<2, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
     }
 }
 

@@ -44,8 +44,6 @@ struct pipe_params {
     int lo_gap;             // g_lo - a (strided) or -1 (contiguous final sweep)
     int prefetch;           // tiles ahead of the load that are prefetched into L2 (0: off)
     int n_boxes;            // TMA boxes per tile (a box has at most 256 rows)
-    int parts;              // 2: the tile's halves (top tile bit) are stored and refilled separately
-                            // while the last step is still working on the other one; 1: whole tiles
     int box_rows;
     uint32_t box_bytes;
     unsigned long long *timing;   // -DQCS_PIPE_TIMING builds only: per-CTA cycle counters
@@ -149,10 +147,8 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
     double2 *wcol = stage_buf + (size_t) STAGES * (1u << TB);
     double2 *wbase = wcol + P.d.wcol_total;                                 // [GROUPS][kMaxSteps]
     uint64_t *bars = (uint64_t *) (wbase + GROUPS * kMaxSteps);
-    // full[STAGES]; computed[STAGES][2] and empty[STAGES][2]: one per half tile
-    uint64_t *full = bars, *computed = bars + STAGES, *empty = bars + 3 * STAGES;
-    diag_gate *sdiag = (diag_gate *) (bars + 5 * STAGES);
-    const int parts = P.parts, boxes_per_part = P.n_boxes / P.parts;
+    uint64_t *full = bars, *computed = bars + STAGES, *empty = bars + 2 * STAGES;
+    diag_gate *sdiag = (diag_gate *) (bars + 3 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     tile_geom G;
@@ -164,10 +160,8 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&full[s], 1);
-            for (int h = 0; h < 2; h++) {
-                mbar_init(&computed[2 * s + h], 1);
-                mbar_init(&empty[2 * s + h], 1);
-            }
+            mbar_init(&computed[s], 1);
+            mbar_init(&empty[s], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -207,18 +201,14 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
                     tile_coords<TB>(P, P.d.tile_first + blockIdx.x + (k + P.prefetch) * gridDim.x, c0, c1, c2);
                     for (int b = 0; b < P.n_boxes; b++) tma_prefetch_3d(&tmap, c0, c1 + b * P.box_rows, c2);
                 }
+                const long long t0 = QCS_TICK(P);
+                mbar_wait(&empty[s], (round & 1u) ^ 1u);
+                QCS_TIMING_ADD(P, 0, QCS_TICK(P) - t0);
                 tile_coords<TB>(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
+                mbar_expect_tx(&full[s], kTileBytes);
                 unsigned char *dst = (unsigned char *) (stage_buf + (size_t) s * (1u << TB));
-                for (int h = 0; h < parts; h++) {
-                    // a half is refilled as soon as its store has read it, while the group that owns
-                    // the stage may still be in the last step of the other half
-                    const long long t0 = QCS_TICK(P);
-                    mbar_wait(&empty[2 * s + h], (round & 1u) ^ 1u);
-                    QCS_TIMING_ADD(P, 0, QCS_TICK(P) - t0);
-                    if (h == 0) mbar_expect_tx(&full[s], kTileBytes);
-                    for (int b = h * boxes_per_part; b < (h + 1) * boxes_per_part; b++)
-                        tma_load_3d(dst + (size_t) b * P.box_bytes, &tmap, &full[s], c0, c1 + b * P.box_rows, c2);
-                }
+                for (int b = 0; b < P.n_boxes; b++)
+                    tma_load_3d(dst + (size_t) b * P.box_bytes, &tmap, &full[s], c0, c1 + b * P.box_rows, c2);
             }
         }
     } else if (warp == 1) {
@@ -227,21 +217,19 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
             for (uint64_t k = 0; k < my_tiles; k++) {
                 const int s = (int) (k % STAGES);
                 const uint32_t round = (uint32_t) (k / STAGES);
+                const long long t0 = QCS_TICK(P);
+                mbar_wait(&computed[s], round & 1u);
+                const long long t1 = QCS_TICK(P);
                 int c0, c1, c2;
                 tile_coords<TB>(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
                 const unsigned char *src = (const unsigned char *) (stage_buf + (size_t) s * (1u << TB));
-                for (int h = 0; h < parts; h++) {
-                    const long long t0 = QCS_TICK(P);
-                    mbar_wait(&computed[2 * s + h], round & 1u);
-                    const long long t1 = QCS_TICK(P);
-                    for (int b = h * boxes_per_part; b < (h + 1) * boxes_per_part; b++)
-                        tma_store_3d(&tmap, src + (size_t) b * P.box_bytes, c0, c1 + b * P.box_rows, c2);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    QCS_TIMING_ADD(P, 1, t1 - t0);               // waiting for a computed (half) tile
-                    QCS_TIMING_ADD(P, 2, QCS_TICK(P) - t1);      // the store reading shared memory
-                    mbar_arrive(&empty[2 * s + h]);
-                }
+                for (int b = 0; b < P.n_boxes; b++)
+                    tma_store_3d(&tmap, src + (size_t) b * P.box_bytes, c0, c1 + b * P.box_rows, c2);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                QCS_TIMING_ADD(P, 1, t1 - t0);               // waiting for a computed tile
+                QCS_TIMING_ADD(P, 2, QCS_TICK(P) - t1);      // the store reading shared memory
+                mbar_arrive(&empty[s]);
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
@@ -272,21 +260,14 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
                 const sweep_step S = P.d.step[st];
                 const bool last = st == P.d.n_steps - 1;
                 const double2 wb = my_wbase[st];
-                // the last step runs half by half (the halves are the column ranges of a step that
-                // does not touch the top tile bit), handing each finished half to the store warp
-                const int pieces = last ? parts : 1;
-                const unsigned piece_cols = (1u << (TB - S.r)) / (unsigned) pieces;
-                for (int h = 0; h < pieces; h++) {
-                    const unsigned cb = (unsigned) h * piece_cols, cc = pieces > 1 ? piece_cols : 0u;
-                    if (P.d.hadamard_only) dispatch_step<true, false>(nullptr, tile, wcol + S.col_off, wb, G, S, TB, base, false, false, last, P.d.scale, tig, GT, sdiag, P.d.n_diag, P.d.index_or, cb, cc);
-                    else if (inv) dispatch_step<true>(nullptr, tile, wcol + S.col_off, wb, G, S, TB, base, false, false, last, P.d.scale, tig, GT, nullptr, 0, 0, cb, cc);
-                    else dispatch_step<false>(nullptr, tile, wcol + S.col_off, wb, G, S, TB, base, false, false, last, P.d.scale, tig, GT, nullptr, 0, 0, cb, cc);
-                    if (last) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
-                    group_barrier(group, GT);
-                    if (last && tig == 0) mbar_arrive(&computed[2 * s + h]);
-                }
+                if (P.d.hadamard_only) dispatch_step<true, false>(nullptr, tile, wcol + S.col_off, wb, G, S, TB, base, false, false, last, P.d.scale, tig, GT, sdiag, P.d.n_diag, P.d.index_or);
+                else if (inv) dispatch_step<true>(nullptr, tile, wcol + S.col_off, wb, G, S, TB, base, false, false, last, P.d.scale, tig, GT);
+                else dispatch_step<false>(nullptr, tile, wcol + S.col_off, wb, G, S, TB, base, false, false, last, P.d.scale, tig, GT);
+                if (last) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
+                group_barrier(group, GT);
             }
             if (tig == 0) {
+                mbar_arrive(&computed[s]);
                 QCS_TIMING_ADD(P, 4 + 2 * group, t1 - t0);              // waiting for the load
                 QCS_TIMING_ADD(P, 5 + 2 * group, QCS_TICK(P) - t1);     // the steps
             }
@@ -336,7 +317,7 @@ constexpr int kNumShapes = (int) (sizeof kShapes / sizeof kShapes[0]);
 size_t pipe_smem(const pipe_shape &sh, const qft::sweep_desc &d)
 {
     return (size_t) sh.stages * ((size_t) 16 << sh.tb) + 16 * (size_t) d.wcol_total + 16 * (size_t) sh.groups * kMaxSteps +
-           8 * 5 * (size_t) sh.stages + sizeof(diag_gate) * (size_t) d.n_diag + 1024;
+           8 * 3 * (size_t) sh.stages + sizeof(diag_gate) * (size_t) d.n_diag + 1024;
 }
 
 template <int TB, int STAGES, int GROUPS, int GT>
@@ -423,9 +404,6 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
     P.box_rows = rows < 256u ? (int) rows : 256;             // a box dimension is at most 256
     P.n_boxes = (int) (rows / (unsigned) P.box_rows);
     P.box_bytes = (uint32_t) (((size_t) 16 << sh.tb) / (size_t) P.n_boxes);
-    // half-tile hand-over needs two boxes and a last step below the top tile bit
-    const qft::sweep_step &last_step = plan.d.step[plan.d.n_steps - 1];
-    P.parts = (reg->opt_split_tiles && P.n_boxes >= 2 && last_step.s + last_step.r < sh.tb) ? 2 : 1;
     box[1] = (cuuint32_t) P.box_rows;
     box[2] = 1;
     CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, tg.amp, dims, strides, box, estr,

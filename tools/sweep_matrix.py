@@ -16,7 +16,6 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 shapes = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2, 3, 4, 5, 6]
 directs = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0]
 runs = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [3]
-split = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 N = 1 << n
 if len(shapes) > 1:
     # one process per shape under a timeout: an experimental shape that hangs must not take
@@ -24,7 +23,7 @@ if len(shapes) > 1:
     for sh in shapes:
         try:
             subprocess.run([sys.executable, __file__, str(n), str(reps), str(sh), ",".join(map(str, directs)),
-                            ",".join(map(str, runs)), str(split)], timeout=90)
+                            ",".join(map(str, runs))], timeout=90)
         except subprocess.TimeoutExpired:
             print(json.dumps({"n": n, "shape": sh, "error": "timeout"}), flush=True)
     sys.exit(0)
@@ -40,7 +39,6 @@ with q.Register(n, 0) as reg:
             for run_bits in runs:
                 reg.set_option(q.OPT_PIPE_SHAPE, shape)
                 reg.set_option(q.OPT_MIN_RUN_BITS, run_bits)
-                reg.set_option(q.OPT_SPLIT_TILES, split)
                 # correctness: inverse_QFT |k> = e^{2 pi i jk/N}/sqrt(N) at bit-reversed j
                 k = 0x1C0FFEE1 % N
                 reg.reset_register()
@@ -66,7 +64,7 @@ with q.Register(n, 0) as reg:
                 prof = reg.profile()
                 reg.set_option(q.OPT_PROFILE, 0)
                 launches, kms, kbytes = prof["tile_sweep"]
-                print(json.dumps({"n": n, "shape": shape, "direct_store": direct, "min_run_bits": run_bits, "split_tiles": split,
+                print(json.dumps({"n": n, "shape": shape, "direct_store": direct, "min_run_bits": run_bits,
                                   "ms_per_iqft": round(ms, 3), "sweeps_per_iqft": launches // reps,
                                   "sweep_GBps": round(kbytes / (kms * 1e-3) / 1e9, 1),
                                   "gates_per_s": round((n + n * (n - 1) // 2) / (ms * 1e-3), 1),
