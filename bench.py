@@ -246,6 +246,10 @@ def run_ours(args):
         reg.set_option(q.OPT_MIN_RUN_BITS, args.min_run_bits)
     if args.global_run_bits > 0:
         reg.set_option(q.OPT_GLOBAL_RUN_BITS, args.global_run_bits)
+    if args.overlap_slices >= 0:
+        reg.set_option(q.OPT_OVERLAP_SLICES, args.overlap_slices)
+    if args.global_sms > 0:
+        reg.set_option(q.OPT_GLOBAL_SMS, args.global_sms)
 
     if circuit is not None:
         args.no_cpu_baseline = True                  # the CPU arm times the headline (iqft) workload
@@ -399,6 +403,8 @@ def main():
     ap.add_argument("--pipe-shape", type=int, default=-1)
     ap.add_argument("--min-run-bits", type=int, default=0)
     ap.add_argument("--global-run-bits", type=int, default=0)
+    ap.add_argument("--overlap-slices", type=int, default=-1)
+    ap.add_argument("--global-sms", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -89,7 +89,14 @@ enum {
     /* sharded registers with peer memory: log2 of the contiguous run (amplitudes per TMA row) of
      * the one sweep that covers the global qubits.  That sweep is NVLink-bound, so it prefers
      * long rows to many stage bits. */
-    QCS_OPT_GLOBAL_RUN_BITS = 9
+    QCS_OPT_GLOBAL_RUN_BITS = 9,
+    /* sharded inverse QFT with peer memory: the sweep over the global qubits runs in this many
+     * slices (a power of two, default 4) on a second stream and a subset of the SMs
+     * (QCS_OPT_GLOBAL_SMS, default 48) while the strided local sweeps of the slices that are
+     * already complete run on the other SMs: the NVLink exchange overlaps the HBM-bound local
+     * work.  0 or 1: one after the other. */
+    QCS_OPT_OVERLAP_SLICES = 10,
+    QCS_OPT_GLOBAL_SMS = 11
 };
 
 /* kernel classes reported by qcs_profile_get */

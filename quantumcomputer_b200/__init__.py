@@ -17,7 +17,7 @@ from . import _lib
 NO_ERROR, INSUFFICIENT_MEMORY, BAD_ARGUMENTS, PERIOD_NOT_FOUND, UNKNOWN_ERROR = range(5)
 POW_VERBATIM, POW_MODULAR = 0, 1
 OPT_FUSION, OPT_PROFILE, OPT_TILE_BITS, OPT_MEASURE_SEQUENTIAL, OPT_PIPELINE, OPT_PREFETCH_TILES = 1, 2, 3, 4, 5, 6
-OPT_PIPE_SHAPE, OPT_MIN_RUN_BITS, OPT_GLOBAL_RUN_BITS = 7, 8, 9
+OPT_PIPE_SHAPE, OPT_MIN_RUN_BITS, OPT_GLOBAL_RUN_BITS, OPT_OVERLAP_SLICES, OPT_GLOBAL_SMS = 7, 8, 9, 10, 11
 KERNEL_CLASSES = ["hadamard", "cphase", "amodc", "fill", "reduce", "tile_sweep",
                   "modexp_sweep", "exchange", "scale", "dense_block", "diag_multi", "global_sweep", "gate_1q"]
 

@@ -191,6 +191,8 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->opt_pipe_shape = -1;
     reg->opt_min_run_bits = 3;
     reg->opt_global_run_bits = 7;
+    reg->opt_overlap_slices = 4;
+    reg->opt_global_sms = 48;
     reg->opt_prefetch_tiles = 0;     // measured: L2 prefetch slows the sweep down (profiles/README.md)
     reg->d_meas = nullptr;
     reg->fusing = 0;
@@ -317,6 +319,14 @@ extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
             if (value < 1 || value > 7) return QCS_BAD_ARGUMENTS;
             reg->opt_min_run_bits = (int) value;
             return QCS_NO_ERROR;
+        case QCS_OPT_OVERLAP_SLICES:
+            if (value < 0 || value > 8 || (value & (value - 1)) != 0) return QCS_BAD_ARGUMENTS;
+            reg->opt_overlap_slices = (int) value;
+            return QCS_NO_ERROR;
+        case QCS_OPT_GLOBAL_SMS:
+            if (value < 1 || value > 1024) return QCS_BAD_ARGUMENTS;
+            reg->opt_global_sms = (int) value;
+            return QCS_NO_ERROR;
         case QCS_OPT_GLOBAL_RUN_BITS:
             if (value < 1 || value > 7) return QCS_BAD_ARGUMENTS;
             reg->opt_global_run_bits = (int) value;
@@ -341,6 +351,8 @@ extern "C" long long qcs_get_option(const qcs_register *reg, int option)
         case QCS_OPT_PIPE_SHAPE: return reg->opt_pipe_shape;
         case QCS_OPT_MIN_RUN_BITS: return reg->opt_min_run_bits;
         case QCS_OPT_GLOBAL_RUN_BITS: return reg->opt_global_run_bits;
+        case QCS_OPT_OVERLAP_SLICES: return reg->opt_overlap_slices;
+        case QCS_OPT_GLOBAL_SMS: return reg->opt_global_sms;
         case QCS_OPT_PREFETCH_TILES: return reg->opt_prefetch_tiles;
         default: return -1;
     }

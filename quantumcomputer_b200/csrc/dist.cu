@@ -129,6 +129,7 @@ struct qcs_dist {
     cudaEvent_t ev_done[3] = {nullptr, nullptr, nullptr};   // slice transformed
     cudaEvent_t ev_tail = nullptr;
     double *h_gather = nullptr;     // pinned
+    cudaEvent_t ev_slice[16] = {};  // global-sweep slice finished on every rank (overlapped schedule)
 };
 
 extern "C" int qcs_comm_unique_id(void *id_out)
@@ -177,6 +178,8 @@ void qcs_dist_destroy(qcs_register *reg)
         if (d->ev_done[b]) cudaEventDestroy(d->ev_done[b]);
     }
     if (d->ev_tail) cudaEventDestroy(d->ev_tail);
+    for (int j = 0; j < 16; j++)
+        if (d->ev_slice[j]) cudaEventDestroy(d->ev_slice[j]);
     for (int b = 0; b < 2; b++) {
         if (d->staging[b]) cudaFree(d->staging[b]);
         if (d->recv_done[b]) cudaEventDestroy(d->recv_done[b]);
@@ -212,7 +215,7 @@ int qcs_dist_barrier(qcs_register *reg)
     return qcs_dist_allgather_double(reg, 0.0, all.data());
 }
 
-int qcs_dist_stream_barrier(qcs_register *reg)
+int qcs_dist_barrier_on(qcs_register *reg, cudaStream_t stream)
 {
     qcs_dist *d = reg->dist;
     if (!d) return QCS_NO_ERROR;
@@ -220,7 +223,20 @@ int qcs_dist_stream_barrier(qcs_register *reg)
     // reached it, i.e. after everything queued before it on every rank's stream
     reg->launches_total++;
     reg->launches[QCS_K_EXCHANGE]++;
-    QCS_NCCL(g_nccl.AllReduce(d->d_gather, d->d_gather, 1, ncclDouble, ncclSum, d->comm, reg->stream));
+    QCS_NCCL(g_nccl.AllReduce(d->d_gather, d->d_gather, 1, ncclDouble, ncclSum, d->comm, stream));
+    return QCS_NO_ERROR;
+}
+
+int qcs_dist_stream_barrier(qcs_register *reg) { return qcs_dist_barrier_on(reg, reg->stream); }
+
+cudaStream_t qcs_dist_side_stream(qcs_register *reg) { return reg->dist ? reg->dist->comm_stream : nullptr; }
+
+int qcs_dist_slice_event(qcs_register *reg, int j, cudaEvent_t *ev)
+{
+    qcs_dist *d = reg->dist;
+    if (!d || j < 0 || j >= 16) return QCS_BAD_ARGUMENTS;
+    if (!d->ev_slice[j]) QCS_CUDA(cudaEventCreateWithFlags(&d->ev_slice[j], cudaEventDisableTiming));
+    *ev = d->ev_slice[j];
     return QCS_NO_ERROR;
 }
 

@@ -52,6 +52,9 @@ struct qcs_register {
     int opt_prefetch_tiles;       // L2 prefetch distance of the pipelined sweep (tiles)
     int opt_pipeline;             // 1: TMA/mbarrier pipelined sweep kernel where it applies
     int opt_pipe_shape;           // which instantiated pipeline shape (qft_pipeline.cu kShapes)
+    int opt_overlap_slices;       // sharded QFT: the global sweep runs in this many slices, the local strided
+                                  // sweeps of a finished slice overlapping the next one (0 / 1: no overlap)
+    int opt_global_sms;           // SMs given to the (NVLink-bound) global sweep while local sweeps run beside it
     int opt_global_run_bits;      // log2 of the contiguous run of the sweep over the global qubits (peer memory)
     int opt_min_run_bits;         // log2 of the shortest contiguous run (amplitudes) a strided tile may use
     int opt_measure_sequential;   // 1: always use the single-CTA sequential scan
@@ -161,6 +164,9 @@ int qcs_dist_barrier(qcs_register *reg);
 // cross-rank barrier ordered on the register's stream (no host synchronisation): work queued
 // after it on any rank starts only when the work queued before it has finished on every rank
 int qcs_dist_stream_barrier(qcs_register *reg);
+int qcs_dist_barrier_on(qcs_register *reg, cudaStream_t stream);
+cudaStream_t qcs_dist_side_stream(qcs_register *reg);       // second stream of a sharded register
+int qcs_dist_slice_event(qcs_register *reg, int j, cudaEvent_t *ev);
 
 // ---- peer memory: peer.cu ----------------------------------------------------
 bool qcs_peer_try_alloc(qcs_register *reg, const void *comm_id);

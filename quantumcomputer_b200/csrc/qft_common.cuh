@@ -40,7 +40,9 @@ struct sweep_desc {
     int wcol_total;         // total column-twiddle entries
     int hadamard_only;      // 1: the stages are bare Hadamards (no phase gates): Walsh-Hadamard sweep
     unsigned long long y_const;   // added to the per-tile y: register bits held by the rank (sharded layouts)
-    unsigned long long tile_first; // first tile of this launch (sub-range launches that overlap an exchange)
+    unsigned long long tile_first; // first tile of this launch (sub-range launches: a rank's share, a slice)
+    int slice_pos, slice_bits;     // a launch may cover one SLICE of the tiles: the tile numbers whose bits
+    unsigned slice_val;            // [slice_pos, slice_pos + slice_bits) equal slice_val (slice_bits = 0: all)
     unsigned long long index_or;   // global index bits held by the rank (for the diagonal masks)
     int n_diag;                    // diagonal gates applied at the end of the sweep
     const diag_gate *diag;         // device pointer
@@ -49,6 +51,15 @@ struct sweep_desc {
                             // is an exact power of two whenever the stage count is even
     sweep_step step[kMaxSteps];
 };
+
+// the k-th tile of a launch -> its tile number: tile_first + k, with the slice value deposited
+__host__ __device__ __forceinline__ uint64_t tile_number(const sweep_desc &d, uint64_t k)
+{
+    const uint64_t t = d.tile_first + k;
+    if (d.slice_bits == 0) return t;
+    const uint64_t low = t & ((1ull << d.slice_pos) - 1ull);
+    return ((t >> d.slice_pos) << (d.slice_pos + d.slice_bits)) | ((uint64_t) d.slice_val << d.slice_pos) | low;
+}
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b)
 {
@@ -282,6 +293,7 @@ struct sweep_target {
     cudaStream_t stream;
     int kind = QCS_K_TILE_SWEEP;    // kernel class the launch is accounted to
     double bytes = 0.0;             // algorithmic bytes of the launch (0: 32 B per amplitude of the tiles)
+    int max_ctas = 0;               // > 0: use at most this many SMs (a concurrent launch takes the others)
 };
 
 struct sweep_plan {

@@ -67,7 +67,8 @@ k_qft_sweep(double2 *__restrict__ amp, uint64_t n_tiles, const sweep_desc P)
 
     unsigned parity = 0;
     const int lo_gap = P.g_lo - P.a;             // number of index bits between the two tile runs
-    for (uint64_t tix = P.tile_first + blockIdx.x; tix < P.tile_first + n_tiles; tix += gridDim.x, parity ^= 1u) {
+    for (uint64_t kt = blockIdx.x; kt < n_tiles; kt += gridDim.x, parity ^= 1u) {
+        const uint64_t tix = tile_number(P, kt);
         // deposit the tile number into the index bits that are not in the tile
         const uint64_t base = lo_gap > 0 ? (((tix >> lo_gap) << P.g_hi) | ((tix & ((1ull << lo_gap) - 1ull)) << P.a))
                                          : (tix << P.t);
@@ -99,6 +100,7 @@ int launch_sweep(qcs_register *reg, const sweep_target &tg, const sweep_plan &p,
     QCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
     if (per_sm < 1) return QCS_UNKNOWN_ERROR;
     uint64_t grid = (uint64_t) reg->sm_count * (uint64_t) per_sm;
+    if (tg.max_ctas > 0 && grid > (uint64_t) tg.max_ctas * (uint64_t) per_sm) grid = (uint64_t) tg.max_ctas * (uint64_t) per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
     qcs_launch_begin(reg, tg.kind, tg.bytes > 0.0 ? tg.bytes : 32.0 * (double) (p.n_tiles << p.d.t));
     kern<<<(unsigned) grid, NT, smem, tg.stream>>>(tg.amp, p.n_tiles, p.d);
@@ -276,6 +278,79 @@ int qcs_fused_sweeps_sharded(qcs_register *reg, unsigned lo, unsigned hi, bool i
         }
         return QCS_NO_ERROR;
     };
+    // ---- overlapped schedule (inverse transform) ------------------------------------------
+    // The global sweep is bound by NVLink and needs only a fraction of the SMs; the local sweeps
+    // are bound by HBM.  The tiles are cut into K slices by the index bits just above the global
+    // sweep's contiguous run, bits [a_glob, a_glob + log2 K): they are "gap" bits (neither in the
+    // tile nor stage bits) of the global sweep and of every strided local sweep whose own run is
+    // not longer, so slice j of those local sweeps touches exactly the amplitudes slice j of the
+    // global sweep produced.  Stream G: global slice 0, barrier, global slice 1, barrier, ...;
+    // stream L: after barrier j, the strided local sweeps of slice j on the other SMs.
+    int K = reg->opt_overlap_slices;
+    int sb = 0;
+    while ((1 << (sb + 1)) <= K) sb++;
+    size_t n_sliceable = 0;
+    if (inverse && K >= 2 && global_plans.size() == 1 && global_plans[0].d.g_lo > global_plans[0].d.a) {
+        for (const sweep_plan &p : local_plans) {
+            const bool strided = p.d.g_lo > p.d.a;
+            if (!strided || p.d.a > a_glob || p.d.g_lo < a_glob + sb || (p.n_tiles >> sb) == 0) break;
+            n_sliceable++;
+        }
+        const sweep_plan &g = global_plans[0];
+        if (((g.n_tiles >> reg->p_global) >> sb) == 0 || g.d.g_lo < a_glob + sb) n_sliceable = 0;
+    }
+    if (n_sliceable > 0) {
+        cudaStream_t G = qcs_dist_side_stream(reg), L = reg->stream;
+        cudaEvent_t ev;
+        QCS_TRY(qcs_dist_slice_event(reg, 15, &ev));
+        QCS_CUDA(cudaEventRecord(ev, L));
+        QCS_CUDA(cudaStreamWaitEvent(G, ev, 0));
+        QCS_TRY(qcs_dist_barrier_on(reg, G));
+        int g_sms = reg->opt_global_sms;
+        if (g_sms >= reg->sm_count) g_sms = reg->sm_count / 2;
+        for (int j = 0; j < (1 << sb); j++) {
+            sweep_plan p = global_plans[0];
+            p.d.hadamard_only = hadamard_only ? 1 : 0;
+            if (hadamard_only) p.d.wcol_total = 0;
+            const uint64_t share = (p.n_tiles >> reg->p_global) >> sb;
+            p.d.tile_first = (uint64_t) reg->rank * share;
+            p.n_tiles = share;
+            p.d.slice_pos = 0;
+            p.d.slice_bits = sb;
+            p.d.slice_val = (unsigned) j;
+            sweep_target tg = {reg->amp_all, reg->n, G};
+            tg.kind = QCS_K_GLOBAL_SWEEP;
+            tg.bytes = 2.0 * 16.0 * (double) (share << p.d.t) * (double) (reg->world - 1) / (double) reg->world;
+            tg.max_ctas = g_sms;
+            QCS_TRY(launch_plan(reg, tg, p));
+            QCS_TRY(qcs_dist_barrier_on(reg, G));
+            QCS_TRY(qcs_dist_slice_event(reg, j, &ev));
+            QCS_CUDA(cudaEventRecord(ev, G));
+            QCS_CUDA(cudaStreamWaitEvent(L, ev, 0));
+            for (size_t k = 0; k < n_sliceable; k++) {
+                sweep_plan q = local_plans[k];
+                q.d.hadamard_only = hadamard_only ? 1 : 0;
+                if (hadamard_only) q.d.wcol_total = 0;
+                q.n_tiles >>= sb;
+                q.d.tile_first = 0;
+                q.d.slice_pos = a_glob - q.d.a;
+                q.d.slice_bits = sb;
+                q.d.slice_val = (unsigned) j;
+                sweep_target tl = {reg->amp, reg->n_local, L};
+                // while global slices are still to come they keep their SMs
+                tl.max_ctas = j + 1 < (1 << sb) ? reg->sm_count - g_sms : 0;
+                QCS_TRY(launch_plan(reg, tl, q));
+            }
+        }
+        const sweep_target tl = {reg->amp, reg->n_local, L};
+        for (size_t k = n_sliceable; k < local_plans.size(); k++) {
+            sweep_plan q = local_plans[k];
+            q.d.hadamard_only = hadamard_only ? 1 : 0;
+            if (hadamard_only) q.d.wcol_total = 0;
+            QCS_TRY(launch_plan(reg, tl, q));
+        }
+        return QCS_NO_ERROR;
+    }
     if (inverse) {
         QCS_TRY(run_global());
         return run_local();

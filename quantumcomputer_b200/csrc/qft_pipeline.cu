@@ -191,20 +191,20 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
             int c0, c1, c2;
             // optional L2 prefetch a few tiles ahead of the shared-memory ring
             for (uint64_t k = 0; k < (uint64_t) P.prefetch && k < my_tiles; k++) {
-                tile_coords<TB>(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
+                tile_coords<TB>(P, tile_number(P.d, blockIdx.x + k * gridDim.x), c0, c1, c2);
                 for (int b = 0; b < P.n_boxes; b++) tma_prefetch_3d(&tmap, c0, c1 + b * P.box_rows, c2);
             }
             for (uint64_t k = 0; k < my_tiles; k++) {
                 const int s = (int) (k % STAGES);
                 const uint32_t round = (uint32_t) (k / STAGES);
                 if (P.prefetch && k + P.prefetch < my_tiles) {
-                    tile_coords<TB>(P, P.d.tile_first + blockIdx.x + (k + P.prefetch) * gridDim.x, c0, c1, c2);
+                    tile_coords<TB>(P, tile_number(P.d, blockIdx.x + (k + P.prefetch) * gridDim.x), c0, c1, c2);
                     for (int b = 0; b < P.n_boxes; b++) tma_prefetch_3d(&tmap, c0, c1 + b * P.box_rows, c2);
                 }
                 const long long t0 = QCS_TICK(P);
                 mbar_wait(&empty[s], (round & 1u) ^ 1u);
                 QCS_TIMING_ADD(P, 0, QCS_TICK(P) - t0);
-                tile_coords<TB>(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
+                tile_coords<TB>(P, tile_number(P.d, blockIdx.x + k * gridDim.x), c0, c1, c2);
                 mbar_expect_tx(&full[s], kTileBytes);
                 unsigned char *dst = (unsigned char *) (stage_buf + (size_t) s * (1u << TB));
                 for (int b = 0; b < P.n_boxes; b++)
@@ -221,7 +221,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
                 mbar_wait(&computed[s], round & 1u);
                 const long long t1 = QCS_TICK(P);
                 int c0, c1, c2;
-                tile_coords<TB>(P, P.d.tile_first + blockIdx.x + k * gridDim.x, c0, c1, c2);
+                tile_coords<TB>(P, tile_number(P.d, blockIdx.x + k * gridDim.x), c0, c1, c2);
                 const unsigned char *src = (const unsigned char *) (stage_buf + (size_t) s * (1u << TB));
                 for (int b = 0; b < P.n_boxes; b++)
                     tma_store_3d(&tmap, src + (size_t) b * P.box_bytes, c0, c1 + b * P.box_rows, c2);
@@ -242,7 +242,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
         for (uint64_t k = group; k < my_tiles; k += GROUPS) {
             const int s = (int) (k % STAGES);
             const uint32_t round = (uint32_t) (k / STAGES);
-            const uint64_t tix = P.d.tile_first + blockIdx.x + k * gridDim.x;
+            const uint64_t tix = tile_number(P.d, blockIdx.x + k * gridDim.x);
             const uint64_t base = lo_gap >= 0 ? (((tix >> lo_gap) << P.d.g_hi) | ((tix & ((1ull << lo_gap) - 1ull)) << P.d.a))
                                               : (tix << TB);
             if (!P.d.hadamard_only && tig < (unsigned) P.d.n_steps) {
@@ -326,6 +326,7 @@ int launch_shape(qcs_register *reg, const CUtensorMap &tmap, const pipe_params &
     auto kern = k_qft_sweep_tma<TB, STAGES, GROUPS, GT>;
     QCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     uint64_t grid = (uint64_t) reg->sm_count;
+    if (tg.max_ctas > 0 && grid > (uint64_t) tg.max_ctas) grid = (uint64_t) tg.max_ctas;
     if (grid > P.n_tiles) grid = P.n_tiles;
     qcs_launch_begin(reg, tg.kind, tg.bytes > 0.0 ? tg.bytes : 32.0 * (double) (P.n_tiles << TB));
     kern<<<(unsigned) grid, 64 + GROUPS * GT, smem, tg.stream>>>(tmap, P);

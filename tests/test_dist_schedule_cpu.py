@@ -230,3 +230,55 @@ def test_peer_memory_sharded_inverse_qft_schedule(oracle_built, world, L, M, a_g
         assert pr.exitcode == 0
     err = ret.get(timeout=5)
     assert err <= 1e-12, err
+
+
+# ---------------------------------------------------------------------------
+# overlapped schedule: slices of the global sweep vs slices of the strided local sweeps
+# ---------------------------------------------------------------------------
+def _tile_number(t, pos, bits, val):
+    """csrc/qft_common.cuh tile_number(): deposit the slice value into the tile number"""
+    low = t & ((1 << pos) - 1)
+    return ((t >> pos) << (pos + bits)) | (val << pos) | low
+
+
+def _tile_indices(tix, a, g_lo, g_hi):
+    """amplitudes of tile `tix` of a strided sweep with tile bits [0,a) U [g_lo,g_hi)"""
+    gap = g_lo - a
+    base = ((tix >> gap) << g_hi) | ((tix & ((1 << gap) - 1)) << a)
+    e = np.arange(1 << (a + g_hi - g_lo), dtype=np.int64)
+    return base | (e & ((1 << a) - 1)) | ((e >> a) << g_lo)
+
+
+@pytest.mark.parametrize("n,p,a_glob,g,sb,locals_", [
+    (16, 1, 4, 3, 2, [(2, 10, 13), (3, 7, 10)]),
+    (17, 2, 5, 4, 1, [(3, 9, 13)]),
+    (18, 3, 4, 3, 2, [(4, 11, 15), (2, 6, 11)]),
+])
+def test_overlap_slices_partition_and_dependencies(n, p, a_glob, g, sb, locals_):
+    """qcs_fused_sweeps_sharded, overlapped schedule: for every slice j the global-sweep tiles of
+    slice j (all ranks' shares) and the tiles of slice j of each strided local sweep (all ranks,
+    local coordinates) cover the same amplitudes, and the slices partition the register."""
+    P = 1 << p
+    n_local = n - p
+    split = n - g
+    K = 1 << sb
+    seen = np.zeros(1 << n, dtype=np.int64)
+    for j in range(K):
+        glob = np.zeros(1 << n, dtype=bool)
+        n_tiles = 1 << (n - a_glob - g)
+        share = (n_tiles >> p) >> sb
+        for r in range(P):
+            for t in range(r * share, (r + 1) * share):
+                glob[_tile_indices(_tile_number(t, 0, sb, j), a_glob, split, n)] = True
+        seen[glob] += 1
+        for (a1, g_lo, g_hi) in locals_:
+            assert a1 <= a_glob and g_lo >= a_glob + sb and g_hi <= split
+            loc = np.zeros(1 << n, dtype=bool)
+            n_tiles_local = (1 << (n_local - a1 - (g_hi - g_lo))) >> sb
+            for r in range(P):
+                for t in range(n_tiles_local):
+                    idx = _tile_indices(_tile_number(t, a_glob - a1, sb, j), a1, g_lo, g_hi)
+                    assert idx.max() < (1 << n_local)
+                    loc[(r << n_local) | idx] = True
+            assert np.array_equal(glob, loc), (j, a1, g_lo, g_hi)
+    assert np.all(seen == 1)
