@@ -91,7 +91,7 @@ enum {
      * long rows to many stage bits. */
     QCS_OPT_GLOBAL_RUN_BITS = 9,
     /* sharded inverse QFT with peer memory: the sweep over the global qubits runs in this many
-     * slices (a power of two, default 4) on a second stream and a subset of the SMs
+     * slices (a power of two <= 8, default 8) on a second stream and a subset of the SMs
      * (QCS_OPT_GLOBAL_SMS, default 48) while the strided local sweeps of the slices that are
      * already complete run on the other SMs: the NVLink exchange overlaps the HBM-bound local
      * work.  0 or 1: one after the other. */

@@ -191,7 +191,7 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->opt_pipe_shape = -1;
     reg->opt_min_run_bits = 3;
     reg->opt_global_run_bits = 7;
-    reg->opt_overlap_slices = 4;
+    reg->opt_overlap_slices = 8;
     reg->opt_global_sms = 48;
     reg->opt_prefetch_tiles = 0;     // measured: L2 prefetch slows the sweep down (profiles/README.md)
     reg->d_meas = nullptr;
