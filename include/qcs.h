@@ -249,6 +249,18 @@ int qcs_fuse_end(qcs_register *reg);
 /* gates recorded and not yet launched */
 unsigned long long qcs_fuse_pending(const qcs_register *reg);
 
+/* Host-only view of the gate-stream scheduler (no device work, usable without a GPU): writes
+ * the passes the recorded stream (kinds[i] = 0: hadamard_gate(q0[i]); 1:
+ * c_phase_shift_gate(q0[i], q1[i], .)) would be launched as on rank `rank` of a register of
+ * n_qubits sharded over world_size ranks, one text line per pass:
+ *   "sweep h=<hex mask of H qubits> [diag=<stream positions>] [after=<stream positions>]"
+ *   "hadamard q=<qubit> [after=...]"      "global h=<mask> [after=...]"      "before=<positions>"
+ * diag: diagonal gates applied inside the sweep; after / before: by standalone kernels after the
+ * pass / before every pass.  QCS_INSUFFICIENT_MEMORY when out_cap is too small. */
+int qcs_schedule_describe(unsigned n_qubits, int world_size, int rank, unsigned long long n_gates,
+                          const int *kinds, const unsigned *q0, const unsigned *q1, char *out,
+                          unsigned long long out_cap);
+
 /* Fused dense block: an arbitrary 2^k x 2^k complex matrix U (row-major,
  * interleaved re/im, k = 3 or 4) applied to qubits 0..k-1 of every basis state,
  * i.e. what a run of gates on those qubits multiplies out to (generalises

@@ -51,6 +51,43 @@ def modpow2k(a, k, Cn):
     return int(lib().qcs_modpow2k(a, k, Cn))
 
 
+def schedule_describe(n_qubits, gates, world_size=1, rank=0):
+    """Passes the gate-stream scheduler would launch for `gates` (the tuples of
+    quantumcomputer_b200.workloads: ("h", q) / ("cp", c, q, theta)); host only, no GPU needed.
+    Returns a list of dicts: {"type": "sweep"|"hadamard"|"global"|"before", "h": [qubits],
+    "diag": [stream positions], "after": [stream positions]}."""
+    kinds = np.array([0 if g[0] == "h" else 1 for g in gates], dtype=np.int32)
+    q0 = np.array([g[1] for g in gates], dtype=np.uint32)
+    q1 = np.array([g[2] if g[0] != "h" else g[1] for g in gates], dtype=np.uint32)
+    cap = 1 << 16
+    while True:
+        buf = C.create_string_buffer(cap)
+        rc = lib().qcs_schedule_describe(n_qubits, world_size, rank, len(gates), kinds.ctypes.data,
+                                         q0.ctypes.data, q1.ctypes.data, buf, cap)
+        if rc == INSUFFICIENT_MEMORY:
+            cap *= 4
+            continue
+        _check(rc, "qcs_schedule_describe")
+        break
+    passes = []
+    for line in buf.value.decode().splitlines():
+        fields = line.split()
+        entry = {"type": fields[0].split("=")[0], "h": [], "diag": [], "after": []}
+        for f in fields:
+            key, _, val = f.partition("=")
+            if key == "h":
+                mask = int(val, 16)
+                entry["h"] = [b for b in range(64) if (mask >> b) & 1]
+            elif key == "q":
+                entry["h"] = [int(val)]
+            elif key in ("diag", "after"):
+                entry[key] = [int(v) for v in val.split(",")]
+            elif key == "before":
+                entry["after"] = [int(v) for v in val.split(",")]
+        passes.append(entry)
+    return passes
+
+
 def comm_unique_id():
     buf = C.create_string_buffer(128)
     _check(lib().qcs_comm_unique_id(buf), "qcs_comm_unique_id")

@@ -53,6 +53,7 @@ SIGNATURES = [
     ("qcs_apply_controlled_gate", C.c_int, [_vp, _u, _u, _vp]),
     ("qcs_save_state", C.c_int, [_vp, C.c_char_p]),
     ("qcs_load_state", C.c_int, [_vp, C.c_char_p]),
+    ("qcs_schedule_describe", C.c_int, [_u, C.c_int, C.c_int, _ull, _vp, _vp, _vp, _vp, _ull]),
     ("qcs_fuse_begin", C.c_int, [_vp]),
     ("qcs_fuse_end", C.c_int, [_vp]),
     ("qcs_fuse_pending", _ull, [_vp]),

@@ -24,6 +24,7 @@
 #include "qft_common.cuh"
 
 #include <string.h>
+#include <string>
 
 namespace {
 
@@ -64,6 +65,7 @@ struct pass {
     unsigned q;                 // type 1
     bool top_stages;            // type 2: all global qubits at once through the qubit-swap pipeline
     std::vector<diag_gate> in_sweep;    // applied in the last step of the sweep (type 0)
+    std::vector<int> in_sweep_idx;      // ... and their positions in the recorded stream
     std::vector<int> after;             // recorded gates applied by standalone kernels after the pass
 };
 
@@ -142,11 +144,13 @@ int launch_diag_list(qcs_register *reg, const std::vector<qcs_pending_gate> &que
 
 }  // namespace
 
-int qcs_fuse_flush(qcs_register *reg)
+// The scheduler proper: host-only (it reads the register's shape and options, nothing on the
+// device), so tests can drive it without a GPU through qcs_schedule_describe.
+static int schedule_stream(const qcs_register *reg, const std::vector<qcs_pending_gate> &queue,
+                           std::vector<pass> &passes, std::vector<int> &before_all)
 {
-    if (reg->queue.empty()) return QCS_NO_ERROR;
-    std::vector<qcs_pending_gate> queue;
-    queue.swap(reg->queue);             // the per-gate calls below must not see a pending queue
+    passes.clear();
+    before_all.clear();
 
     // ---- 1. groups: {H set} then {diagonal gates}, cut in program order
     struct group { uint64_t hset = 0, dmask = 0; std::vector<int> diag; };
@@ -166,7 +170,6 @@ int qcs_fuse_flush(qcs_register *reg)
     }
 
     // ---- 2. passes
-    std::vector<pass> passes;
     const uint64_t local_mask = reg->n_local >= 64 ? ~0ull : ((1ull << reg->n_local) - 1ull);
     for (size_t gi = 0; gi < groups.size(); gi++) {
         const uint64_t hl = groups[gi].hset & local_mask, hg = groups[gi].hset & ~local_mask;
@@ -213,7 +216,6 @@ int qcs_fuse_flush(qcs_register *reg)
     }
 
     // ---- 3. place every diagonal gate
-    std::vector<int> before_all;        // no pass may precede them
     for (size_t i = 0; i < queue.size(); i++) {
         if (queue[i].kind != 1) continue;
         const uint64_t bits = (1ull << queue[i].q0) | (1ull << queue[i].q1);
@@ -232,13 +234,27 @@ int qcs_fuse_flush(qcs_register *reg)
         }
         if (best >= 0) {
             diag_gate dg;
-            if (localise(reg, queue[i], dg)) passes[(size_t) best].in_sweep.push_back(dg);
+            if (localise(reg, queue[i], dg)) {
+                passes[(size_t) best].in_sweep.push_back(dg);
+                passes[(size_t) best].in_sweep_idx.push_back((int) i);
+            }
         } else if (earliest < 0) {
             before_all.push_back((int) i);
         } else {
             passes[(size_t) earliest].after.push_back((int) i);
         }
     }
+    return QCS_NO_ERROR;
+}
+
+int qcs_fuse_flush(qcs_register *reg)
+{
+    if (reg->queue.empty()) return QCS_NO_ERROR;
+    std::vector<qcs_pending_gate> queue;
+    queue.swap(reg->queue);             // the per-gate calls below must not see a pending queue
+    std::vector<pass> passes;
+    std::vector<int> before_all;        // diagonal gates no pass may precede
+    QCS_TRY(schedule_stream(reg, queue, passes, before_all));
 
     // ---- 4. launch
     size_t need = 1024;
@@ -274,6 +290,64 @@ int qcs_fuse_flush(qcs_register *reg)
         }
         QCS_TRY(launch_diag_list(reg, queue, ps.after, d_scratch, stage));
     }
+    return QCS_NO_ERROR;
+}
+
+// Host-only view of the scheduler for tests and tooling: the passes a recorded stream would be
+// launched as, one line each, for a register of n_qubits sharded over world_size ranks
+// (library-default options).  "sweep h=<hex mask of H qubits> diag=<stream positions>",
+// "hadamard q=<qubit>", "global h=<mask>", each optionally followed by " after=<positions>" (diagonal
+// gates run by standalone kernels after the pass); a leading "before=<positions>" line lists
+// diagonal gates that precede every pass.  Gates that are the identity on this rank are omitted.
+extern "C" int qcs_schedule_describe(unsigned n_qubits, int world_size, int rank, unsigned long long n_gates,
+                                     const int *kinds, const unsigned *q0, const unsigned *q1, char *out,
+                                     unsigned long long out_cap)
+{
+    if (!out || out_cap == 0 || (n_gates && (!kinds || !q0 || !q1))) return QCS_BAD_ARGUMENTS;
+    if (n_qubits < 1 || n_qubits > 62 || world_size < 1 || (world_size & (world_size - 1)) || rank < 0 || rank >= world_size)
+        return QCS_BAD_ARGUMENTS;
+    int p = 0;
+    while ((1 << p) < world_size) p++;
+    if ((unsigned) p >= n_qubits) return QCS_BAD_ARGUMENTS;
+    qcs_register fake = {};
+    fake.n = n_qubits;
+    fake.n_local = n_qubits - (unsigned) p;
+    fake.N = 1ull << fake.n;
+    fake.N_local = 1ull << fake.n_local;
+    fake.rank = rank;
+    fake.world = world_size;
+    fake.p_global = p;
+    fake.opt_fusion = 1;
+    fake.opt_pipeline = 1;
+    fake.opt_pipe_shape = -1;
+    fake.opt_min_run_bits = 3;
+    std::vector<qcs_pending_gate> queue;
+    for (unsigned long long i = 0; i < n_gates; i++) {
+        if (q0[i] >= n_qubits || (kinds[i] == 1 && q1[i] >= n_qubits) || (kinds[i] != 0 && kinds[i] != 1)) return QCS_BAD_ARGUMENTS;
+        queue.push_back({kinds[i], q0[i], kinds[i] == 1 ? q1[i] : q0[i], 1.0, 0.0});
+    }
+    std::vector<pass> passes;
+    std::vector<int> before_all;
+    QCS_TRY(schedule_stream(&fake, queue, passes, before_all));
+    std::string text;
+    auto list = [&](const char *key, const std::vector<int> &v) {
+        if (v.empty()) return;
+        text += key;
+        for (size_t k = 0; k < v.size(); k++) text += (k ? "," : "") + std::to_string(v[k]);
+    };
+    if (!before_all.empty()) { list("before=", before_all); text += "\n"; }
+    for (const pass &ps : passes) {
+        char buf[64];
+        if (ps.type == 0) snprintf(buf, sizeof buf, "sweep h=%llx", (unsigned long long) ps.hmask);
+        else if (ps.type == 1) snprintf(buf, sizeof buf, "hadamard q=%u", ps.q);
+        else snprintf(buf, sizeof buf, "global h=%llx", (unsigned long long) ps.hmask);
+        text += buf;
+        list(" diag=", ps.in_sweep_idx);
+        list(" after=", ps.after);
+        text += "\n";
+    }
+    if (text.size() + 1 > out_cap) return QCS_INSUFFICIENT_MEMORY;
+    memcpy(out, text.c_str(), text.size() + 1);
     return QCS_NO_ERROR;
 }
 
