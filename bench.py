@@ -373,6 +373,9 @@ def run_ours(args):
                        "l2": f"state ({16 * reg.local_states / 2 ** 30:.0f} GiB per GPU) is far larger than the "
                              f"126 MB L2; no flush needed",
                        "norm_before": norm_in, "norm_after": norm_out},
+            # gates/s cannot scale with the GPU count when n grows with it (a gate on n+1 qubits is
+            # twice the work): amplitude updates per second = gates * 2^n / time is the rate that can
+            "work_rate": {"value": gates * float(1 << n) * args.steps / (ms * 1e-3), "unit": "amplitude-gate updates/s"},
             "roofline": roofline, "kernels": per_class,
             "gpu_launches": int(launches), "clocks": clocks,
         }
