@@ -278,7 +278,7 @@ int qcs_fused_sweeps_sharded(qcs_register *reg, unsigned lo, unsigned hi, bool i
         }
         return QCS_NO_ERROR;
     };
-    // ---- overlapped schedule (inverse transform) ------------------------------------------
+    // ---- overlapped schedule -----------------------------------------------------------------
     // The global sweep is bound by NVLink and needs only a fraction of the SMs; the local sweeps
     // are bound by HBM.  The tiles are cut into K slices by the index bits just above the global
     // sweep's contiguous run, bits [a_glob, a_glob + log2 K): they are "gap" bits (neither in the
@@ -289,15 +289,80 @@ int qcs_fused_sweeps_sharded(qcs_register *reg, unsigned lo, unsigned hi, bool i
     int K = reg->opt_overlap_slices;
     int sb = 0;
     while ((1 << (sb + 1)) <= K) sb++;
+    // the strided local sweeps next to the global sweep (first in the inverse order, last in the
+    // forward order) whose tiles leave the slice bits alone
     size_t n_sliceable = 0;
-    if (inverse && K >= 2 && global_plans.size() == 1 && global_plans[0].d.g_lo > global_plans[0].d.a) {
-        for (const sweep_plan &p : local_plans) {
+    if (K >= 2 && global_plans.size() == 1 && global_plans[0].d.g_lo > global_plans[0].d.a) {
+        for (size_t k = 0; k < local_plans.size(); k++) {
+            const sweep_plan &p = local_plans[inverse ? k : local_plans.size() - 1 - k];
             const bool strided = p.d.g_lo > p.d.a;
             if (!strided || p.d.a > a_glob || p.d.g_lo < a_glob + sb || (p.n_tiles >> sb) == 0) break;
             n_sliceable++;
         }
         const sweep_plan &g = global_plans[0];
         if (((g.n_tiles >> reg->p_global) >> sb) == 0 || g.d.g_lo < a_glob + sb) n_sliceable = 0;
+    }
+    // one slice of the global sweep / of a strided local sweep
+    auto global_slice = [&](int j, cudaStream_t st, int max_ctas) -> int {
+        sweep_plan p = global_plans[0];
+        p.d.hadamard_only = hadamard_only ? 1 : 0;
+        if (hadamard_only) p.d.wcol_total = 0;
+        const uint64_t share = (p.n_tiles >> reg->p_global) >> sb;
+        p.d.tile_first = (uint64_t) reg->rank * share;
+        p.n_tiles = share;
+        p.d.slice_pos = 0;
+        p.d.slice_bits = sb;
+        p.d.slice_val = (unsigned) j;
+        sweep_target tg = {reg->amp_all, reg->n, st};
+        tg.kind = QCS_K_GLOBAL_SWEEP;
+        tg.bytes = 2.0 * 16.0 * (double) (share << p.d.t) * (double) (reg->world - 1) / (double) reg->world;
+        tg.max_ctas = max_ctas;
+        return launch_plan(reg, tg, p);
+    };
+    auto local_slice = [&](size_t k, int j, cudaStream_t st, int max_ctas) -> int {
+        sweep_plan q = local_plans[k];
+        q.d.hadamard_only = hadamard_only ? 1 : 0;
+        if (hadamard_only) q.d.wcol_total = 0;
+        q.n_tiles >>= sb;
+        q.d.tile_first = 0;
+        q.d.slice_pos = a_glob - q.d.a;
+        q.d.slice_bits = sb;
+        q.d.slice_val = (unsigned) j;
+        sweep_target tl = {reg->amp, reg->n_local, st};
+        tl.max_ctas = max_ctas;
+        return launch_plan(reg, tl, q);
+    };
+    auto local_full = [&](size_t k, cudaStream_t st) -> int {
+        sweep_plan q = local_plans[k];
+        q.d.hadamard_only = hadamard_only ? 1 : 0;
+        if (hadamard_only) q.d.wcol_total = 0;
+        const sweep_target tl = {reg->amp, reg->n_local, st};
+        return launch_plan(reg, tl, q);
+    };
+    if (n_sliceable > 0 && !inverse) {
+        // forward transform: the mirror image.  L: the unsliced local sweeps, then slice by slice the
+        // strided ones; G: after a barrier, the global sweep of each finished slice.
+        cudaStream_t G = qcs_dist_side_stream(reg), L = reg->stream;
+        cudaEvent_t ev;
+        int g_sms = reg->opt_global_sms;
+        if (g_sms >= reg->sm_count) g_sms = reg->sm_count / 2;
+        const size_t first_sliced = local_plans.size() - n_sliceable;
+        for (size_t k = 0; k < first_sliced; k++) QCS_TRY(local_full(k, L));
+        for (int j = 0; j < (1 << sb); j++) {
+            // global slices of earlier j run beside these on their own SMs
+            for (size_t k = first_sliced; k < local_plans.size(); k++)
+                QCS_TRY(local_slice(k, j, L, j > 0 ? reg->sm_count - g_sms : 0));
+            QCS_TRY(qcs_dist_slice_event(reg, j, &ev));
+            QCS_CUDA(cudaEventRecord(ev, L));
+            QCS_CUDA(cudaStreamWaitEvent(G, ev, 0));
+            QCS_TRY(qcs_dist_barrier_on(reg, G));          // slice j is finished on every rank
+            QCS_TRY(global_slice(j, G, j + 1 < (1 << sb) ? g_sms : 0));
+        }
+        QCS_TRY(qcs_dist_barrier_on(reg, G));
+        QCS_TRY(qcs_dist_slice_event(reg, 15, &ev));
+        QCS_CUDA(cudaEventRecord(ev, G));
+        QCS_CUDA(cudaStreamWaitEvent(L, ev, 0));
+        return QCS_NO_ERROR;
     }
     if (n_sliceable > 0) {
         cudaStream_t G = qcs_dist_side_stream(reg), L = reg->stream;
@@ -309,46 +374,16 @@ int qcs_fused_sweeps_sharded(qcs_register *reg, unsigned lo, unsigned hi, bool i
         int g_sms = reg->opt_global_sms;
         if (g_sms >= reg->sm_count) g_sms = reg->sm_count / 2;
         for (int j = 0; j < (1 << sb); j++) {
-            sweep_plan p = global_plans[0];
-            p.d.hadamard_only = hadamard_only ? 1 : 0;
-            if (hadamard_only) p.d.wcol_total = 0;
-            const uint64_t share = (p.n_tiles >> reg->p_global) >> sb;
-            p.d.tile_first = (uint64_t) reg->rank * share;
-            p.n_tiles = share;
-            p.d.slice_pos = 0;
-            p.d.slice_bits = sb;
-            p.d.slice_val = (unsigned) j;
-            sweep_target tg = {reg->amp_all, reg->n, G};
-            tg.kind = QCS_K_GLOBAL_SWEEP;
-            tg.bytes = 2.0 * 16.0 * (double) (share << p.d.t) * (double) (reg->world - 1) / (double) reg->world;
-            tg.max_ctas = g_sms;
-            QCS_TRY(launch_plan(reg, tg, p));
+            QCS_TRY(global_slice(j, G, g_sms));
             QCS_TRY(qcs_dist_barrier_on(reg, G));
             QCS_TRY(qcs_dist_slice_event(reg, j, &ev));
             QCS_CUDA(cudaEventRecord(ev, G));
             QCS_CUDA(cudaStreamWaitEvent(L, ev, 0));
-            for (size_t k = 0; k < n_sliceable; k++) {
-                sweep_plan q = local_plans[k];
-                q.d.hadamard_only = hadamard_only ? 1 : 0;
-                if (hadamard_only) q.d.wcol_total = 0;
-                q.n_tiles >>= sb;
-                q.d.tile_first = 0;
-                q.d.slice_pos = a_glob - q.d.a;
-                q.d.slice_bits = sb;
-                q.d.slice_val = (unsigned) j;
-                sweep_target tl = {reg->amp, reg->n_local, L};
-                // while global slices are still to come they keep their SMs
-                tl.max_ctas = j + 1 < (1 << sb) ? reg->sm_count - g_sms : 0;
-                QCS_TRY(launch_plan(reg, tl, q));
-            }
+            // while global slices are still to come they keep their SMs
+            for (size_t k = 0; k < n_sliceable; k++)
+                QCS_TRY(local_slice(k, j, L, j + 1 < (1 << sb) ? reg->sm_count - g_sms : 0));
         }
-        const sweep_target tl = {reg->amp, reg->n_local, L};
-        for (size_t k = n_sliceable; k < local_plans.size(); k++) {
-            sweep_plan q = local_plans[k];
-            q.d.hadamard_only = hadamard_only ? 1 : 0;
-            if (hadamard_only) q.d.wcol_total = 0;
-            QCS_TRY(launch_plan(reg, tl, q));
-        }
+        for (size_t k = n_sliceable; k < local_plans.size(); k++) QCS_TRY(local_full(k, L));
         return QCS_NO_ERROR;
     }
     if (inverse) {
