@@ -270,7 +270,8 @@ extern "C" void qcs_register_destroy(qcs_register *reg)
     if (!reg) return;
     cudaSetDevice(reg->device);
     if (reg->stream) cudaStreamSynchronize(reg->stream);
-    if (reg->peer && reg->dist) qcs_dist_barrier(reg);   // no rank unmaps while a peer may still touch its shard
+    // no collective here: a peer that still touches this shard does so through its own mapping of
+    // the allocation, which stays alive until that peer releases its imported handle
     if (reg->dist) qcs_dist_destroy(reg);
     for (auto &s : reg->pending) { cudaEventDestroy(s.begin); cudaEventDestroy(s.end); }
     for (auto &s : reg->free_slots) { cudaEventDestroy(s.begin); cudaEventDestroy(s.end); }

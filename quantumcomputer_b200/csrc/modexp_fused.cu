@@ -144,10 +144,16 @@ int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, 
 {
     const unsigned first = reg->n - n_gates;                  // qc_shor.c:720,728
     const unsigned M = (unsigned) reg->M_size;
-    // Hadamards: local qubits by Walsh-Hadamard sweeps, global ones by exchange
+    // Hadamards: local qubits by Walsh-Hadamard sweeps; global ones inside the sweep over the
+    // stitched array when the register has peer memory, else by exchange
     const unsigned h_hi = reg->n < reg->n_local ? reg->n : reg->n_local;
-    if (first < h_hi) QCS_TRY(qcs_fused_hadamards(reg, first, h_hi));
-    if (reg->world > 1) {
+    const bool sharded_sweeps = reg->world > 1 && reg->peer && reg->n_local >= 15 && first + 12 <= reg->n_local;
+    if (sharded_sweeps) {
+        QCS_TRY(qcs_fused_sweeps_sharded(reg, first, reg->n, true, true));
+    } else if (first < h_hi) {
+        QCS_TRY(qcs_fused_hadamards(reg, first, h_hi));
+    }
+    if (reg->world > 1 && !sharded_sweeps) {
         if (first <= reg->n_local && reg->n_local >= 2u * (unsigned) reg->p_global)
             QCS_TRY(qcs_dist_top_stages(reg, 0, true, true));       // H on every global qubit at once
         else
