@@ -379,6 +379,7 @@ static int hadamard_any(qcs_register *reg, unsigned q)
 {
     if (q >= reg->n) return QCS_BAD_ARGUMENTS;
     if (q < reg->n_local) return qcs_k_hadamard_local(reg, q);
+    if (reg->peer) return qcs_k_hadamard_peer(reg, q);
     return qcs_dist_hadamard_global(reg, q);
 }
 

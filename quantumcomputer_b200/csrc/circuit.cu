@@ -58,7 +58,9 @@ k_diag_multi(double2 *__restrict__ amp, uint64_t n_pairs, const diag_gate *__res
 }
 
 struct pass {
-    int type;                   // 0: tile sweep, 1: single local Hadamard kernel, 2: global Hadamard(s)
+    int type;                   // 0: tile sweep, 1: single local Hadamard kernel, 2: global Hadamard(s),
+                                // 3: run of H qubits reaching the global ones, as sharded sweeps on peer memory
+    unsigned run_lo, run_hi;    // type 3
     int group;
     uint64_t hmask;             // qubits this pass applies H to
     sweep_plan plan;            // type 0
@@ -172,7 +174,26 @@ static int schedule_stream(const qcs_register *reg, const std::vector<qcs_pendin
     // ---- 2. passes
     const uint64_t local_mask = reg->n_local >= 64 ? ~0ull : ((1ull << reg->n_local) - 1ull);
     for (size_t gi = 0; gi < groups.size(); gi++) {
-        const uint64_t hl = groups[gi].hset & local_mask, hg = groups[gi].hset & ~local_mask;
+        uint64_t hl = groups[gi].hset & local_mask, hg = groups[gi].hset & ~local_mask;
+        if (hg && reg->peer && reg->n_local >= 15) {
+            // peer memory: the run of H qubits that ends at the top global qubit in the set goes
+            // through the sharded sweeps (global sweep on the stitched array + local sweeps)
+            unsigned hi = reg->n;
+            while (hi > 0 && !((groups[gi].hset >> (hi - 1)) & 1ull)) hi--;
+            unsigned lo = hi;
+            while (lo > 0 && ((groups[gi].hset >> (lo - 1)) & 1ull)) lo--;
+            if (lo + 12 <= reg->n_local) {
+                pass ps;
+                ps.type = 3;
+                ps.group = (int) gi;
+                ps.run_lo = lo;
+                ps.run_hi = hi;
+                ps.hmask = ((hi >= 64 ? ~0ull : ((1ull << hi) - 1ull))) & ~((1ull << lo) - 1ull);
+                passes.push_back(ps);
+                hl &= ~ps.hmask;
+                hg &= ~ps.hmask;
+            }
+        }
         if (hg) {
             // sharded register, Hadamards on global qubits: all p of them at once through the
             // qubit-swap pipeline when that is the whole global set, else pairwise exchanges
@@ -282,11 +303,14 @@ int qcs_fuse_flush(qcs_register *reg)
             QCS_TRY(qcs_launch_sweep_plan(reg, ps.plan));
         } else if (ps.type == 1) {
             QCS_TRY(qcs_k_hadamard_local(reg, ps.q));
+        } else if (ps.type == 3) {
+            QCS_TRY(qcs_fused_sweeps_sharded(reg, ps.run_lo, ps.run_hi, true, true));
         } else if (ps.top_stages) {
             QCS_TRY(qcs_dist_top_stages(reg, 0, true, true));
         } else {
             for (unsigned q = reg->n_local; q < reg->n; q++)
-                if ((ps.hmask >> q) & 1ull) QCS_TRY(qcs_dist_hadamard_global(reg, q));
+                if ((ps.hmask >> q) & 1ull)
+                    QCS_TRY(reg->peer ? qcs_k_hadamard_peer(reg, q) : qcs_dist_hadamard_global(reg, q));
         }
         QCS_TRY(launch_diag_list(reg, queue, ps.after, d_scratch, stage));
     }

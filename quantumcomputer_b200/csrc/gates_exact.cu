@@ -88,7 +88,7 @@ k_scale(double2 *__restrict__ amp, uint64_t n_amps, double s)
 // ---------------------------------------------------------------------------
 template <int U>
 __global__ void __launch_bounds__(kThreads)
-k_hadamard_exact(double2 *__restrict__ amp, uint64_t n_pairs, unsigned q)
+k_hadamard_exact(double2 *__restrict__ amp, uint64_t first_pair, uint64_t n_pairs, unsigned q)
 {
     const double h = 0.70710678118654752440;   // M_SQRT1_2
     const uint64_t bit = 1ull << q;
@@ -98,7 +98,7 @@ k_hadamard_exact(double2 *__restrict__ amp, uint64_t n_pairs, unsigned q)
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const uint64_t p = first + (uint64_t) u * kThreads;
-        i0[u] = qcs_insert_zero_bit(p, q);
+        i0[u] = qcs_insert_zero_bit(first_pair + p, q);
         if (p < n_pairs) {
             a0[u] = amp[i0[u]];
             a1[u] = amp[i0[u] | bit];
@@ -298,8 +298,24 @@ int qcs_k_hadamard_local(qcs_register *reg, unsigned q)
     constexpr int U = 4;
     const uint64_t n_pairs = reg->N_local >> 1;
     qcs_launch_begin(reg, QCS_K_HADAMARD, 32.0 * (double) reg->N_local);
-    k_hadamard_exact<U><<<grid_for(n_pairs, kThreads * U), kThreads, 0, reg->stream>>>(reg->amp, n_pairs, q);
+    k_hadamard_exact<U><<<grid_for(n_pairs, kThreads * U), kThreads, 0, reg->stream>>>(reg->amp, 0, n_pairs, q);
     return qcs_launch_end(reg, QCS_K_HADAMARD, "k_hadamard_exact");
+}
+
+// Hadamard on a global qubit of a register with peer memory: the same kernel (the same
+// reference-order arithmetic) on the stitched array, this rank taking its share of the pairs of
+// the whole register; half of each pair it touches lives on the partner rank (NVLink).
+int qcs_k_hadamard_peer(qcs_register *reg, unsigned q)
+{
+    constexpr int U = 4;
+    if (!reg->peer || q < reg->n_local || q >= reg->n) return QCS_BAD_ARGUMENTS;
+    const uint64_t share = (reg->N >> 1) / (uint64_t) reg->world;
+    QCS_TRY(qcs_dist_stream_barrier(reg));
+    qcs_launch_begin(reg, QCS_K_HADAMARD, 32.0 * (double) reg->N_local);
+    k_hadamard_exact<U><<<grid_for(share, kThreads * U), kThreads, 0, reg->stream>>>(
+        reg->amp_all, (uint64_t) reg->rank * share, share, q);
+    QCS_TRY(qcs_launch_end(reg, QCS_K_HADAMARD, "k_hadamard_exact"));
+    return qcs_dist_stream_barrier(reg);
 }
 
 int qcs_k_phase_masked(qcs_register *reg, int nbits, unsigned b0, unsigned b1, double c, double s)

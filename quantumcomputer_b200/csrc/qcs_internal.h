@@ -120,6 +120,7 @@ int qcs_k_collapse(qcs_register *reg, uint64_t local_index, bool owner);
 int qcs_k_fill_synthetic(qcs_register *reg, uint64_t seed);
 int qcs_k_scale(qcs_register *reg, double s);
 int qcs_k_hadamard_local(qcs_register *reg, unsigned q);
+int qcs_k_hadamard_peer(qcs_register *reg, unsigned q);     // global qubit, register with peer memory
 // multiply by (c + i s) every local amplitude whose bits in `mask_bits` are all 1
 int qcs_k_phase_masked(qcs_register *reg, int nbits, unsigned b0, unsigned b1, double c, double s);
 int qcs_k_amodc(qcs_register *reg, unsigned C, unsigned A, int ctrl_local /* -1: always on */,

@@ -109,6 +109,16 @@ def main():
         got = gather_state(sh, rank, world)
         check(f"n={n} M={M} arbitrary gates", got, single.get_state() if rank == 0 else None)
 
+        # deferred gate stream across the global qubits: layered circuit + a few stray gates
+        from quantumcomputer_b200.workloads import apply_gates, layered_circuit
+        stream = layered_circuit(n, 2) + [("h", n - 1), ("cp", n - 1, 0, 0.4), ("h", n - 1), ("h", 2)]
+        def fused_stream(r):
+            with r.fused():
+                apply_gates(r, stream)
+        both(fused_stream)
+        got = gather_state(sh, rank, world)
+        check(f"n={n} M={M} fused gate stream", got, single.get_state() if rank == 0 else None)
+
         # sampling without collapse
         rs = [0.0, 0.2, 0.5, 0.93, 1.0]
         a = sh.sample_states(rs)
