@@ -486,8 +486,7 @@ static int qft_any(qcs_register *reg, unsigned lo, unsigned hi, bool inverse)
     // sharded register, transform reaches the global qubits.  With peer memory the sweeps whose
     // tile holds global qubits run on the stitched array (qft_fused.cu); without it their stages
     // run as exchange + sweep + exchange (dist.cu), the local ones as ordinary sweeps
-    if (reg->peer && hi == reg->n && reg->n_local >= 15 && lo + 12 <= reg->n_local)
-        return qcs_fused_sweeps_sharded(reg, lo, hi, inverse, false);
+    if (qcs_sharded_sweeps_supported(reg, lo, hi)) return qcs_fused_sweeps_sharded(reg, lo, hi, inverse, false);
     const unsigned q = reg->n_local - (unsigned) reg->p_global;
     if (hi != reg->n || lo > q || reg->n_local < 2u * (unsigned) reg->p_global)
         return qft_gate_by_gate(reg, lo, hi, inverse);       // odd shapes: pairwise exchanges, gate by gate

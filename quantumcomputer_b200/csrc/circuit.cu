@@ -175,14 +175,14 @@ static int schedule_stream(const qcs_register *reg, const std::vector<qcs_pendin
     const uint64_t local_mask = reg->n_local >= 64 ? ~0ull : ((1ull << reg->n_local) - 1ull);
     for (size_t gi = 0; gi < groups.size(); gi++) {
         uint64_t hl = groups[gi].hset & local_mask, hg = groups[gi].hset & ~local_mask;
-        if (hg && reg->peer && reg->n_local >= 15) {
+        if (hg && reg->peer) {
             // peer memory: the run of H qubits that ends at the top global qubit in the set goes
             // through the sharded sweeps (global sweep on the stitched array + local sweeps)
             unsigned hi = reg->n;
             while (hi > 0 && !((groups[gi].hset >> (hi - 1)) & 1ull)) hi--;
             unsigned lo = hi;
             while (lo > 0 && ((groups[gi].hset >> (lo - 1)) & 1ull)) lo--;
-            if (lo + 12 <= reg->n_local) {
+            if (qcs_sharded_sweeps_supported(reg, lo, hi)) {
                 pass ps;
                 ps.type = 3;
                 ps.group = (int) gi;

@@ -147,7 +147,7 @@ int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, 
     // Hadamards: local qubits by Walsh-Hadamard sweeps; global ones inside the sweep over the
     // stitched array when the register has peer memory, else by exchange
     const unsigned h_hi = reg->n < reg->n_local ? reg->n : reg->n_local;
-    const bool sharded_sweeps = reg->world > 1 && reg->peer && reg->n_local >= 15 && first + 12 <= reg->n_local;
+    const bool sharded_sweeps = reg->world > 1 && qcs_sharded_sweeps_supported(reg, first, reg->n);
     if (sharded_sweeps) {
         QCS_TRY(qcs_fused_sweeps_sharded(reg, first, reg->n, true, true));
     } else if (first < h_hi) {

@@ -138,6 +138,7 @@ int qcs_fused_qft(qcs_register *reg, unsigned lo, unsigned hi, bool inverse);
 // the same on a sharded register with peer memory: qubits up to n, sweeps whose tile holds
 // global qubits run on the stitched array, every rank taking its share of the tiles
 int qcs_fused_sweeps_sharded(qcs_register *reg, unsigned lo, unsigned hi, bool inverse, bool hadamard_only);
+bool qcs_sharded_sweeps_supported(const qcs_register *reg, unsigned lo, unsigned hi);
 int qcs_fused_hadamards(qcs_register *reg, unsigned lo, unsigned hi);
 int qcs_fused_top_sweep(qcs_register *reg, double2 *buf, unsigned c, unsigned p, unsigned lo,
                         unsigned long long y_const, bool inverse, bool hadamard_only, cudaStream_t stream);

@@ -229,11 +229,25 @@ int qcs_fused_qft(qcs_register *reg, unsigned lo, unsigned hi, bool inverse)
 //     separates it from the work around it;
 //   * the remaining stages are ordinary sweeps on the rank's own shard: no communication.
 // NVLink traffic: each rank reads and writes (world-1)/world of a shard, once.
+// can qcs_fused_sweeps_sharded run the transform on [lo, hi)?  (callers fall back to the
+// exchange schedules of dist.cu otherwise)
+bool qcs_sharded_sweeps_supported(const qcs_register *reg, unsigned lo, unsigned hi)
+{
+    if (!reg->peer || !reg->amp_all || lo >= hi || hi > reg->n || hi <= reg->n_local) return false;
+    const int T = default_tile_bits(reg);
+    if ((int) reg->n_local < T + 3 || (int) lo + T > (int) reg->n_local) return false;
+    int a_glob = reg->opt_global_run_bits;
+    if (a_glob > T - reg->p_global) a_glob = T - reg->p_global;
+    if (a_glob < 1) return false;
+    int split = (int) hi - (T - a_glob);
+    if (split < (int) lo) split = (int) lo;
+    return split <= (int) reg->n_local;
+}
+
 int qcs_fused_sweeps_sharded(qcs_register *reg, unsigned lo, unsigned hi, bool inverse, bool hadamard_only)
 {
-    if (!reg->peer || !reg->amp_all || lo >= hi || hi > reg->n) return QCS_BAD_ARGUMENTS;
+    if (!qcs_sharded_sweeps_supported(reg, lo, hi)) return QCS_BAD_ARGUMENTS;
     const int T = default_tile_bits(reg);
-    if ((int) reg->n_local < T + 3 || hi <= reg->n_local) return QCS_BAD_ARGUMENTS;
     // The sweep over the global qubits is bound by NVLink, not by HBM: it keeps long contiguous
     // runs (2^a amplitudes per TMA row) and takes along only as many local stage bits as fit.
     int a_glob = reg->opt_global_run_bits;
