@@ -622,6 +622,9 @@ extern "C" int qcs_sample_states(qcs_register *reg, unsigned long long n_shots, 
 {
     QCS_ENTER(reg);
     if (n_shots && (!r || !state_nums)) return QCS_BAD_ARGUMENTS;
+    bool handled = false;
+    QCS_TRY(qcs_k_sample_many(reg, n_shots, r, state_nums, &handled));
+    if (handled) return QCS_NO_ERROR;
     for (unsigned long long k = 0; k < n_shots; k++) {
         uint64_t idx = 0;
         QCS_TRY(locate_state(reg, r[k], &idx));

@@ -341,10 +341,15 @@ __device__ __forceinline__ bool apply_map(double &s, pair64 f, int e)
     return true;
 }
 
+// RECORD = false: stop at the first index whose running sum reaches r (measure_state).
+// RECORD = true : never stop; write the exact running sum at the start of every super-chunk and,
+//                 last, after the final element (bnd[0 .. n_super]) -- the variate-independent part
+//                 of the scan, computed once for any number of samples (qcs_sample_states).
+template <bool RECORD>
 __global__ void __launch_bounds__(1024)
 k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks, double cum_in, double r,
              const int *__restrict__ code, const int *__restrict__ super_code, const pair64 *__restrict__ maps,
-             const pair64 *__restrict__ super_maps, walk_result *__restrict__ out)
+             const pair64 *__restrict__ super_maps, walk_result *__restrict__ out, double *__restrict__ bnd)
 {
     __shared__ double p[kChunk];
     __shared__ int s_code[kWalkBlock];
@@ -373,6 +378,7 @@ k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
                 uint64_t sc = sc_next;
                 for (; sc < sb_end; sc++) {
                     const int cd = s_code[sc - sc_next];
+                    if (RECORD) bnd[sc] = s;
                     if (cd == kCodeZero) continue;
                     if (cd == kCodeSeq) { req = (long long) sc; break; }
                     if (!apply_map(s, s_map[sc - sc_next], cd - 2000)) { s_bad = 1; break; }
@@ -417,7 +423,7 @@ k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
                     const uint64_t len = limit - base < (uint64_t) kChunk ? limit - base : (uint64_t) kChunk;
                     for (uint64_t j = 0; j < len; j++) {
                         s = __dadd_rn(s, p[j]);                 // qc_shor.c:286
-                        if (s >= r) { hit = base + j; s_found = 1; break; }   // qc_shor.c:289
+                        if (!RECORD && s >= r) { hit = base + j; s_found = 1; break; }   // qc_shor.c:289
                     }
                 }
                 __syncthreads();
@@ -428,6 +434,7 @@ k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (RECORD) bnd[n_super] = s;
         out->cum = s;
         out->index = hit;
         out->found = s_found;
@@ -473,13 +480,13 @@ static int measure_scan_sequential(qcs_register *reg, double cum_in, double r, u
     return QCS_NO_ERROR;
 }
 
-int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limit,
-                       int *found, uint64_t *index, double *cum_out)
+// chunk / super-chunk summaries of amp[first .. first + limit) for the variate r (pass a huge r
+// for variate-independent summaries), then the exact walk.  bnd != nullptr: record the running sum
+// at the super-chunk boundaries instead of searching for r.
+static int parallel_scan(qcs_register *reg, uint64_t first, double cum_in, double r, uint64_t limit,
+                         int *found, uint64_t *index, double *cum_out, double *d_bnd, int *bad)
 {
-    // small registers: the plain sequential scan is already fast
-    if (limit < (1ull << 17) || reg->opt_measure_sequential)
-        return measure_scan_sequential(reg, cum_in, r, limit, found, index, cum_out);
-
+    const double2 *amp = reg->amp + first;
     const uint64_t n_chunks = (limit + kChunk - 1) >> kChunkBits;
     const uint64_t n_super = (n_chunks + kSuper - 1) >> kSuperBits;
     if (!reg->d_meas) {
@@ -506,13 +513,13 @@ int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limi
     if (grid > cap) grid = cap;
 
     qcs_launch_begin(reg, QCS_K_REDUCE, 16.0 * (double) limit);
-    k_chunk_sums<<<(unsigned) grid, 256, 0, reg->stream>>>(reg->amp, limit, n_chunks, csum);
+    k_chunk_sums<<<(unsigned) grid, 256, 0, reg->stream>>>(amp, limit, n_chunks, csum);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_chunk_sums"));
     qcs_launch_begin(reg, QCS_K_REDUCE, 12.0 * (double) n_chunks);
     k_classify<<<1, 1024, 0, reg->stream>>>(csum, n_chunks, cum_in, r, delta, code, super_code);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_classify"));
     qcs_launch_begin(reg, QCS_K_REDUCE, 16.0 * (double) limit * (r < 1.0 ? (r > 0.0 ? r : 0.0) : 1.0));
-    k_chunk_maps<<<(unsigned) grid, 128, 0, reg->stream>>>(reg->amp, limit, n_chunks, code, maps);
+    k_chunk_maps<<<(unsigned) grid, 128, 0, reg->stream>>>(amp, limit, n_chunks, code, maps);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_chunk_maps"));
     qcs_launch_begin(reg, QCS_K_REDUCE, 20.0 * (double) n_chunks);
     k_super_maps<<<(unsigned) ((n_super + 255) / 256), 256, 0, reg->stream>>>(n_chunks, n_super, code, super_code,
@@ -520,18 +527,82 @@ int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limi
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_super_maps"));
     walk_result *d_res = (walk_result *) reg->d_small;
     qcs_launch_begin(reg, QCS_K_REDUCE, 20.0 * (double) n_super);
-    k_exact_walk<<<1, 1024, 0, reg->stream>>>(reg->amp, limit, n_chunks, cum_in, r, code, super_code, maps,
-                                              super_maps, d_res);
+    if (d_bnd)
+        k_exact_walk<true><<<1, 1024, 0, reg->stream>>>(amp, limit, n_chunks, cum_in, r, code, super_code, maps,
+                                                        super_maps, d_res, d_bnd);
+    else
+        k_exact_walk<false><<<1, 1024, 0, reg->stream>>>(amp, limit, n_chunks, cum_in, r, code, super_code, maps,
+                                                         super_maps, d_res, nullptr);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_exact_walk"));
     QCS_CUDA(cudaMemcpyAsync(reg->h_small, d_res, sizeof(walk_result), cudaMemcpyDeviceToHost, reg->stream));
     QCS_CUDA(cudaStreamSynchronize(reg->stream));
     const walk_result *h = (const walk_result *) reg->h_small;
-    if (h->bad) {
+    *bad = h->bad;
+    *found = h->found;
+    *index = first + h->index;
+    *cum_out = h->cum;
+    return QCS_NO_ERROR;
+}
+
+int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limit,
+                       int *found, uint64_t *index, double *cum_out)
+{
+    // small registers: the plain sequential scan is already fast
+    if (limit < (1ull << 17) || reg->opt_measure_sequential)
+        return measure_scan_sequential(reg, cum_in, r, limit, found, index, cum_out);
+    int bad = 0;
+    QCS_TRY(parallel_scan(reg, 0, cum_in, r, limit, found, index, cum_out, nullptr, &bad));
+    if (bad) {
         fprintf(stderr, "qcs: measure_state: binade invariant failed, falling back to the sequential GPU scan\n");
         return measure_scan_sequential(reg, cum_in, r, limit, found, index, cum_out);
     }
-    *found = h->found;
-    *index = h->index;
-    *cum_out = h->cum;
+    return QCS_NO_ERROR;
+}
+
+// Many variates against one state (qcs_sample_states, single-GPU registers): the exact sequential
+// running sum at every boundary of 2^20 amplitudes is computed ONCE (two passes over the state,
+// independent of the variates); a variate is then located by a binary search over the boundaries --
+// the running sums are monotone -- and one exact scan of the 2^20 amplitudes it falls into.
+// indices[k] is what measure_state would return for r[k] (qc_shor.c:283-292).
+int qcs_k_sample_many(qcs_register *reg, uint64_t n_shots, const double *r, unsigned long long *indices,
+                      bool *handled)
+{
+    *handled = false;
+    const uint64_t limit = reg->N_local - 1;            // qc_shor.c:283: index N-1 is the fall-through
+    if (reg->world != 1 || limit < (1ull << 21) || reg->opt_measure_sequential || n_shots < 3) return QCS_NO_ERROR;
+    const uint64_t n_chunks = (limit + kChunk - 1) >> kChunkBits;
+    const uint64_t n_super = (n_chunks + kSuper - 1) >> kSuperBits;
+    double *d_bnd = nullptr;
+    QCS_CUDA(cudaMalloc((void **) &d_bnd, (n_super + 1) * sizeof(double)));
+    int found = 0, bad = 0;
+    uint64_t index = 0;
+    double total = 0.0;
+    int rc = parallel_scan(reg, 0, 0.0, 1e300, limit, &found, &index, &total, d_bnd, &bad);
+    std::vector<double> bnd((size_t) n_super + 1);
+    if (rc == QCS_NO_ERROR && !bad) {
+        if (cudaMemcpyAsync(bnd.data(), d_bnd, bnd.size() * sizeof(double), cudaMemcpyDeviceToHost, reg->stream) != cudaSuccess ||
+            cudaStreamSynchronize(reg->stream) != cudaSuccess)
+            rc = QCS_UNKNOWN_ERROR;
+    }
+    cudaFree(d_bnd);
+    if (rc != QCS_NO_ERROR) return rc;
+    if (bad) return QCS_NO_ERROR;                       // caller takes the one-scan-per-variate path
+    const uint64_t super_len = (uint64_t) kSuper << kChunkBits;
+    for (uint64_t k = 0; k < n_shots; k++) {
+        // first super-chunk whose closing running sum reaches r[k]
+        uint64_t lo = 0, hi = n_super;                  // answer in [lo, hi]; hi = n_super: none
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) / 2;
+            if (bnd[(size_t) mid + 1] >= r[k]) hi = mid; else lo = mid + 1;
+        }
+        if (lo == n_super) { indices[k] = reg->N - 1; continue; }
+        const uint64_t first = lo * super_len;
+        const uint64_t len = limit - first < super_len ? limit - first : super_len;
+        double cum = 0.0;
+        QCS_TRY(parallel_scan(reg, first, bnd[(size_t) lo], r[k], len, &found, &index, &cum, nullptr, &bad));
+        if (bad || !found) return QCS_NO_ERROR;         // never observed: redo everything the slow way
+        indices[k] = index;
+    }
+    *handled = true;
     return QCS_NO_ERROR;
 }

@@ -133,6 +133,9 @@ int qcs_k_norm2_local(qcs_register *reg, double *out_host);
 int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limit,
                        int *found, uint64_t *index, double *cum_out);
 
+// many variates against one state; *handled = false: not applicable, use one scan per variate
+int qcs_k_sample_many(qcs_register *reg, uint64_t n_shots, const double *r, unsigned long long *indices, bool *handled);
+
 // ---- fused sweeps: qft_fused.cu / modexp_fused.cu ---------------------------
 int qcs_fused_qft(qcs_register *reg, unsigned lo, unsigned hi, bool inverse);
 // the same on a sharded register with peer memory: qubits up to n, sweeps whose tile holds

@@ -88,7 +88,7 @@ def test_gate_special_cases_agree_with_reference_gates(qcs, oracle_built):
         assert abs(reg.norm2() - 4.0 * np.sum(np.abs(base.reshape(-1, 2, 16)[:, 0, :]) ** 2)) < 1e-12
 
 
-@pytest.mark.parametrize("L,M", [(3, 4), (10, 0), (18, 0), (20, 1)])
+@pytest.mark.parametrize("L,M", [(3, 4), (10, 0), (18, 0), (20, 1), (23, 0), (22, 3)])
 def test_sampling_without_collapse_matches_measure_state(qcs, oracle_built, L, M):
     """Every sampled index equals what measure_state returns for the same r (oracle for small
     registers, the engine's own measure_state -- pinned to the oracle elsewhere -- for all)."""
@@ -98,6 +98,15 @@ def test_sampling_without_collapse_matches_measure_state(qcs, oracle_built, L, M
         reg.fill_synthetic(40 + n)
         reg.scale(1.0 / math.sqrt(reg.norm2()))
         state = reg.get_state().copy()
+        if n >= 22:
+            # registers of >= 2^21 amplitudes take the single-pass path (boundary sums once, then one
+            # 2^20-amplitude scan per variate): probe variates at, just below and just above exact
+            # sequential prefix sums, including the ones at the 2^20 boundaries
+            p = state.real * state.real + state.imag * state.imag
+            cum = np.cumsum(p)                     # close to (not identical with) the sequential sums
+            for i in ((1 << 20) - 1, 1 << 20, (1 << 21) + 5, (1 << n) - 3):
+                rs += [float(cum[i]), float(np.nextafter(cum[i], 0.0)), float(np.nextafter(cum[i], 2.0))]
+            rs += [float(x) for x in np.random.default_rng(n).random(20)]
         got = reg.sample_states(rs)
         assert np.array_equal(reg.get_state().view(np.float64), state.view(np.float64)), "sampling must not collapse"
         want = []
