@@ -261,6 +261,13 @@ int qcs_schedule_describe(unsigned n_qubits, int world_size, int rank, unsigned 
                           const int *kinds, const unsigned *q0, const unsigned *q1, char *out,
                           unsigned long long out_cap);
 
+/* Host-only view of the sweep planner (no device work): the fused sweeps an inverse transform on
+ * qubits [lo, hi) of an n_qubits register is run as (tile_bits / min_run_bits = 0: library
+ * defaults), one text line per sweep:
+ *   "sweep a=<run bits> g=[<g_lo>,<g_hi>) tiles=<count> steps=<lowest bit>+<radix bits>,... scale=<factor>" */
+int qcs_plan_describe(unsigned n_qubits, unsigned lo, unsigned hi, int tile_bits, int min_run_bits,
+                      char *out, unsigned long long out_cap);
+
 /* Fused dense block: an arbitrary 2^k x 2^k complex matrix U (row-major,
  * interleaved re/im, k = 3 or 4) applied to qubits 0..k-1 of every basis state,
  * i.e. what a run of gates on those qubits multiplies out to (generalises

@@ -88,6 +88,22 @@ def schedule_describe(n_qubits, gates, world_size=1, rank=0):
     return passes
 
 
+def plan_describe(n_qubits, lo=0, hi=None, tile_bits=0, min_run_bits=0):
+    """Sweeps of the fused inverse transform on qubits [lo, hi); host only, no GPU needed.
+    Returns a list of dicts {"a", "g_lo", "g_hi", "tiles", "steps": [(lowest bit, radix bits)], "scale"}."""
+    hi = n_qubits if hi is None else hi
+    buf = C.create_string_buffer(1 << 14)
+    _check(lib().qcs_plan_describe(n_qubits, lo, hi, tile_bits, min_run_bits, buf, len(buf)), "qcs_plan_describe")
+    sweeps = []
+    for line in buf.value.decode().splitlines():
+        f = dict(kv.split("=", 1) for kv in line.split()[1:])
+        g_lo, g_hi = f["g"].strip("[)").split(",")
+        sweeps.append({"a": int(f["a"]), "g_lo": int(g_lo), "g_hi": int(g_hi), "tiles": int(f["tiles"]),
+                       "steps": [tuple(int(v) for v in st.split("+")) for st in f["steps"].split(",")],
+                       "scale": float(f["scale"])})
+    return sweeps
+
+
 def comm_unique_id():
     buf = C.create_string_buffer(128)
     _check(lib().qcs_comm_unique_id(buf), "qcs_comm_unique_id")

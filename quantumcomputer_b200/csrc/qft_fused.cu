@@ -34,6 +34,9 @@
 // QCS_OPT_FUSION = 0 keeps the gate-by-gate kernels available.
 #include "qft_common.cuh"
 
+#include <string.h>
+#include <string>
+
 
 namespace {
 
@@ -415,3 +418,33 @@ int qcs_fused_hadamards(qcs_register *reg, unsigned lo, unsigned hi)
     return run_sweeps(reg, lo, hi, true, true);
 }
 
+
+// Host-only view of the sweep planner for tests and tooling (no device work): the sweeps an
+// inverse transform on qubits [lo, hi) of a 2^n_qubits-amplitude array is run as, one line each:
+//   "sweep a=<run bits> g=[<g_lo>,<g_hi>) tiles=<count> steps=<low_phys>+<r>,... scale=<factor>"
+extern "C" int qcs_plan_describe(unsigned n_qubits, unsigned lo, unsigned hi, int tile_bits, int min_run_bits,
+                                 char *out, unsigned long long out_cap)
+{
+    if (!out || out_cap == 0 || n_qubits < 1 || n_qubits > 62 || lo >= hi || hi > n_qubits) return QCS_BAD_ARGUMENTS;
+    if (tile_bits == 0) tile_bits = 12;
+    if (min_run_bits == 0) min_run_bits = 3;
+    if (tile_bits < 4 || tile_bits > 13 || min_run_bits < 1 || min_run_bits > 7) return QCS_BAD_ARGUMENTS;
+    std::vector<sweep_plan> plans;
+    plan_inverse(n_qubits, lo, hi, tile_bits, min_run_bits, plans);
+    std::string text;
+    for (const sweep_plan &p : plans) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "sweep a=%d g=[%d,%d) tiles=%llu steps=", p.d.a, p.d.g_lo, p.d.g_hi,
+                 (unsigned long long) p.n_tiles);
+        text += buf;
+        for (int k = 0; k < p.d.n_steps; k++) {
+            snprintf(buf, sizeof buf, "%s%d+%d", k ? "," : "", p.d.step[k].low_phys, p.d.step[k].r);
+            text += buf;
+        }
+        snprintf(buf, sizeof buf, " scale=%.17g\n", p.d.scale);
+        text += buf;
+    }
+    if (text.size() + 1 > out_cap) return QCS_INSUFFICIENT_MEMORY;
+    memcpy(out, text.c_str(), text.size() + 1);
+    return QCS_NO_ERROR;
+}

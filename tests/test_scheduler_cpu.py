@@ -122,3 +122,44 @@ def test_bad_arguments(qcs):
         qcs.schedule_describe(4, [("h", 4)])
     with pytest.raises(qcs.QcsError):
         qcs.schedule_describe(4, [("h", 1)], world_size=3)
+
+
+# ---------------------------------------------------------------------------
+# the sweep planner (csrc/qft_common.cuh plan_inverse) through qcs_plan_describe
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n,lo,tile_bits,run_bits", [(7, 4, 0, 0), (10, 5, 0, 0), (14, 0, 0, 0), (20, 3, 11, 4),
+                                                     (30, 0, 0, 0), (30, 0, 11, 0), (31, 0, 0, 0), (33, 0, 0, 0),
+                                                     (33, 0, 11, 4), (35, 5, 0, 0), (26, 0, 9, 3), (18, 2, 13, 3)])
+def test_sweep_plan_covers_every_stage_once_in_order(qcs, n, lo, tile_bits, run_bits):
+    """The stages l = n-1 .. lo of inverse_QFT (qc_shor.c:682-689) appear exactly once, top first;
+    every tile is a contiguous run [0, a) plus the run [g_lo, g_hi) that holds its stage bits; the
+    tiles of a sweep partition the register; the scalings multiply to 2^(-stages/2)."""
+    sweeps = qcs.plan_describe(n, lo, n, tile_bits, run_bits)
+    t = min(tile_bits or 12, n)
+    expect = n - 1
+    scale = 1.0
+    for sw in sweeps:
+        tile = sw["a"] + (sw["g_hi"] - sw["g_lo"])
+        assert tile == t and sw["tiles"] == 1 << (n - t)
+        assert sw["a"] <= sw["g_lo"] <= sw["g_hi"] <= n
+        for low, r in sw["steps"]:
+            assert 1 <= r <= 4
+            assert low + r - 1 == expect, "stages must come top first without gaps"
+            in_run = low >= sw["g_lo"] and low + r <= sw["g_hi"]
+            in_low = low + r <= sw["a"]
+            assert in_run or in_low, "a step's bits lie inside the tile"
+            expect = low - 1
+        scale *= sw["scale"]
+    assert expect == lo - 1
+    assert abs(scale - 2.0 ** (-(n - lo) / 2.0)) <= 1e-15 * scale
+
+
+def test_sweep_counts_of_the_benchmark_sizes(qcs):
+    """n = 30 is three sweeps with 2^12 tiles (128 B runs), four with 2^11; n = 33 four / five."""
+    assert len(qcs.plan_describe(30)) == 3
+    assert [s["a"] for s in qcs.plan_describe(30)] == [3, 3, 12]
+    assert len(qcs.plan_describe(30, tile_bits=11)) == 4
+    assert len(qcs.plan_describe(33)) == 4 and qcs.plan_describe(33)[0]["a"] == 5
+    assert len(qcs.plan_describe(33, tile_bits=11, min_run_bits=4)) == 5
+    with pytest.raises(qcs.QcsError):
+        qcs.plan_describe(10, 5, 5)
