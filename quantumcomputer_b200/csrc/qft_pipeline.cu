@@ -407,9 +407,12 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
     P.box_bytes = (uint32_t) (((size_t) 16 << sh.tb) / (size_t) P.n_boxes);
     box[1] = (cuuint32_t) P.box_rows;
     box[2] = 1;
+    // 128 B rows: promoting the requests to 256 B would fetch a neighbour's half-line with every row
+    // (measured at n = 30: 21.2-21.4 ms for every promotion setting -- not a lever)
+    const CUtensorMapL2promotion promo = (strided && plan.d.a <= 3) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                                    : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, tg.amp, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
         fprintf(stderr, "qcs: cuTensorMapEncodeTiled failed (%d)\n", (int) cr);
         return QCS_UNKNOWN_ERROR;
