@@ -157,7 +157,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     total = args.steps + args.warmup
-    n = pick_reference_n(150.0 / max(total, 1))
+    n = args.qubits if args.qubits else pick_reference_n(150.0 / max(total, 1))
     kind = None
     for _ in range(args.warmup):
         kind, _dt = reference_iqft_seconds(n)

@@ -1,0 +1,37 @@
+"""CPU tests of bench.py: the reference arm's JSON line carries the contract's keys, and the
+GPU arm fails loudly (no CPU fallback) when no CUDA device is present."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+
+def run_bench(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                          timeout=300, cwd=ROOT)
+
+
+def test_reference_arm_line(oracle_built):
+    out = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--qubits", "8")
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "qft_gates_per_sec" and line["unit"] == "gates/s"
+    assert line["higher_is_better"] is True and line["steps"] == 2 and line["warmup"] == 1
+    assert line["value"] > 0 and line["config"]["qubits"] == 8 and line["config"]["gates_per_step"] == 36
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0
+
+
+def test_gpu_arm_fails_loudly_without_a_gpu(qcs):
+    if qcs.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    out = run_bench("--steps", "1", "--warmup", "3", "--no-e2e", "--no-cpu-baseline")
+    assert out.returncode != 0
+    assert "no usable CUDA device" in out.stderr and "no CPU path" in out.stderr
+    assert not out.stdout.strip(), "no bench line may be printed without a GPU"
