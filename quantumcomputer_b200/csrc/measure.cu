@@ -568,40 +568,74 @@ int qcs_k_sample_many(qcs_register *reg, uint64_t n_shots, const double *r, unsi
                       bool *handled)
 {
     *handled = false;
-    const uint64_t limit = reg->N_local - 1;            // qc_shor.c:283: index N-1 is the fall-through
-    if (reg->world != 1 || limit < (1ull << 21) || reg->opt_measure_sequential || n_shots < 3) return QCS_NO_ERROR;
+    // qc_shor.c:283: index N-1 is the fall-through, so the last shard stops one element early
+    const uint64_t limit = reg->rank == reg->world - 1 ? reg->N_local - 1 : reg->N_local;
+    if (reg->N_local < (1ull << 22) || reg->opt_measure_sequential || n_shots < 3) return QCS_NO_ERROR;
     const uint64_t n_chunks = (limit + kChunk - 1) >> kChunkBits;
     const uint64_t n_super = (n_chunks + kSuper - 1) >> kSuperBits;
     double *d_bnd = nullptr;
     QCS_CUDA(cudaMalloc((void **) &d_bnd, (n_super + 1) * sizeof(double)));
-    int found = 0, bad = 0;
-    uint64_t index = 0;
-    double total = 0.0;
-    int rc = parallel_scan(reg, 0, 0.0, 1e300, limit, &found, &index, &total, d_bnd, &bad);
     std::vector<double> bnd((size_t) n_super + 1);
-    if (rc == QCS_NO_ERROR && !bad) {
-        if (cudaMemcpyAsync(bnd.data(), d_bnd, bnd.size() * sizeof(double), cudaMemcpyDeviceToHost, reg->stream) != cudaSuccess ||
-            cudaStreamSynchronize(reg->stream) != cudaSuccess)
-            rc = QCS_UNKNOWN_ERROR;
+    std::vector<double> rank_end((size_t) reg->world, 0.0);   // exact running sum after each shard
+    int found = 0, bad = 0, rc = QCS_NO_ERROR;
+    uint64_t index = 0;
+    double total = 0.0, carry = 0.0;
+    // sharded: the running sum is handed from rank to rank in index order, once
+    for (int turn = 0; turn < reg->world && rc == QCS_NO_ERROR; turn++) {
+        double mine = 0.0;
+        if (turn == reg->rank) {
+            rc = parallel_scan(reg, 0, carry, 1e300, limit, &found, &index, &total, d_bnd, &bad);
+            if (rc == QCS_NO_ERROR && !bad &&
+                (cudaMemcpyAsync(bnd.data(), d_bnd, bnd.size() * sizeof(double), cudaMemcpyDeviceToHost, reg->stream) != cudaSuccess ||
+                 cudaStreamSynchronize(reg->stream) != cudaSuccess))
+                rc = QCS_UNKNOWN_ERROR;
+            mine = bad ? -1.0 : total;                   // a negative sum tells every rank to give up
+        }
+        if (reg->world > 1) {
+            std::vector<double> all((size_t) reg->world);
+            const int rc2 = qcs_dist_allgather_double(reg, rc == QCS_NO_ERROR ? mine : -1.0, all.data());
+            if (rc == QCS_NO_ERROR) rc = rc2;
+            mine = all[(size_t) turn];
+        }
+        rank_end[(size_t) turn] = mine;
+        carry = mine;
+        if (mine < 0.0) bad = 1;
+        if (bad) break;
     }
     cudaFree(d_bnd);
     if (rc != QCS_NO_ERROR) return rc;
     if (bad) return QCS_NO_ERROR;                       // caller takes the one-scan-per-variate path
     const uint64_t super_len = (uint64_t) kSuper << kChunkBits;
     for (uint64_t k = 0; k < n_shots; k++) {
-        // first super-chunk whose closing running sum reaches r[k]
-        uint64_t lo = 0, hi = n_super;                  // answer in [lo, hi]; hi = n_super: none
-        while (lo < hi) {
-            const uint64_t mid = (lo + hi) / 2;
-            if (bnd[(size_t) mid + 1] >= r[k]) hi = mid; else lo = mid + 1;
+        // the shard, then the super-chunk, whose closing running sum first reaches r[k]
+        int owner = 0;
+        while (owner < reg->world && !(rank_end[(size_t) owner] >= r[k])) owner++;
+        double answer = (double) (reg->N - 1);          // indices < 2^53 are exact in a double
+        int failed = 0;
+        if (owner == reg->rank) {
+            uint64_t lo = 0, hi = n_super;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) / 2;
+                if (bnd[(size_t) mid + 1] >= r[k]) hi = mid; else lo = mid + 1;
+            }
+            if (lo == n_super) failed = 1;               // cannot happen: rank_end == bnd[n_super]
+            else {
+                const uint64_t first = lo * super_len;
+                const uint64_t len = limit - first < super_len ? limit - first : super_len;
+                double cum = 0.0;
+                rc = parallel_scan(reg, first, bnd[(size_t) lo], r[k], len, &found, &index, &cum, nullptr, &bad);
+                if (rc != QCS_NO_ERROR || bad || !found) failed = 1;
+                else answer = (double) ((uint64_t) reg->rank * reg->N_local + index);
+            }
         }
-        if (lo == n_super) { indices[k] = reg->N - 1; continue; }
-        const uint64_t first = lo * super_len;
-        const uint64_t len = limit - first < super_len ? limit - first : super_len;
-        double cum = 0.0;
-        QCS_TRY(parallel_scan(reg, first, bnd[(size_t) lo], r[k], len, &found, &index, &cum, nullptr, &bad));
-        if (bad || !found) return QCS_NO_ERROR;         // never observed: redo everything the slow way
-        indices[k] = index;
+        if (reg->world > 1 && owner < reg->world) {
+            std::vector<double> all((size_t) reg->world);
+            QCS_TRY(qcs_dist_allgather_double(reg, failed ? -1.0 : answer, all.data()));
+            answer = all[(size_t) owner];
+            failed = answer < 0.0;
+        }
+        if (failed) return rc;                           // never observed: redo everything the slow way
+        indices[k] = (unsigned long long) answer;
     }
     *handled = true;
     return QCS_NO_ERROR;
