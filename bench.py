@@ -120,6 +120,9 @@ class ClockSampler:
 # --------------------------------------------------------------------------
 # CPU arms (the only places that execute oracle/)
 # --------------------------------------------------------------------------
+REF_N = 12          # the reference arm and cpu_baseline time the same n (4^n index scan per gate: 3-7 s per IQFT)
+
+
 def reference_iqft_seconds(n):
     """One inverse_QFT over all n qubits with the unmodified reference
     (oracle/_ref) if it was compiled, else the oracle restatement."""
@@ -142,14 +145,13 @@ def reference_iqft_seconds(n):
     return kind, dt
 
 
-def pick_reference_n(budget_s, kind_is_reference=True):
-    # measured cost of one reference inverse_QFT grows ~4.5x per qubit
-    table = {8: 0.015, 9: 0.07, 10: 0.32, 11: 1.6, 12: 6.8, 13: 31.0, 14: 146.0}
-    best = 8
-    for n, t in table.items():
-        if t <= budget_s:
-            best = max(best, n)
-    return best
+def reference_n_for(total_runs):
+    """n of the reference runs: REF_N unless (steps + warmup) of them would take much more than a few
+    minutes (cost grows ~4.5x per qubit, BASELINE.md section 2: 3-7 s at n = 12)."""
+    n = REF_N
+    while n > 8 and total_runs * 7.0 * 4.5 ** (n - REF_N) > 240.0:
+        n -= 1
+    return n
 
 
 def run_reference_arm(args):
@@ -157,7 +159,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     total = args.steps + args.warmup
-    n = args.qubits if args.qubits else pick_reference_n(150.0 / max(total, 1))
+    n = args.qubits if args.qubits else reference_n_for(total)
     kind = None
     for _ in range(args.warmup):
         kind, _dt = reference_iqft_seconds(n)
@@ -169,7 +171,8 @@ def run_reference_arm(args):
     total_s = sum(times)
     value = gates * len(times) / total_s
     sample = (f"inverse_QFT over all n={n} qubits ({gates} gates) of the synthetic state, seed {SEED}; "
-              f"the reference builds each gate as a 4^n-scan COO matrix, so n=30 is out of reach")
+              f"the reference builds each gate as a 4^n-scan COO matrix, so n=30 is out of reach; "
+              f"serial program: 1 thread of {os.cpu_count()} host cores")
     line = {
         "impl": "reference", "metric": "qft_gates_per_sec", "value": value, "unit": "gates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -184,39 +187,421 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(budget_s=25.0):
-    n = pick_reference_n(budget_s / 1.5)
+def port_gate_rate(n, all_cores, budget_s):
+    """The matrix-free restatement (oracle/qcs_oracle.c, O(2^n) per gate, the reference's arithmetic
+    order) on the inverse-QFT gate sequence of an n-qubit synthetic state, in program order
+    (qc_shor.c:682-689), stopped after budget_s seconds: gates done / time."""
+    import oracle
+    cls = oracle.RestatementAllCores if all_cores else oracle.Restatement
+    obj = cls(n, 0)
+    threads = obj.threads()
+    obj.fill_synthetic(SEED)
+    obj.scale(1.0 / math.sqrt(obj.norm2()))
+    done, t0 = 0, time.perf_counter()
+    for l in range(n - 1, -1, -1):
+        obj.hadamard_gate(l)
+        done += 1
+        for k in range(l - 1, -1, -1):
+            obj.c_phase_shift_gate(l, k, math.pi / float(1 << (l - k)))
+            done += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    obj.close()
+    return {"value": done / dt, "unit": "gates/s", "cores": threads, "kind": "port", "qubits": n,
+            "sample": f"first {done} of the {qft_gate_count(n)} gates of inverse_QFT at n={n} in program order "
+                      f"({dt:.1f} s), matrix-free restatement, {threads} thread(s) of {os.cpu_count()} host cores",
+            "n30_equivalent": done / dt * 2.0 ** (n - 30)}
+
+
+def cpu_baseline():
+    """(1) the unmodified reference at the reference arm's n; (2) the fair O(2^n)-per-gate port on one
+    thread (n = 24) and on all cores (n = 26), each a bounded sample."""
+    import oracle
+    n = REF_N
     kind, dt = reference_iqft_seconds(n)
     gates = qft_gate_count(n)
-    return {"value": gates / dt, "unit": "gates/s", "cores": 1, "kind": kind,
-            "sample": f"one inverse_QFT over all n={n} qubits ({gates} gates, {dt:.2f} s) of the synthetic "
-                      f"state, seed {SEED}; serial program, 1 thread of {os.cpu_count()} host cores"}
+    out = {"value": gates / dt, "unit": "gates/s", "cores": 1, "kind": kind,
+           "sample": f"one inverse_QFT over all n={n} qubits ({gates} gates, {dt:.2f} s) of the synthetic "
+                     f"state, seed {SEED}; serial program, 1 thread of {os.cpu_count()} host cores"}
+    try:
+        out["port_1_thread"] = port_gate_rate(24, False, 8.0)
+        if oracle.have_restatement_omp():
+            out["port_all_cores"] = port_gate_rate(26, True, 8.0)
+    except Exception as exc:                       # the baseline must never take the bench line down
+        out["port_error"] = repr(exc)
+    return out
 
 
 # --------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------
+NV_PEER_GBS = 770.0      # measured peer copy per direction per GPU (B200_PROFILING.md; nominal 900)
+
+
+def bitrev(x, bits):
+    r = 0
+    for _ in range(bits):
+        r = (r << 1) | (x & 1)
+        x >>= 1
+    return r
+
+
+class Ranks:
+    """torch.distributed plumbing of the bench (rendezvous, barrier, max / all-ok over ranks)."""
+
+    def __init__(self, q):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        self.q = q
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local_rank)
+            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+            self.torch = torch
+
+    def comm_id(self):
+        if self.dist is None:
+            return None
+        ids = [self.q.comm_unique_id() if self.rank == 0 else None]
+        self.dist.broadcast_object_list(ids, src=0)
+        return ids[0]
+
+    def barrier(self, reg=None):
+        if reg is not None:
+            reg.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def max(self, x):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def parity_block(q, reg, n, ranks):
+    """In-run correctness evidence on the register the timed region uses (every rank takes part):
+      * inverse_QFT of a basis state |k> against the closed form e^{2 pi i jk/N}/sqrt(N) at
+        bit-reversed j (SURVEY KAT-4, qc_shor.c:678-690), 16 probes in every rank's shard;
+      * QFT after inverse_QFT restores the synthetic state (64 probes per shard) and the norm;
+      * sample_states (one scan for all variates) against one locate per variate (the code path
+        measure_state runs), then measure_state itself: same index, collapsed state has norm 1.
+    Errors are relative to the amplitude scale 1/sqrt(N); the bar is north_star's 1e-12."""
+    import numpy as np
+    rank, world = ranks.rank, ranks.world
+    N, nl = 1 << n, reg.local_states
+    scale = 1.0 / math.sqrt(N)
+    rng = np.random.default_rng(97 + rank)
+    probes = sorted(set([0, 1, nl - 1, nl // 2, nl // 2 + 77] + [int(x) for x in rng.integers(0, nl, size=11)]))
+
+    # ---- closed form
+    k = (N - 1) - 0x12345 if n > 20 else N - 3           # lives in the last rank's shard: all global bits set
+    reg.reset_register()                                  # |0...01>
+    if rank == 0:
+        reg.set_state(np.array([0j]), first=1)
+    if k // nl == rank:
+        reg.set_state(np.array([1 + 0j]), first=k % nl)
+    reg.inverse_QFT()
+    err_closed = 0.0
+    for li in probes:
+        j = bitrev(rank * nl + li, n)
+        want = np.exp(2j * math.pi * ((j * k) % N) / N) * scale
+        err_closed = max(err_closed, abs(reg.get_state(li, 1)[0] - want) / scale)
+    norm_closed = reg.norm2()
+    reg.QFT()
+    back = abs(reg.get_state(k % nl, 1)[0] - 1.0) if k // nl == rank else 0.0
+
+    # ---- round trip on the synthetic state
+    reg.fill_synthetic(SEED)
+    reg.scale(1.0 / math.sqrt(reg.norm2()))
+    probes2 = sorted(set(probes + [int(x) for x in rng.integers(0, nl, size=48)]))
+    before = np.array([reg.get_state(li, 1)[0] for li in probes2])
+    reg.inverse_QFT()
+    mid = np.array([reg.get_state(li, 1)[0] for li in probes2])
+    reg.QFT()
+    after = np.array([reg.get_state(li, 1)[0] for li in probes2])
+    err_round = float(np.max(np.abs(after - before))) / scale
+    moved = float(np.max(np.abs(mid - before))) / scale    # the transform did something
+    norm_round = reg.norm2()
+
+    # ---- measurement (state: the synthetic one again, to rounding)
+    rs = [0.123456789, 0.5, 0.987654321]
+    many = [int(x) for x in reg.sample_states(rs)]
+    single = [int(reg.sample_states([r])[0]) for r in rs]
+    # i.i.d. random amplitudes: the cumulative probability is linear in the index to ~1/sqrt(N)
+    linear = max(abs(idx / N - r) for idx, r in zip(many, rs))
+    measured = int(reg.measure_state(rs[0]))
+    norm_collapsed = reg.norm2()
+    measure_ok = many == single and measured == many[0] and norm_collapsed == 1.0 and linear < 1e-3
+
+    err_closed = ranks.max(max(err_closed, back))       # `back`: |amp[k] - 1| after the forward transform
+    err_round = ranks.max(err_round)
+    moved = ranks.max(moved)
+    bad = ranks.max(0.0 if measure_ok else 1.0)
+    ok = (err_closed <= 1e-12 and err_round <= 1e-12 and moved > 1e-3 and bad == 0.0 and
+          abs(norm_closed - 1.0) < 1e-12 and abs(norm_round - 1.0) < 1e-12)
+    return {"ok": bool(ok), "max_rel_err": max(err_closed, err_round),
+            "closed_form_max_rel_err": err_closed, "closed_form_probes": len(probes) * world,
+            "round_trip_max_rel_err": err_round, "round_trip_probes": len(probes2) * world,
+            "norm_after_closed_form": norm_closed, "norm_after_round_trip": norm_round,
+            "measure": {"ok": bool(bad == 0.0), "indices": many, "variates": rs,
+                        "sample_states_equals_locate": many == single, "measure_state_index": measured,
+                        "norm_after_collapse": norm_collapsed},
+            "tolerance": 1e-12,
+            "what": "inverse_QFT|k> vs closed form at bit-reversed probes in every shard; QFT(inverse_QFT(state)) "
+                    "vs state; sample_states vs per-variate locate vs measure_state"}
+
+
+def roofline_from_profile(prof, n, world, circuit_is_qft, peak, peak_src):
+    dom = max((k for k in prof if prof[k][0] > 0), key=lambda k: prof[k][1])
+    d_launches, d_ms, d_bytes = prof[dom]
+    achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
+    kernel_ms = sum(v[1] for v in prof.values())
+    if dom == "global_sweep":
+        # multi-GPU: the sweep over the global qubits is bound by NVLink; the denominator is the
+        # measured peer copy per direction per GPU stated in B200_PROFILING.md (nominal 900)
+        return {"bound": "nvlink", "kernel": dom, "achieved": achieved, "peak": NV_PEER_GBS, "unit": "GB/s",
+                "frac": achieved / NV_PEER_GBS,
+                "peak_source": "B200_PROFILING.md measured peer copy per direction per GPU (of measured)",
+                "traffic": None, "launches": d_launches, "avg_launch_ms": d_ms / d_launches,
+                "algorithmic_bytes_per_launch": d_bytes / d_launches,
+                "share_of_kernel_time": d_ms / kernel_ms if kernel_ms else None,
+                "bytes_model": "NVLink bytes per direction per GPU and launch (remote reads, or remote writes, of the "
+                               "rank's share of the tiles of the global sweep)",
+                "local_sweeps_GBps": (prof["tile_sweep"][2] / (prof["tile_sweep"][1] * 1e-3) / 1e9
+                                      if prof["tile_sweep"][1] > 0 else None)}
+    traffic, traffic_src = (profiled_traffic(n) if (dom == "tile_sweep" and circuit_is_qft and world == 1)
+                            else (None, None))
+    return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "peak_source": peak_src + " (of measured)",
+            "traffic": traffic,
+            "traffic_source": (traffic_src + " (committed ncu --set full capture of this workload, not this run)"
+                               if traffic_src else None),
+            "launches": d_launches, "avg_launch_ms": d_ms / d_launches,
+            "algorithmic_bytes_per_launch": d_bytes / d_launches,
+            "share_of_kernel_time": d_ms / kernel_ms if kernel_ms else None,
+            "bytes_model": CLASS_BYTES_NOTE.get(dom, "")}
+
+
+def timed_steps(q, reg, ranks, one_step, steps, warmup, sample_clocks):
+    """W warm-up steps, then K steps between barriers, device-timed, max over ranks."""
+    for _ in range(warmup):
+        one_step()
+    ranks.barrier(reg)
+    reg.set_option(q.OPT_PROFILE, 1)
+    reg.profile_reset()
+    sampler = ClockSampler(ranks.local_rank) if sample_clocks else None
+    if sampler:
+        sampler.start()
+    ranks.barrier(reg)
+    reg.timer_start()
+    for _ in range(steps):
+        one_step()
+    ms = reg.timer_stop()
+    ranks.barrier(reg)
+    clocks = sampler.stop() if sampler else None
+    ms = ranks.max(ms)
+    prof = reg.profile()
+    launches = reg.launch_count
+    reg.set_option(q.OPT_PROFILE, 0)
+    return ms, prof, launches, clocks
+
+
+def apply_tuning(q, reg, args):
+    reg.set_option(q.OPT_FUSION, 0 if args.no_fusion else 1)
+    if args.tile_bits:
+        reg.set_option(q.OPT_TILE_BITS, args.tile_bits)
+    if args.prefetch >= 0:
+        reg.set_option(q.OPT_PREFETCH_TILES, args.prefetch)
+    if args.pipe_shape >= 0:
+        reg.set_option(q.OPT_PIPE_SHAPE, args.pipe_shape)
+    if args.min_run_bits > 0:
+        reg.set_option(q.OPT_MIN_RUN_BITS, args.min_run_bits)
+    if args.global_run_bits > 0:
+        reg.set_option(q.OPT_GLOBAL_RUN_BITS, args.global_run_bits)
+    if args.overlap_slices >= 0:
+        reg.set_option(q.OPT_OVERLAP_SLICES, args.overlap_slices)
+    if args.global_sms > 0:
+        reg.set_option(q.OPT_GLOBAL_SMS, args.global_sms)
+    for name, opt in (("l2_pair", "OPT_L2_PAIR"), ("keep_permuted", "OPT_KEEP_PERMUTED")):
+        v = getattr(args, name, -1)
+        if v >= 0 and hasattr(q, opt):
+            reg.set_option(getattr(q, opt), v)
+
+
+def north_star_block(q, ranks, args, peak, peak_src):
+    """BASELINE `metric`: QFT time at n = 33 (1 GPU), 34 (2), 35 (4 and 8), timed in this run."""
+    world = ranks.world
+    n = {1: 33, 2: 34, 4: 35, 8: 35}.get(world)
+    if n is None:
+        return None
+    p = int(math.log2(world))
+    reg = q.Register(n, 0, device=ranks.local_rank, rank=ranks.rank, world_size=world, comm_id=ranks.comm_id())
+    apply_tuning(q, reg, args)
+    try:
+        import numpy as np
+        # parity at this size: closed form of a basis state at 8 probes per shard
+        N, nl = 1 << n, reg.local_states
+        k = (N - 1) - 0x54321
+        reg.reset_register()
+        if ranks.rank == 0:
+            reg.set_state(np.array([0j]), first=1)
+        if k // nl == ranks.rank:
+            reg.set_state(np.array([1 + 0j]), first=k % nl)
+        reg.inverse_QFT()
+        scale = 1.0 / math.sqrt(N)
+        err = 0.0
+        for li in (0, 1, nl - 1, nl // 2 + 5, nl // 3, nl // 5, nl // 7, (nl // 11) * 3):
+            j = bitrev(ranks.rank * nl + li, n)
+            want = np.exp(2j * math.pi * ((j * k) % N) / N) * scale
+            err = max(err, abs(reg.get_state(li, 1)[0] - want) / scale)
+        err = ranks.max(err)
+        norm_closed = reg.norm2()
+        reg.fill_synthetic(SEED)
+        reg.scale(1.0 / math.sqrt(reg.norm2()))
+        steps = max(1, min(args.steps, args.north_star_steps))
+        ms, prof, launches, _ = timed_steps(q, reg, ranks, reg.inverse_QFT, steps, 3, False)
+        norm_out = reg.norm2()
+        gates = qft_gate_count(n)
+        out = {"qubits": n, "n_gpus": world, "state_bytes_per_gpu": int(16 * nl), "steps": steps, "warmup": 3,
+               "ms_per_qft": ms / steps, "gates_per_step": gates, "gates_per_sec": gates * steps / (ms * 1e-3),
+               "n30_equivalent_gates_per_sec": gates * 2.0 ** (n - 30) * steps / (ms * 1e-3),
+               "parallelism": f"top {p} qubits global", "gpu_launches": int(launches),
+               "parity": {"ok": bool(err <= 1e-12 and abs(norm_closed - 1.0) < 1e-12 and abs(norm_out - 1.0) < 1e-10),
+                          "closed_form_max_rel_err": err, "closed_form_probes": 8 * world,
+                          "norm_after_closed_form": norm_closed, "norm_after_timed_steps": norm_out},
+               "roofline": roofline_from_profile(prof, n, world, False, peak, peak_src),
+               "kernels": {kk: {"launches": v[0], "ms": round(v[1], 4),
+                                "GBps": round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] > 0 else None}
+                           for kk, v in prof.items() if v[0]}}
+    finally:
+        reg.close()
+    return out
+
+
+def run_shor(q, ranks, args):
+    """BASELINE configs[0] / [1]: wall time of the quantum half of find_period (qc_shor.c:922-928:
+    reset_register, quantum_computation, measure_state) through the C ABI, beside the reference's
+    own time for the same calls on the host, the measured index compared run by run; plus one
+    n = 30 quantum_computation (L = 18, M = 12) for the throughput of the modular-exponentiation sweep."""
+    from quantumcomputer_b200.workloads import mt19937_uniforms
+    import numpy as np
+    if ranks.world != 1:
+        raise SystemExit("--workload shor is a single-GPU workload")
+    import oracle
+    if not oracle.have_restatement():
+        oracle.build()
+    peak, peak_src = measured_peaks()
+    runs = max(5, min(args.steps, 40))
+    cases = []
+    specs = [("cfg1 (BASELINE configs[0])", 15, 7, 3, 4, q.POW_VERBATIM, 12345),
+             ("cfg2 reference-safe (BASELINE configs[1])", 21, 2, 5, 5, q.POW_VERBATIM, 2021),
+             ("cfg2 full size, intended a^x mod C", 21, 2, 10, 5, q.POW_MODULAR, 2021)]
+    for name, Cn, a, L, M, mode, seed in specs:
+        n = L + M
+        rs = mt19937_uniforms(seed, runs)
+        with q.Register(L, M, device=ranks.local_rank) as reg:
+            for _ in range(3):                                   # warm-up (module load, allocations)
+                reg.reset_register(); reg.quantum_computation(Cn, a, mode); reg.measure_state(0.5)
+            before = reg.launch_count
+            got, t_gpu = [], []
+            for r in rs:
+                t0 = time.perf_counter()
+                reg.reset_register()
+                reg.quantum_computation(Cn, a, mode)
+                got.append(int(reg.measure_state(r)))
+                t_gpu.append(time.perf_counter() - t0)
+            launches = (reg.launch_count - before) / runs
+        # the CPU side: the unmodified reference where it finishes in seconds and the pow mode is its own,
+        # else the matrix-free restatement
+        use_ref = oracle.have_reference() and mode == q.POW_VERBATIM and n <= 10
+        cpu = oracle.Reference(L, M) if use_ref else oracle.Restatement(L, M)
+        want, t_cpu = [], []
+        cpu_runs = runs if n <= 7 else min(runs, 5)
+        for r in rs[:cpu_runs]:
+            t0 = time.perf_counter()
+            cpu.reset_register()
+            if use_ref:
+                cpu.quantum_computation(Cn, a)
+                want.append(int(cpu.measure_state_r(r)))
+            else:
+                cpu.quantum_computation(Cn, a, 1 if mode == q.POW_MODULAR else 0)
+                want.append(int(cpu.measure_state(r)))
+            t_cpu.append(time.perf_counter() - t0)
+        cpu.close()
+        cases.append({"case": name, "C": Cn, "a": a, "L": L, "M": M, "qubits": n,
+                      "gates": 3 * L + L * (L - 1) // 2,
+                      "gpu_ms_per_find_period": 1e3 * float(np.median(t_gpu)), "gpu_runs": runs,
+                      "gpu_launches_per_find_period": launches,
+                      "cpu_ms_per_find_period": 1e3 * float(np.median(t_cpu)), "cpu_runs": cpu_runs,
+                      "cpu_kind": "reference" if use_ref else "port", "cpu_cores": 1,
+                      "measured_indices_identical": got[:cpu_runs] == want, "indices": got[:8]})
+    # ---- n = 30: the modular exponentiation as one block-local sweep
+    L, M, Cn, a = 18, 12, 4087, 7                                 # 4087 = 61 * 67 < 2^12
+    with q.Register(L, M, device=ranks.local_rank) as reg:
+        reg.reset_register(); reg.quantum_computation(Cn, a, q.POW_MODULAR); reg.synchronize()
+        reg.set_option(q.OPT_PROFILE, 1)
+        reg.profile_reset()
+        reg.timer_start()
+        big_runs = 5
+        for _ in range(big_runs):
+            reg.reset_register()
+            reg.quantum_computation(Cn, a, q.POW_MODULAR)
+        ms = reg.timer_stop()
+        prof = reg.profile()
+        launches = reg.launch_count
+        norm = reg.norm2()
+        idx = int(reg.measure_state(0.6180339887))
+    per_class = {k: {"launches": v[0], "ms": round(v[1], 4),
+                     "GBps": round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] > 0 else None}
+                 for k, v in prof.items() if v[0]}
+    mx = prof["modexp_sweep"]
+    mx_gbps = mx[2] / (mx[1] * 1e-3) / 1e9 if mx[1] > 0 else 0.0
+    gates30 = 3 * L + L * (L - 1) // 2
+    ok = all(c["measured_indices_identical"] for c in cases) and abs(norm - 1.0) < 1e-10
+    line = {"metric": "shor_quantum_computation_gates_per_sec", "value": gates30 * big_runs / (ms * 1e-3), "unit": "gates/s",
+            "n_gpus": 1, "steps": big_runs, "warmup": 1, "ms_per_step": ms / big_runs, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 amplitudes, u32 index arithmetic", "data": "synthetic",
+            "config": {"workload": f"reset_register + quantum_computation(C={Cn}, a={a}), L={L}, M={M} (n=30, {gates30} gates "
+                                   f"per step: {L} H, {L} controlled a^(2^k) mod C, inverse QFT on the L register)",
+                       "qubits": 30, "norm_after": norm, "measured_index": idx},
+            "roofline": {"bound": "hbm", "kernel": "modexp_sweep", "achieved": mx_gbps, "peak": peak, "unit": "GB/s",
+                         "frac": mx_gbps / peak, "peak_source": peak_src + " (of measured)", "traffic": None,
+                         "launches": mx[0], "avg_launch_ms": mx[1] / max(mx[0], 1),
+                         "algorithmic_bytes_per_launch": mx[2] / max(mx[0], 1),
+                         "bytes_model": "32 * 2^n * C / 2^M B per launch (read + write the rows f < C of every block)"},
+            "kernels": per_class, "gpu_launches": int(launches),
+            "find_period": cases, "parity": {"ok": bool(ok)}}
+    print(json.dumps(line), flush=True)
+    ranks.close()
+    if not ok:
+        raise SystemExit(3)
+
+
 def run_ours(args):
     import quantumcomputer_b200 as q
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ranks = Ranks(q)
+    rank, world, local_rank = ranks.rank, ranks.world, ranks.local_rank
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
         args.gpus = world
-
-    dist = None
-    comm_id = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-        ids = [q.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        comm_id = ids[0]
+    if args.workload == "shor":
+        return run_shor(q, ranks, args)
 
     p = int(math.log2(world))
     if args.workload == "layered":
@@ -234,25 +619,12 @@ def run_ours(args):
         gates = qft_gate_count(n)
         workload = (f"inverse_QFT over all n={n} qubits of a synthetic random state "
                     f"(BASELINE configs[2]; {gates} gates per step)")
-    reg = q.Register(n, 0, device=local_rank, rank=rank, world_size=world, comm_id=comm_id)
-    reg.set_option(q.OPT_FUSION, 0 if args.no_fusion else 1)
-    if args.tile_bits:
-        reg.set_option(q.OPT_TILE_BITS, args.tile_bits)
-    if args.prefetch >= 0:
-        reg.set_option(q.OPT_PREFETCH_TILES, args.prefetch)
-    if args.pipe_shape >= 0:
-        reg.set_option(q.OPT_PIPE_SHAPE, args.pipe_shape)
-    if args.min_run_bits > 0:
-        reg.set_option(q.OPT_MIN_RUN_BITS, args.min_run_bits)
-    if args.global_run_bits > 0:
-        reg.set_option(q.OPT_GLOBAL_RUN_BITS, args.global_run_bits)
-    if args.overlap_slices >= 0:
-        reg.set_option(q.OPT_OVERLAP_SLICES, args.overlap_slices)
-    if args.global_sms > 0:
-        reg.set_option(q.OPT_GLOBAL_SMS, args.global_sms)
+    reg = q.Register(n, 0, device=local_rank, rank=rank, world_size=world, comm_id=ranks.comm_id())
+    apply_tuning(q, reg, args)
 
     if circuit is not None:
         args.no_cpu_baseline = True                  # the CPU arm times the headline (iqft) workload
+        args.no_north_star = True
         if 16 * reg.local_states > 32 * 2 ** 30:
             args.no_e2e = True                       # no 128 GiB pinned host mirror of an n = 33 state
 
@@ -263,44 +635,24 @@ def run_ours(args):
             with reg.fused():
                 apply_gates(reg, circuit)
 
-    def barrier():
-        reg.synchronize()
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    # ---- in-run parity on this register (all ranks), before anything is timed
+    parity = None
+    if circuit is None and not args.no_parity:
+        parity = parity_block(q, reg, n, ranks)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"error": "parity check failed", "parity": parity}), flush=True)
+            reg.close()
+            ranks.close()
+            raise SystemExit(3)
 
     # synthetic state, generated on the device, normalised
     reg.fill_synthetic(SEED)
     reg.scale(1.0 / math.sqrt(reg.norm2()))
     norm_in = reg.norm2()
 
-    for _ in range(args.warmup):
-        one_step()
-    barrier()
-
     # ---- device-resident throughput ("value")
-    reg.set_option(q.OPT_PROFILE, 1)
-    reg.profile_reset()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    reg.timer_start()
-    for _ in range(args.steps):
-        one_step()
-    ms = reg.timer_stop()
-    barrier()
-    clocks = sampler.stop()
-    ms = max_over_ranks(ms)
-    prof = reg.profile()
-    launches = reg.launch_count
-    reg.set_option(q.OPT_PROFILE, 0)
+    ms, prof, launches, clocks = timed_steps(q, reg, ranks, one_step, args.steps, args.warmup, True)
     norm_out = reg.norm2()
 
     # ---- end to end through the C ABI with host buffers ("e2e")
@@ -310,8 +662,8 @@ def run_ours(args):
         pinned = q.PinnedBuffer(2 * local)
         reg.get_state(0, local, out=pinned.array)          # a normalised host-resident input
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        barrier()
-        t_ms = 0.0
+        ranks.barrier(reg)
+        t_ms, h2d_ms = 0.0, 0.0
         for step_i in range(e2e_steps):
             reg.timer_start()
             reg.set_state_async(pinned.array)               # H2D from pinned memory
@@ -319,75 +671,74 @@ def run_ours(args):
             # the step's result, as in find_period (qc_shor.c:923-928): the measured index (8 bytes D2H)
             result = reg.measure_state(((step_i * 2654435761 + 12345) % 2 ** 32) / 2.0 ** 32)
             t_ms += reg.timer_stop()
-        t_ms = max_over_ranks(t_ms)
+        # the upload alone, for the PCIe share of the number above
+        reg.timer_start()
+        reg.set_state_async(pinned.array)
+        h2d_ms = ranks.max(reg.timer_stop())
+        t_ms = ranks.max(t_ms)
         e2e = {"value": gates * e2e_steps / (t_ms * 1e-3), "unit": "gates/s",
                "h2d_bytes_per_step": int(16 * local * world), "d2h_bytes_per_step": 8 * world,
                "steps": e2e_steps, "ms_per_step": t_ms / e2e_steps,
+               "h2d_ms": h2d_ms, "h2d_GBps_per_gpu": 16 * local / (h2d_ms * 1e-3) / 1e9,
                "result": "measure_state index read back each step (qc_shor.c:928)", "last_result": result}
         pinned.close()
 
+    peak, peak_src = measured_peaks()
+    line = None
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        # dominant kernel class = most device time
-        dom = max((k for k in prof if prof[k][0] > 0), key=lambda k: prof[k][1])
-        d_launches, d_ms, d_bytes = prof[dom]
-        achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
-        kernel_ms = sum(v[1] for v in prof.values())
-        traffic, traffic_src = profiled_traffic(n) if (dom == "tile_sweep" and circuit is None and world == 1) else (None, None)
-        if dom == "global_sweep":
-            # multi-GPU: the sweep over the global qubits is bound by NVLink; the denominator is the
-            # measured peer copy per direction per GPU stated in B200_PROFILING.md (nominal 900)
-            nv_peak = 770.0
-            roofline = {"bound": "nvlink", "kernel": dom, "achieved": achieved, "peak": nv_peak, "unit": "GB/s",
-                        "frac": achieved / nv_peak,
-                        "peak_source": "B200_PROFILING.md measured peer copy per direction per GPU (of measured)",
-                        "traffic": None, "launches": d_launches, "avg_launch_ms": d_ms / d_launches,
-                        "algorithmic_bytes_per_launch": d_bytes / d_launches,
-                        "share_of_kernel_time": d_ms / kernel_ms if kernel_ms else None,
-                        "bytes_model": "NVLink bytes per direction per GPU and launch: 2*(P-1)/P * 16*2^n_local "
-                                       "(remote reads + remote writes of the rank's share of the tiles)",
-                        "local_sweeps_GBps": (prof["tile_sweep"][2] / (prof["tile_sweep"][1] * 1e-3) / 1e9
-                                              if prof["tile_sweep"][1] > 0 else None)}
-        else:
-            roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "peak_source": peak_src + " (of measured)",
-                        "traffic": traffic, "traffic_source": traffic_src, "launches": d_launches,
-                        "avg_launch_ms": d_ms / d_launches,
-                        "algorithmic_bytes_per_launch": d_bytes / d_launches,
-                        "share_of_kernel_time": d_ms / kernel_ms if kernel_ms else None,
-                        "bytes_model": CLASS_BYTES_NOTE.get(dom, "")}
         per_class = {k: {"launches": v[0], "ms": round(v[1], 4),
                          "GBps": round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] > 0 else None}
                      for k, v in prof.items() if v[0]}
+        gates_per_s = gates * args.steps / (ms * 1e-3)
+        # Weak scaling grows n with the GPU count, and one gate on n+1 qubits is twice the work, so for
+        # N > 1 the value is the n = 30-equivalent gate rate (gates/s x 2^(n-30)): extensive in the GPU
+        # count, identical to gates/s at N = 1 (n = 30).
+        value = gates_per_s * 2.0 ** (n - 30) if (circuit is None and world > 1) else gates_per_s
         line = {
             "metric": "qft_gates_per_sec" if circuit is None else "layered_circuit_gates_per_sec",
-            "value": gates * args.steps / (ms * 1e-3), "unit": "gates/s",
+            "value": value, "unit": "gates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload,
                        "qubits": n, "gates_per_step": gates, "state_bytes_per_gpu": int(16 * reg.local_states),
+                       "value_definition": ("gates/s at n=30" if world == 1 or circuit is not None else
+                                            f"n=30-equivalent gates/s = gates/s at n={n} x 2^(n-30) "
+                                            f"(= amplitude-gate updates/s / 2^30), so that it can scale with the GPU count"),
+                       "gates_per_sec_at_n": gates_per_s,
                        "fusion": int(reg.get_option(q.OPT_FUSION)), "parallelism": f"top {p} qubits global",
                        "pipe_shape": int(reg.get_option(q.OPT_PIPE_SHAPE)),
                        "min_run_bits": int(reg.get_option(q.OPT_MIN_RUN_BITS)),
                        "l2": f"state ({16 * reg.local_states / 2 ** 30:.0f} GiB per GPU) is far larger than the "
                              f"126 MB L2; no flush needed",
                        "norm_before": norm_in, "norm_after": norm_out},
-            # gates/s cannot scale with the GPU count when n grows with it (a gate on n+1 qubits is
-            # twice the work): amplitude updates per second = gates * 2^n / time is the rate that can
             "work_rate": {"value": gates * float(1 << n) * args.steps / (ms * 1e-3), "unit": "amplitude-gate updates/s"},
-            "roofline": roofline, "kernels": per_class,
+            "roofline": roofline_from_profile(prof, n, world, circuit is None, peak, peak_src),
+            "kernels": per_class,
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if parity is not None:
+            line["parity"] = parity
         if e2e is not None:
             line["e2e"] = e2e
+    reg.close()
+
+    # ---- BASELINE's multi-GPU metric at its own sizes, same run
+    if circuit is None and not args.no_north_star and not args.qubits:
+        ns = north_star_block(q, ranks, args, peak, peak_src)
+        if rank == 0 and ns is not None:
+            line["north_star"] = ns
+            if not ns["parity"]["ok"]:
+                line["error"] = "north_star parity check failed"
+
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
-    reg.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    failed = rank == 0 and "error" in line
+    ranks.close()
+    if failed:
+        raise SystemExit(3)
 
 
 def main():
@@ -400,8 +751,9 @@ def main():
     ap.add_argument("--no-fusion", action="store_true", help="gate-by-gate reference-order kernels")
     ap.add_argument("--tile-bits", type=int, default=0)
     ap.add_argument("--prefetch", type=int, default=-1, help="L2 prefetch distance in tiles (-1: library default)")
-    ap.add_argument("--workload", choices=["iqft", "layered"], default="iqft",
-                    help="iqft: BASELINE configs[2] (default, the headline metric); layered: configs[3]")
+    ap.add_argument("--workload", choices=["iqft", "layered", "shor"], default="iqft",
+                    help="iqft: BASELINE configs[2] (default, the headline metric); layered: configs[3]; "
+                         "shor: configs[0] / [1] wall time per find_period beside the reference's + an n = 30 quantum_computation")
     ap.add_argument("--layers", type=int, default=8)
     ap.add_argument("--pipe-shape", type=int, default=-1)
     ap.add_argument("--min-run-bits", type=int, default=0)
@@ -411,6 +763,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity block")
+    ap.add_argument("--no-north-star", action="store_true", help="skip the n = 33/34/35 block")
+    ap.add_argument("--north-star-steps", type=int, default=5)
+    ap.add_argument("--l2-pair", type=int, default=-1)
+    ap.add_argument("--keep-permuted", type=int, default=-1)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

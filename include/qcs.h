@@ -217,6 +217,11 @@ int qcs_get_state(qcs_register *reg, unsigned long long first, unsigned long lon
                   double *interleaved_out);
 int qcs_set_state(qcs_register *reg, unsigned long long first, unsigned long long count,
                   const double *interleaved_in);
+/* qcs_set_state returns when the copy is done.  The _async form is stream-ordered: the source
+ * (pinned, qcs_host_alloc) must stay valid and unchanged until qcs_synchronize / any synchronising
+ * call returns. */
+int qcs_set_state_async(qcs_register *reg, unsigned long long first, unsigned long long count,
+                        const double *interleaved_in);
 
 /* Arbitrary single-qubit gate: the 2x2 complex matrix u (row-major, interleaved re/im, 8
  * doubles) on qubit_num -- what HADAMARD_BASE_MATRIX (Q:210-213) is one instance of -- and its

@@ -7,6 +7,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ORACLE_SO = os.path.join(_HERE, "_build", "libqcsoracle.so")
+_ORACLE_OMP_SO = os.path.join(_HERE, "_build", "libqcsoracle_omp.so")
 _REF_SO = os.path.join(_HERE, "_ref", "libqcref.so")
 
 _u = C.c_uint
@@ -26,6 +27,10 @@ def have_restatement():
 
 def have_reference():
     return os.path.exists(_REF_SO)
+
+
+def have_restatement_omp():
+    return os.path.exists(_ORACLE_OMP_SO)
 
 
 def _as_dp(a):
@@ -51,8 +56,8 @@ class MT19937:
         return float(self._lib.orc_mt_uniform(C.byref(self._g)))
 
 
-def _load_restatement():
-    lib = C.CDLL(_ORACLE_SO)
+def _load_restatement(path=None):
+    lib = C.CDLL(path or _ORACLE_SO)
     vp = C.c_void_p
     lib.orc_create.restype = vp
     lib.orc_create.argtypes = [C.c_int, C.c_int]
@@ -92,6 +97,7 @@ def _load_restatement():
     lib.orc_synthetic_u.argtypes = [C.c_uint64, C.c_uint64]
     lib.orc_fill_synthetic.argtypes = [vp, C.c_uint64]
     lib.orc_scale.argtypes = [vp, C.c_double]
+    lib.orc_threads.restype = C.c_int
     return lib
 
 
@@ -105,6 +111,10 @@ class Restatement:
         if cls._lib is None:
             cls._lib = _load_restatement()
         return cls._lib
+
+    @classmethod
+    def threads(cls):
+        return int(cls.lib().orc_threads())
 
     def __init__(self, L_size, M_size):
         self.L, self.M = L_size, M_size
@@ -206,6 +216,19 @@ class Restatement:
     @classmethod
     def synthetic_u(cls, seed, k):
         return float(cls.lib().orc_synthetic_u(seed, k))
+
+
+class RestatementAllCores(Restatement):
+    """The same restatement compiled with -fopenmp: the row loops of hadamard_gate and
+    c_phase_shift_gate run on all host cores (bit-identical results; bench.py's cpu_baseline)."""
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            cls._lib = _load_restatement(_ORACLE_OMP_SO)
+        return cls._lib
 
 
 def _load_reference():

@@ -34,6 +34,20 @@ static inline void accumulate(double *dst, double m_re, double m_im, const doubl
     dst[1] += (m_re * c_im) + (m_im * c_re);
 }
 
+/* The all-cores CPU baseline of bench.py (the "fair" matrix-free port) is this same
+ * file compiled with -fopenmp: the rows of a Hadamard / controlled-phase gate are independent, so
+ * the row loop is split over the threads and each thread zeroes its own rows (operate_matrix's
+ * zeroing, qc_shor.c:393) -- the arithmetic per row, and therefore every result bit, is unchanged. */
+#ifdef _OPENMP
+#define ORC_ZERO(nxt, N) ((void) 0)
+#define ORC_ROW_ZERO(p) do { (p)[0] = 0.0; (p)[1] = 0.0; } while (0)
+#define ORC_PARALLEL_FOR _Pragma("omp parallel for schedule(static)")
+#else
+#define ORC_ZERO(nxt, N) memset(nxt, 0, 2 * (N) * sizeof(double))
+#define ORC_ROW_ZERO(p) ((void) 0)
+#define ORC_PARALLEL_FOR
+#endif
+
 static void finish_gate(orc_register *r)
 {
     /* swap_states, qc_shor.c:242-249 */
@@ -89,9 +103,11 @@ void orc_hadamard_gate(orc_register *r, unsigned q)
     const double h = M_SQRT1_2;
     const double *cur = r->cur;
     double *nxt = r->nxt;
-    memset(nxt, 0, 2 * N * sizeof(double));                /* qc_shor.c:393 */
+    ORC_ZERO(nxt, N);                                      /* qc_shor.c:393 */
+    ORC_PARALLEL_FOR
     for (uint64_t i = 0; i < N; i++) {
         uint64_t j0 = i & ~bit, j1 = i | bit;
+        ORC_ROW_ZERO(nxt + 2 * i);
         double m0 = h;                                      /* H[b][0] */
         double m1 = (i & bit) ? -h : h;                     /* H[b][1] */
         accumulate(nxt + 2 * i, m0, 0.0, cur + 2 * j0);
@@ -111,8 +127,8 @@ void orc_c_phase_shift_gate(orc_register *r, unsigned c, unsigned q, double thet
     const double e_re = 1.0 * cos(theta), e_im = 1.0 * sin(theta);   /* gsl_complex_polar, qc_shor.c:526 */
     const double *cur = r->cur;
     double *nxt = r->nxt;
-    memset(nxt, 0, 2 * N * sizeof(double));
     if (c == q) {
+        memset(nxt, 0, 2 * N * sizeof(double));
         /* degenerate call (never made by the reference): the delta test leaves
          * rows/cols free in one bit only, base index is 3*bit */
         for (uint64_t i = 0; i < N; i++) {
@@ -128,8 +144,11 @@ void orc_c_phase_shift_gate(orc_register *r, unsigned c, unsigned q, double thet
         return;
     }
     const uint64_t lo = cb < qb ? cb : qb, hi = cb < qb ? qb : cb;
+    ORC_ZERO(nxt, N);
+    ORC_PARALLEL_FOR
     for (uint64_t i = 0; i < N; i++) {
         uint64_t base = i & ~(cb | qb);
+        ORC_ROW_ZERO(nxt + 2 * i);
         int bi = ((i & cb) ? 2 : 0) + ((i & qb) ? 1 : 0);
         uint64_t cols[4] = { base, base | lo, base | hi, base | lo | hi };
         for (int s = 0; s < 4; s++) {
@@ -391,6 +410,17 @@ void orc_fill_synthetic(orc_register *r, uint64_t seed)
         r->cur[2 * i] = orc_synthetic_u(seed, 2 * i);
         r->cur[2 * i + 1] = orc_synthetic_u(seed, 2 * i + 1);
     }
+}
+
+/* threads the row loops run on: 1 unless built with -fopenmp */
+int orc_threads(void)
+{
+#ifdef _OPENMP
+    extern int omp_get_max_threads(void);
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
 }
 
 void orc_scale(orc_register *r, double s)

@@ -283,12 +283,11 @@ class Register:
             a = np.ascontiguousarray(a, dtype=np.complex128).view(np.float64)
         a = np.ascontiguousarray(a)
         _check(self._l.qcs_set_state(self._h, first, a.size // 2, a.ctypes.data), "set_state")
-        self.synchronize()      # `a` may be a temporary
 
     def set_state_async(self, float64_array, first=0):
         """Host -> device copy without the trailing synchronise (pinned source)."""
-        _check(self._l.qcs_set_state(self._h, first, float64_array.size // 2,
-                                     float64_array.ctypes.data), "set_state")
+        _check(self._l.qcs_set_state_async(self._h, first, float64_array.size // 2,
+                                           float64_array.ctypes.data), "set_state_async")
 
     # ---- deferred gate stream
     def fuse_begin(self):

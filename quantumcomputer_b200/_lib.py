@@ -48,6 +48,7 @@ SIGNATURES = [
     ("qcs_nonzero_states", C.c_int, [_vp, _ull, C.POINTER(_ull), _dp, C.POINTER(_ull)]),
     ("qcs_get_state", C.c_int, [_vp, _ull, _ull, _vp]),
     ("qcs_set_state", C.c_int, [_vp, _ull, _ull, _vp]),
+    ("qcs_set_state_async", C.c_int, [_vp, _ull, _ull, _vp]),
     ("qcs_sample_states", C.c_int, [_vp, _ull, _vp, _vp]),
     ("qcs_apply_gate", C.c_int, [_vp, _u, _vp]),
     ("qcs_apply_controlled_gate", C.c_int, [_vp, _u, _u, _vp]),

@@ -651,6 +651,20 @@ extern "C" int qcs_set_state(qcs_register *reg, unsigned long long first, unsign
     if (first > reg->N_local || count > reg->N_local - first || (!interleaved_in && count)) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaMemcpyAsync(reg->amp + first, interleaved_in, count * sizeof(double2),
                              cudaMemcpyHostToDevice, reg->stream));
+    // the caller may reuse or free the buffer as soon as this returns (qcs_get_state synchronises too)
+    QCS_CUDA(cudaStreamSynchronize(reg->stream));
+    return QCS_NO_ERROR;
+}
+
+// the same, stream-ordered: the source (pinned memory from qcs_host_alloc for a real overlap) must
+// stay valid and unchanged until qcs_synchronize or any synchronising call returns
+extern "C" int qcs_set_state_async(qcs_register *reg, unsigned long long first, unsigned long long count,
+                                   const double *interleaved_in)
+{
+    QCS_ENTER(reg);
+    if (first > reg->N_local || count > reg->N_local - first || (!interleaved_in && count)) return QCS_BAD_ARGUMENTS;
+    QCS_CUDA(cudaMemcpyAsync(reg->amp + first, interleaved_in, count * sizeof(double2),
+                             cudaMemcpyHostToDevice, reg->stream));
     return QCS_NO_ERROR;
 }
 

@@ -32,6 +32,7 @@ using qft::diag_gate;
 using qft::sweep_plan;
 
 constexpr int kThreads = 256;
+constexpr size_t kDiagScratchSlots = 1024;   // head of d_diag: staging of the standalone diagonal passes
 constexpr int kMaxDiagPerSweep = 48;   // beyond this a sweep turns FP64-bound: spill to a diagonal pass
 
 // one pass over the shard applying a list of diagonal gates: 32 B per amplitude
@@ -127,9 +128,12 @@ int launch_diag_list(qcs_register *reg, const std::vector<qcs_pending_gate> &que
         if (localise(reg, queue[(size_t) gi], dg)) host_stage.push_back(dg);
     }
     if (host_stage.empty()) return QCS_NO_ERROR;
-    for (size_t at = 0; at < host_stage.size(); at += 1024) {
-        const int n = (int) std::min<size_t>(1024, host_stage.size() - at);
-        QCS_CUDA(cudaMemcpyAsync(d_slot + at, host_stage.data() + at, (size_t) n * sizeof(diag_gate),
+    // every chunk of 1024 gates goes through the SAME 1024-slot scratch region: the slots after it
+    // hold the in-sweep tables of later sweeps.  Reuse is safe in stream order (chunk k's kernel has
+    // read the region before chunk k+1's copy overwrites it).
+    for (size_t at = 0; at < host_stage.size(); at += kDiagScratchSlots) {
+        const int n = (int) std::min<size_t>(kDiagScratchSlots, host_stage.size() - at);
+        QCS_CUDA(cudaMemcpyAsync(d_slot, host_stage.data() + at, (size_t) n * sizeof(diag_gate),
                                  cudaMemcpyHostToDevice, reg->stream));
         const uint64_t n_pairs = reg->N_local >> 1;
         uint64_t grid = (n_pairs + kThreads - 1) / kThreads;
@@ -138,7 +142,7 @@ int launch_diag_list(qcs_register *reg, const std::vector<qcs_pending_gate> &que
         if (grid < 1) grid = 1;
         qcs_launch_begin(reg, QCS_K_DIAG, 32.0 * (double) reg->N_local);
         k_diag_multi<<<(unsigned) grid, kThreads, (size_t) n * sizeof(diag_gate), reg->stream>>>(
-            reg->amp, n_pairs, d_slot + at, n);
+            reg->amp, n_pairs, d_slot, n);
         QCS_TRY(qcs_launch_end(reg, QCS_K_DIAG, "k_diag_multi"));
     }
     return QCS_NO_ERROR;
@@ -278,15 +282,15 @@ int qcs_fuse_flush(qcs_register *reg)
     QCS_TRY(schedule_stream(reg, queue, passes, before_all));
 
     // ---- 4. launch
-    size_t need = 1024;
+    size_t need = kDiagScratchSlots;
     for (const pass &ps : passes) need += ps.in_sweep.size();
     QCS_TRY(ensure_diag_capacity(reg, need));
     diag_gate *d_all = (diag_gate *) reg->d_diag;
     // the array may still be read by the sweeps of the previous flush: reuse is stream-ordered
     // (the copies below are issued on the same stream as those sweeps)
     std::vector<diag_gate> stage;
-    diag_gate *d_scratch = d_all;       // first 1024 slots: standalone diagonal passes
-    size_t at = 1024;
+    diag_gate *d_scratch = d_all;       // first kDiagScratchSlots slots: standalone diagonal passes
+    size_t at = kDiagScratchSlots;
     {
         std::vector<diag_gate> all;
         for (const pass &ps : passes) all.insert(all.end(), ps.in_sweep.begin(), ps.in_sweep.end());

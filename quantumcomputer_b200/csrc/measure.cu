@@ -547,6 +547,10 @@ static int parallel_scan(qcs_register *reg, uint64_t first, double cum_in, doubl
 int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limit,
                        int *found, uint64_t *index, double *cum_out)
 {
+    // qc_shor.c:286-289: the sum only grows, so a running sum that already reaches r (r <= 0 on the
+    // first shard; gsl_rng_uniform can return exactly 0.0) stops at the first index whatever its
+    // amplitude -- the chunk classification below would skip all-zero chunks without that test
+    if (limit > 0 && cum_in >= r) return measure_scan_sequential(reg, cum_in, r, 1, found, index, cum_out);
     // small registers: the plain sequential scan is already fast
     if (limit < (1ull << 17) || reg->opt_measure_sequential)
         return measure_scan_sequential(reg, cum_in, r, limit, found, index, cum_out);
@@ -619,7 +623,11 @@ int qcs_k_sample_many(qcs_register *reg, uint64_t n_shots, const double *r, unsi
                 if (bnd[(size_t) mid + 1] >= r[k]) hi = mid; else lo = mid + 1;
             }
             if (lo == n_super) failed = 1;               // cannot happen: rank_end == bnd[n_super]
-            else {
+            else if (bnd[(size_t) lo] >= r[k]) {
+                // the running sum reaches r before the first addend (only lo == 0 with r <= the
+                // carried-in sum): the scan stops at its first index (qc_shor.c:289)
+                answer = (double) ((uint64_t) reg->rank * reg->N_local + lo * super_len);
+            } else {
                 const uint64_t first = lo * super_len;
                 const uint64_t len = limit - first < super_len ? limit - first : super_len;
                 double cum = 0.0;

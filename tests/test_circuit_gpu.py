@@ -134,3 +134,23 @@ def test_layered_circuit_round_trip_large(qcs):
             apply(reg, inverse)
         after = np.array([reg.get_state(i, 1)[0] for i in probe])
         assert np.linalg.norm(after - before) <= 1e-12 * math.sqrt(len(probe)) * np.max(np.abs(before)) * 100
+
+
+def test_more_than_1024_diagonal_gates_in_one_window(qcs, oracle_built):
+    """A standalone diagonal list longer than the 1024-slot scratch region must not overwrite the
+    in-sweep gate tables that later sweeps read (they live right behind the scratch slots)."""
+    n = 13
+    rng = np.random.default_rng(2025)
+    head = [("cp", int(rng.integers(n)), int(rng.integers(n)), float(rng.uniform(-3, 3))) for _ in range(2500)]
+    # a layer whose sweeps carry in-sweep diagonal gates, then another long diagonal run
+    tail = layered_circuit(n, 2)
+    tail += [("cp", int(rng.integers(n)), int(rng.integers(n)), float(rng.uniform(-3, 3))) for _ in range(1500)]
+    gates = head + tail
+    o, base = start_state(oracle_built, n, 41)
+    apply(o, gates)
+    want = o.get_state()
+    with qcs.Register(n, 0) as reg:
+        reg.set_state(base)
+        with reg.fused():
+            apply(reg, gates)
+        assert rel_l2(reg.get_state(), want) <= TOL

@@ -168,3 +168,22 @@ def test_live_reference_agrees_on_random_circuits(oracle_built):
         assert bits_equal(ref.get_state(), o.get_state()), trial
         r = float(rng.uniform())
         assert ref.measure_state_r(r) == o.measure_state(r)
+
+
+def test_all_cores_restatement_is_bit_identical(oracle_built):
+    """bench.py's all-cores CPU baseline is qcs_oracle.c built with -fopenmp (row loops split over
+    the threads): same bits as the one-thread build."""
+    import math
+    if not oracle_built.have_restatement_omp():
+        pytest.skip("no OpenMP build of the restatement on this host")
+    n = 11
+    a, b = oracle_built.Restatement(n, 0), oracle_built.RestatementAllCores(n, 0)
+    a.fill_synthetic(7)
+    a.scale(1.0 / math.sqrt(a.norm2()))
+    b.set_state(a.get_state())
+    for obj in (a, b):
+        obj.inverse_QFT()
+        obj.hadamard_gate(0)
+        obj.c_phase_shift_gate(3, 9, 0.37)
+    assert np.array_equal(a.get_state().view(np.float64), b.get_state().view(np.float64))
+    assert a.threads() == 1 and b.threads() >= 1
