@@ -96,7 +96,14 @@ enum {
      * already complete run on the other SMs: the NVLink exchange overlaps the HBM-bound local
      * work.  0 or 1: one after the other. */
     QCS_OPT_OVERLAP_SLICES = 10,
-    QCS_OPT_GLOBAL_SMS = 11
+    QCS_OPT_GLOBAL_SMS = 11,
+    /* 1 (default): the last strided sweep and the contiguous sweep of a fused transform run as ONE
+     * launch over blocks of <= QCS_OPT_L2_PAIR_MAX_BLOCK bytes (default 32 MiB) whose intermediate
+     * state stays in the 126 MB L2: the pair reads and writes HBM once.  The second sweep trails the
+     * first by one block plus QCS_OPT_L2_PAIR_LAG tiles (default 444 = 3 tiles per SM). */
+    QCS_OPT_L2_PAIR = 12,
+    QCS_OPT_L2_PAIR_LAG = 13,
+    QCS_OPT_L2_PAIR_MAX_BLOCK = 14
 };
 
 /* kernel classes reported by qcs_profile_get */
@@ -140,6 +147,17 @@ void qcs_register_destroy(qcs_register *reg);
 int qcs_comm_unique_id(void *id_out);
 int qcs_register_create_sharded(qcs_register **out, int L_size, int M_size, int device,
                                 int rank, int world_size, const void *comm_id);
+
+/* The same sharded register for ONE caller: the allocation block of main(), Q:1316-1324, for a
+ * state spread over n_gpus = 2^p devices of the box (devices 0 .. n_gpus-1), no launcher and no
+ * communicator id.  The handle is used exactly like a single-GPU register -- find_period's
+ * reset_register / quantum_computation / measure_state (Q:922-928) run sharded unchanged; every
+ * call is executed by one worker thread per GPU inside the library.  Bulk calls (qcs_get_state,
+ * qcs_set_state, qcs_nonzero_states) address the whole register; qcs_local_states == qcs_num_states,
+ * qcs_world_size == 1, qcs_num_gpus == n_gpus; profile counters are per GPU (shard 0's), the
+ * stopwatch is the maximum over the GPUs.  n_gpus == 1 is qcs_register_create on the current device. */
+int qcs_register_create_multi(qcs_register **out, int L_size, int M_size, int n_gpus);
+int qcs_num_gpus(const qcs_register *reg);
 
 int qcs_L_size(const qcs_register *reg);
 int qcs_M_size(const qcs_register *reg);

@@ -18,6 +18,7 @@ NO_ERROR, INSUFFICIENT_MEMORY, BAD_ARGUMENTS, PERIOD_NOT_FOUND, UNKNOWN_ERROR = 
 POW_VERBATIM, POW_MODULAR = 0, 1
 OPT_FUSION, OPT_PROFILE, OPT_TILE_BITS, OPT_MEASURE_SEQUENTIAL, OPT_PIPELINE, OPT_PREFETCH_TILES = 1, 2, 3, 4, 5, 6
 OPT_PIPE_SHAPE, OPT_MIN_RUN_BITS, OPT_GLOBAL_RUN_BITS, OPT_OVERLAP_SLICES, OPT_GLOBAL_SMS = 7, 8, 9, 10, 11
+OPT_L2_PAIR, OPT_L2_PAIR_LAG, OPT_L2_PAIR_MAX_BLOCK = 12, 13, 14
 KERNEL_CLASSES = ["hadamard", "cphase", "amodc", "fill", "reduce", "tile_sweep",
                   "modexp_sweep", "exchange", "scale", "dense_block", "diag_multi", "global_sweep", "gate_1q"]
 
@@ -136,10 +137,15 @@ class Register:
     """Device register: the replacement of the reference's ``Register`` struct
     (qc_shor.c:194-203) plus the operators that act on it."""
 
-    def __init__(self, L_size, M_size, device=-1, rank=0, world_size=1, comm_id=None):
+    def __init__(self, L_size, M_size, device=-1, rank=0, world_size=1, comm_id=None, n_gpus=1):
+        """world_size > 1: this process's shard of a sharded register (one process per GPU);
+        n_gpus > 1: the whole register sharded over the first n_gpus devices, driven from this
+        one process (qcs_register_create_multi)."""
         self._l = lib()
         self._h = C.c_void_p()
-        if world_size == 1:
+        if n_gpus > 1:
+            rc = self._l.qcs_register_create_multi(C.byref(self._h), L_size, M_size, n_gpus)
+        elif world_size == 1:
             rc = self._l.qcs_register_create(C.byref(self._h), L_size, M_size, device)
         else:
             rc = self._l.qcs_register_create_sharded(C.byref(self._h), L_size, M_size, device,
@@ -183,6 +189,10 @@ class Register:
     @property
     def local_states(self):
         return self._l.qcs_local_states(self._h)
+
+    @property
+    def num_gpus(self):
+        return self._l.qcs_num_gpus(self._h)
 
     @property
     def peer_memory(self):

@@ -23,6 +23,8 @@ SIGNATURES = [
     ("qcs_comm_unique_id", C.c_int, [_vp]),
     ("qcs_register_create_sharded", C.c_int,
      [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    ("qcs_register_create_multi", C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int]),
+    ("qcs_num_gpus", C.c_int, [_vp]),
     ("qcs_L_size", C.c_int, [_vp]),
     ("qcs_M_size", C.c_int, [_vp]),
     ("qcs_num_qubits", _u, [_vp]),

@@ -182,6 +182,7 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->p_global = p;
     reg->dist = nullptr;
     reg->peer = nullptr;
+    reg->group = nullptr;
     reg->amp_all = nullptr;
     reg->opt_fusion = 1;
     reg->opt_profile = 0;
@@ -195,6 +196,11 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->opt_global_sms = 48;
     reg->opt_prefetch_tiles = 0;     // measured: L2 prefetch slows the sweep down (profiles/README.md)
     reg->d_meas = nullptr;
+    reg->d_pair = nullptr;
+    reg->d_pair_cap = 0;
+    reg->opt_l2_pair = 1;
+    reg->opt_l2_pair_lag = 3 * 148;
+    reg->opt_l2_pair_max_block = 32ll << 20;
     reg->fusing = 0;
     reg->d_diag = nullptr;
     reg->d_diag_cap = 0;
@@ -268,6 +274,7 @@ extern "C" int qcs_register_create_sharded(qcs_register **out, int L_size, int M
 extern "C" void qcs_register_destroy(qcs_register *reg)
 {
     if (!reg) return;
+    if (reg->group) { qcs_group_destroy(reg); return; }
     cudaSetDevice(reg->device);
     if (reg->stream) cudaStreamSynchronize(reg->stream);
     // no collective here: a peer that still touches this shard does so through its own mapping of
@@ -282,6 +289,7 @@ extern "C" void qcs_register_destroy(qcs_register *reg)
     if (reg->d_partials) cudaFree(reg->d_partials);
     if (reg->d_small) cudaFree(reg->d_small);
     if (reg->d_meas) cudaFree(reg->d_meas);
+    if (reg->d_pair) cudaFree(reg->d_pair);
     if (reg->d_diag) cudaFree(reg->d_diag);
     if (reg->h_small) cudaFreeHost(reg->h_small);
     if (reg->stream) cudaStreamDestroy(reg->stream);
@@ -295,10 +303,15 @@ extern "C" unsigned long long qcs_num_states(const qcs_register *reg) { return r
 extern "C" unsigned long long qcs_local_states(const qcs_register *reg) { return reg ? reg->N_local : 0; }
 extern "C" int qcs_rank(const qcs_register *reg) { return reg ? reg->rank : -1; }
 extern "C" int qcs_world_size(const qcs_register *reg) { return reg ? reg->world : 0; }
-extern "C" int qcs_peer_memory(const qcs_register *reg) { return reg && reg->peer ? 1 : 0; }
+extern "C" int qcs_peer_memory(const qcs_register *reg)
+{
+    if (reg && reg->group) return qcs_peer_memory(qcs_group_member(reg, 0));
+    return reg && reg->peer ? 1 : 0;
+}
 
 extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
 {
+    QCS_GROUP_FORWARD(reg, qcs_set_option(m, option, value));
     QCS_ENTER(reg);      // recorded gates are launched under the options they were recorded with
     switch (option) {
         case QCS_OPT_FUSION: reg->opt_fusion = value != 0; return QCS_NO_ERROR;
@@ -336,6 +349,15 @@ extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
             if (value < 0 || value > 64) return QCS_BAD_ARGUMENTS;
             reg->opt_prefetch_tiles = (int) value;
             return QCS_NO_ERROR;
+        case QCS_OPT_L2_PAIR: reg->opt_l2_pair = value != 0; return QCS_NO_ERROR;
+        case QCS_OPT_L2_PAIR_LAG:
+            if (value < 0 || value > (1 << 20)) return QCS_BAD_ARGUMENTS;
+            reg->opt_l2_pair_lag = (int) value;
+            return QCS_NO_ERROR;
+        case QCS_OPT_L2_PAIR_MAX_BLOCK:
+            if (value < (1 << 20)) return QCS_BAD_ARGUMENTS;
+            reg->opt_l2_pair_max_block = value;
+            return QCS_NO_ERROR;
         default: return QCS_BAD_ARGUMENTS;
     }
 }
@@ -343,6 +365,7 @@ extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
 extern "C" long long qcs_get_option(const qcs_register *reg, int option)
 {
     if (!reg) return -1;
+    if (reg->group) return qcs_get_option(qcs_group_member(reg, 0), option);
     switch (option) {
         case QCS_OPT_FUSION: return reg->opt_fusion;
         case QCS_OPT_PROFILE: return reg->opt_profile;
@@ -355,12 +378,16 @@ extern "C" long long qcs_get_option(const qcs_register *reg, int option)
         case QCS_OPT_OVERLAP_SLICES: return reg->opt_overlap_slices;
         case QCS_OPT_GLOBAL_SMS: return reg->opt_global_sms;
         case QCS_OPT_PREFETCH_TILES: return reg->opt_prefetch_tiles;
+        case QCS_OPT_L2_PAIR: return reg->opt_l2_pair;
+        case QCS_OPT_L2_PAIR_LAG: return reg->opt_l2_pair_lag;
+        case QCS_OPT_L2_PAIR_MAX_BLOCK: return reg->opt_l2_pair_max_block;
         default: return -1;
     }
 }
 
 extern "C" int qcs_synchronize(qcs_register *reg)
 {
+    QCS_GROUP_FORWARD(reg, qcs_synchronize(m));
     QCS_ENTER(reg);
     QCS_CUDA(cudaStreamSynchronize(reg->stream));
     return QCS_NO_ERROR;
@@ -371,6 +398,7 @@ extern "C" int qcs_synchronize(qcs_register *reg)
 // ---------------------------------------------------------------------------
 extern "C" int qcs_reset_register(qcs_register *reg)
 {
+    QCS_GROUP_FORWARD(reg, qcs_reset_register(m));
     QCS_ENTER(reg);
     return qcs_k_reset(reg);
 }
@@ -385,6 +413,7 @@ static int hadamard_any(qcs_register *reg, unsigned q)
 
 extern "C" int qcs_hadamard_gate(qcs_register *reg, unsigned qubit_num)
 {
+    QCS_GROUP_FORWARD(reg, qcs_hadamard_gate(m, qubit_num));
     QCS_ENTER_GATE(reg);
     if (reg->fusing && reg->opt_fusion) {
         if (qubit_num >= reg->n) return QCS_BAD_ARGUMENTS;
@@ -411,6 +440,7 @@ static int cphase_any(qcs_register *reg, unsigned c, unsigned q, double co, doub
 
 extern "C" int qcs_c_phase_shift_gate(qcs_register *reg, unsigned c_qubit_num, unsigned qubit_num, double theta)
 {
+    QCS_GROUP_FORWARD(reg, qcs_c_phase_shift_gate(m, c_qubit_num, qubit_num, theta));
     QCS_ENTER_GATE(reg);
     // gsl_complex_polar(1.0, theta), qc_shor.c:526: host libm like the reference
     if (reg->fusing && reg->opt_fusion) {
@@ -440,6 +470,7 @@ static int amodc_any(qcs_register *reg, unsigned C, unsigned long long atox, uns
 
 extern "C" int qcs_c_amodc_gate(qcs_register *reg, unsigned C, unsigned long long atox, unsigned c_qubit_num)
 {
+    QCS_GROUP_FORWARD(reg, qcs_c_amodc_gate(m, C, atox, c_qubit_num));
     QCS_ENTER(reg);
     return amodc_any(reg, C, atox, c_qubit_num);
 }
@@ -500,30 +531,35 @@ static int qft_any(qcs_register *reg, unsigned lo, unsigned hi, bool inverse)
 
 extern "C" int qcs_inverse_QFT(qcs_register *reg)
 {
+    QCS_GROUP_FORWARD(reg, qcs_inverse_QFT(m));
     QCS_ENTER(reg);
     return qft_any(reg, (unsigned) reg->M_size, reg->n, true);
 }
 
 extern "C" int qcs_QFT(qcs_register *reg)
 {
+    QCS_GROUP_FORWARD(reg, qcs_QFT(m));
     QCS_ENTER(reg);
     return qft_any(reg, (unsigned) reg->M_size, reg->n, false);
 }
 
 extern "C" int qcs_inverse_QFT_range(qcs_register *reg, unsigned lo, unsigned hi)
 {
+    QCS_GROUP_FORWARD(reg, qcs_inverse_QFT_range(m, lo, hi));
     QCS_ENTER(reg);
     return qft_any(reg, lo, hi, true);
 }
 
 extern "C" int qcs_QFT_range(qcs_register *reg, unsigned lo, unsigned hi)
 {
+    QCS_GROUP_FORWARD(reg, qcs_QFT_range(m, lo, hi));
     QCS_ENTER(reg);
     return qft_any(reg, lo, hi, false);
 }
 
 extern "C" int qcs_quantum_computation(qcs_register *reg, unsigned C, unsigned a, int pow_mode)
 {
+    QCS_GROUP_FORWARD(reg, qcs_quantum_computation(m, C, a, pow_mode));
     QCS_ENTER(reg);
     if (C == 0 || (pow_mode != QCS_POW_VERBATIM && pow_mode != QCS_POW_MODULAR)) return QCS_BAD_ARGUMENTS;
     const unsigned first = reg->n - (unsigned) reg->L_size;          // qc_shor.c:720
@@ -552,6 +588,13 @@ extern "C" int qcs_quantum_computation(qcs_register *reg, unsigned C, unsigned a
 // ---------------------------------------------------------------------------
 extern "C" int qcs_norm2(qcs_register *reg, double *sum_of_sq)
 {
+    if (reg && reg->group) {
+        if (!sum_of_sq) return QCS_BAD_ARGUMENTS;
+        std::vector<double> v((size_t) qcs_group_world(reg), 0.0);
+        const int rc = qcs_group_run(reg, [&](qcs_register *m) { return qcs_norm2(m, &v[(size_t) m->rank]); });
+        *sum_of_sq = v[0];                        // the rank-ordered sum, identical on every shard
+        return rc;
+    }
     QCS_ENTER(reg);
     if (!sum_of_sq) return QCS_BAD_ARGUMENTS;
     double mine = 0.0;
@@ -577,22 +620,46 @@ static int locate_state(qcs_register *reg, double r, uint64_t *out_index)
         QCS_TRY(qcs_k_measure_scan(reg, 0.0, r, reg->N_local - 1, &found, &index, &cum));
         if (found) global_index = index;
     } else {
-        // the running sum is handed from rank to rank in index order
+        // Everything except the walk runs on all shards at once: chunk sums -> one all-gather of the
+        // shards' approximate totals (enough for the rigorous classification bounds) -> chunk and
+        // super-chunk maps.  Only the exact running sum is handed from shard to shard in index order,
+        // one packed all-gather {sum, found, index, error code} per shard.
+        const uint64_t limit = reg->rank == reg->world - 1 ? reg->N_local - 1 : reg->N_local;
+        const bool parallel = qcs_k_scan_parallel_ok(reg, limit);
+        std::vector<double> all((size_t) reg->world * 4);
+        int rc = QCS_NO_ERROR;
+        if (parallel) {
+            double mine = 0.0;
+            rc = qcs_k_scan_sums(reg, limit, &mine);
+            const double pack[2] = {mine, (double) rc};
+            QCS_TRY(qcs_dist_allgather_doubles(reg, pack, 2, all.data()));
+            double before = 0.0;
+            for (int s = 0; s < reg->world; s++) {
+                if (all[(size_t) s * 2 + 1] != 0.0) rc = (int) all[(size_t) s * 2 + 1];    // every shard returns the same error
+                if (s < reg->rank) before += all[(size_t) s * 2];
+            }
+            if (rc != QCS_NO_ERROR) return rc;
+            rc = qcs_k_scan_maps(reg, before, r, limit);
+        }
         for (int turn = 0; turn < reg->world; turn++) {
-            if (turn == reg->rank && !found) {
-                const uint64_t limit = reg->rank == reg->world - 1 ? reg->N_local - 1 : reg->N_local;
-                QCS_TRY(qcs_k_measure_scan(reg, cum, r, limit, &found, &index, &cum));
+            if (turn == reg->rank && rc == QCS_NO_ERROR && !found) {
+                int bad = 0;
+                if (parallel) rc = qcs_k_scan_walk(reg, cum, r, limit, &found, &index, &cum, &bad);
+                if (rc == QCS_NO_ERROR && (!parallel || bad)) {
+                    if (bad) fprintf(stderr, "qcs: measure_state: binade invariant failed, falling back to the sequential GPU scan\n");
+                    rc = qcs_k_measure_scan(reg, cum, r, limit, &found, &index, &cum);
+                }
                 if (found) global_index = (uint64_t) reg->rank * reg->N_local + index;
             }
-            // share (cum, found, index) of the rank whose turn it was
-            std::vector<double> all((size_t) reg->world);
-            QCS_TRY(qcs_dist_allgather_double(reg, cum, all.data()));
-            cum = all[(size_t) turn];
-            QCS_TRY(qcs_dist_allgather_double(reg, found ? 1.0 : 0.0, all.data()));
-            found = all[(size_t) turn] != 0.0;
-            // indices < 2^53 are exact in a double
-            QCS_TRY(qcs_dist_allgather_double(reg, (double) global_index, all.data()));
-            global_index = (uint64_t) all[(size_t) turn];
+            // {running sum, found, index (< 2^53: exact in a double), error code} of the shard whose turn it was
+            const double pack[4] = {cum, found ? 1.0 : 0.0, (double) global_index, (double) rc};
+            QCS_TRY(qcs_dist_allgather_doubles(reg, pack, 4, all.data()));
+            // an error on any shard ends the scan on all of them
+            for (int s = 0; s < reg->world; s++)
+                if (all[(size_t) s * 4 + 3] != 0.0) return (int) all[(size_t) s * 4 + 3];
+            cum = all[(size_t) turn * 4];
+            found = all[(size_t) turn * 4 + 1] != 0.0;
+            global_index = (uint64_t) all[(size_t) turn * 4 + 2];
             if (found) break;
         }
     }
@@ -602,6 +669,13 @@ static int locate_state(qcs_register *reg, double r, uint64_t *out_index)
 
 extern "C" int qcs_measure_state(qcs_register *reg, double r, unsigned long long *state_num)
 {
+    if (reg && reg->group) {
+        if (!state_num) return QCS_BAD_ARGUMENTS;
+        std::vector<unsigned long long> v((size_t) qcs_group_world(reg), 0ull);
+        const int rc = qcs_group_run(reg, [&](qcs_register *m) { return qcs_measure_state(m, r, &v[(size_t) m->rank]); });
+        *state_num = v[0];
+        return rc;
+    }
     QCS_ENTER(reg);
     if (!state_num) return QCS_BAD_ARGUMENTS;
     uint64_t global_index = 0;
@@ -620,6 +694,17 @@ extern "C" int qcs_measure_state(qcs_register *reg, double r, unsigned long long
 extern "C" int qcs_sample_states(qcs_register *reg, unsigned long long n_shots, const double *r,
                                  unsigned long long *state_nums)
 {
+    if (reg && reg->group) {
+        if (n_shots && (!r || !state_nums)) return QCS_BAD_ARGUMENTS;
+        // every shard fills a complete copy of the answer; the caller gets shard 0's
+        std::vector<std::vector<unsigned long long>> v((size_t) qcs_group_world(reg));
+        const int rc = qcs_group_run(reg, [&](qcs_register *m) {
+            v[(size_t) m->rank].assign((size_t) n_shots, 0ull);
+            return qcs_sample_states(m, n_shots, r, v[(size_t) m->rank].data());
+        });
+        for (unsigned long long k = 0; k < n_shots; k++) state_nums[k] = v[0][(size_t) k];
+        return rc;
+    }
     QCS_ENTER(reg);
     if (n_shots && (!r || !state_nums)) return QCS_BAD_ARGUMENTS;
     bool handled = false;
@@ -636,6 +721,15 @@ extern "C" int qcs_sample_states(qcs_register *reg, unsigned long long n_shots, 
 extern "C" int qcs_get_state(qcs_register *reg, unsigned long long first, unsigned long long count,
                              double *interleaved_out)
 {
+    if (reg && reg->group) {
+        if (first > reg->N || count > reg->N - first || (!interleaved_out && count)) return QCS_BAD_ARGUMENTS;
+        return qcs_group_run(reg, [&](qcs_register *m) -> int {
+            const unsigned long long lo = (unsigned long long) m->rank * m->N_local, hi = lo + m->N_local;
+            const unsigned long long a = first > lo ? first : lo, b = first + count < hi ? first + count : hi;
+            if (a >= b) return QCS_NO_ERROR;
+            return qcs_get_state(m, a - lo, b - a, interleaved_out + 2 * (a - first));
+        });
+    }
     QCS_ENTER(reg);
     if (first > reg->N_local || count > reg->N_local - first || (!interleaved_out && count)) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaMemcpyAsync(interleaved_out, reg->amp + first, count * sizeof(double2),
@@ -647,6 +741,15 @@ extern "C" int qcs_get_state(qcs_register *reg, unsigned long long first, unsign
 extern "C" int qcs_set_state(qcs_register *reg, unsigned long long first, unsigned long long count,
                              const double *interleaved_in)
 {
+    if (reg && reg->group) {
+        if (first > reg->N || count > reg->N - first || (!interleaved_in && count)) return QCS_BAD_ARGUMENTS;
+        return qcs_group_run(reg, [&](qcs_register *m) -> int {
+            const unsigned long long lo = (unsigned long long) m->rank * m->N_local, hi = lo + m->N_local;
+            const unsigned long long a = first > lo ? first : lo, b = first + count < hi ? first + count : hi;
+            if (a >= b) return QCS_NO_ERROR;
+            return qcs_set_state(m, a - lo, b - a, interleaved_in + 2 * (a - first));
+        });
+    }
     QCS_ENTER(reg);
     if (first > reg->N_local || count > reg->N_local - first || (!interleaved_in && count)) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaMemcpyAsync(reg->amp + first, interleaved_in, count * sizeof(double2),
@@ -661,6 +764,15 @@ extern "C" int qcs_set_state(qcs_register *reg, unsigned long long first, unsign
 extern "C" int qcs_set_state_async(qcs_register *reg, unsigned long long first, unsigned long long count,
                                    const double *interleaved_in)
 {
+    if (reg && reg->group) {
+        if (first > reg->N || count > reg->N - first || (!interleaved_in && count)) return QCS_BAD_ARGUMENTS;
+        return qcs_group_run(reg, [&](qcs_register *m) -> int {
+            const unsigned long long lo = (unsigned long long) m->rank * m->N_local, hi = lo + m->N_local;
+            const unsigned long long a = first > lo ? first : lo, b = first + count < hi ? first + count : hi;
+            if (a >= b) return QCS_NO_ERROR;
+            return qcs_set_state_async(m, a - lo, b - a, interleaved_in + 2 * (a - first));
+        });
+    }
     QCS_ENTER(reg);
     if (first > reg->N_local || count > reg->N_local - first || (!interleaved_in && count)) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaMemcpyAsync(reg->amp + first, interleaved_in, count * sizeof(double2),
@@ -672,6 +784,30 @@ extern "C" int qcs_nonzero_states(qcs_register *reg, unsigned long long capacity
                                   unsigned long long *indices, double *abs_values,
                                   unsigned long long *count)
 {
+    if (reg && reg->group) {
+        if (!count) return QCS_BAD_ARGUMENTS;
+        const int world = qcs_group_world(reg);
+        std::vector<std::vector<unsigned long long>> idx((size_t) world);
+        std::vector<std::vector<double>> mag((size_t) world);
+        std::vector<unsigned long long> cnt((size_t) world, 0ull);
+        const int rc = qcs_group_run(reg, [&](qcs_register *m) {
+            idx[(size_t) m->rank].assign((size_t) capacity, 0ull);
+            mag[(size_t) m->rank].assign((size_t) capacity, 0.0);
+            return qcs_nonzero_states(m, capacity, idx[(size_t) m->rank].data(), mag[(size_t) m->rank].data(),
+                                      &cnt[(size_t) m->rank]);
+        });
+        unsigned long long total = 0;
+        for (int r = 0; r < world; r++) {
+            const unsigned long long have = cnt[(size_t) r] < capacity ? cnt[(size_t) r] : capacity;
+            for (unsigned long long i = 0; i < have && total + i < capacity; i++) {
+                if (indices) indices[total + i] = idx[(size_t) r][(size_t) i];
+                if (abs_values) abs_values[total + i] = mag[(size_t) r][(size_t) i];
+            }
+            total += cnt[(size_t) r];
+        }
+        *count = total;
+        return rc;
+    }
     QCS_ENTER(reg);
     if (!count) return QCS_BAD_ARGUMENTS;
     // display_state, testing_and_debug.c:7-26: a console listing, so the
@@ -702,12 +838,14 @@ extern "C" int qcs_nonzero_states(qcs_register *reg, unsigned long long capacity
 
 extern "C" int qcs_fill_synthetic(qcs_register *reg, unsigned long long seed)
 {
+    QCS_GROUP_FORWARD(reg, qcs_fill_synthetic(m, seed));
     QCS_ENTER(reg);
     return qcs_k_fill_synthetic(reg, seed);
 }
 
 extern "C" int qcs_scale(qcs_register *reg, double factor)
 {
+    QCS_GROUP_FORWARD(reg, qcs_scale(m, factor));
     QCS_ENTER(reg);
     return qcs_k_scale(reg, factor);
 }
@@ -717,6 +855,7 @@ extern "C" int qcs_scale(qcs_register *reg, double factor)
 // ---------------------------------------------------------------------------
 extern "C" int qcs_timer_start(qcs_register *reg)
 {
+    QCS_GROUP_FORWARD(reg, qcs_timer_start(m));
     QCS_ENTER(reg);
     QCS_CUDA(cudaEventRecord(reg->timer_begin, reg->stream));
     return QCS_NO_ERROR;
@@ -724,6 +863,14 @@ extern "C" int qcs_timer_start(qcs_register *reg)
 
 extern "C" int qcs_timer_stop(qcs_register *reg, double *milliseconds)
 {
+    if (reg && reg->group) {
+        if (!milliseconds) return QCS_BAD_ARGUMENTS;
+        std::vector<double> v((size_t) qcs_group_world(reg), 0.0);
+        const int rc = qcs_group_run(reg, [&](qcs_register *m) { return qcs_timer_stop(m, &v[(size_t) m->rank]); });
+        *milliseconds = 0.0;
+        for (double x : v) *milliseconds = x > *milliseconds ? x : *milliseconds;     // max over the GPUs
+        return rc;
+    }
     QCS_ENTER(reg);
     if (!milliseconds) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaEventRecord(reg->timer_end, reg->stream));
@@ -734,10 +881,15 @@ extern "C" int qcs_timer_stop(qcs_register *reg, double *milliseconds)
     return QCS_NO_ERROR;
 }
 
-extern "C" unsigned long long qcs_launch_count(const qcs_register *reg) { return reg ? reg->launches_total : 0; }
+extern "C" unsigned long long qcs_launch_count(const qcs_register *reg)
+{
+    if (reg && reg->group) return qcs_launch_count(qcs_group_member(reg, 0));     // per GPU
+    return reg ? reg->launches_total : 0;
+}
 
 extern "C" int qcs_profile_reset(qcs_register *reg)
 {
+    QCS_GROUP_FORWARD(reg, qcs_profile_reset(m));
     QCS_ENTER(reg);
     QCS_TRY(qcs_profile_resolve(reg));
     reg->launches_total = 0;
@@ -750,6 +902,17 @@ extern "C" int qcs_profile_reset(qcs_register *reg)
 extern "C" int qcs_profile_get(qcs_register *reg, int k, unsigned long long *launches, double *milliseconds,
                                double *algorithmic_bytes)
 {
+    if (reg && reg->group) {                     // per GPU: shard 0's counters
+        std::vector<unsigned long long> l((size_t) qcs_group_world(reg), 0ull);
+        std::vector<double> t((size_t) qcs_group_world(reg), 0.0), b((size_t) qcs_group_world(reg), 0.0);
+        const int rc = qcs_group_run(reg, [&](qcs_register *m) {
+            return qcs_profile_get(m, k, &l[(size_t) m->rank], &t[(size_t) m->rank], &b[(size_t) m->rank]);
+        });
+        if (launches) *launches = l[0];
+        if (milliseconds) *milliseconds = t[0];
+        if (algorithmic_bytes) *algorithmic_bytes = b[0];
+        return rc;
+    }
     QCS_ENTER(reg);
     if (k < 0 || k >= QCS_K_COUNT) return QCS_BAD_ARGUMENTS;
     QCS_TRY(qcs_profile_resolve(reg));

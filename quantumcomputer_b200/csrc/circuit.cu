@@ -381,6 +381,7 @@ extern "C" int qcs_schedule_describe(unsigned n_qubits, int world_size, int rank
 
 extern "C" int qcs_fuse_begin(qcs_register *reg)
 {
+    QCS_GROUP_FORWARD(reg, qcs_fuse_begin(m));
     if (!reg) return QCS_BAD_ARGUMENTS;
     if (reg->fusing) return QCS_BAD_ARGUMENTS;
     reg->fusing = 1;
@@ -389,6 +390,7 @@ extern "C" int qcs_fuse_begin(qcs_register *reg)
 
 extern "C" int qcs_fuse_end(qcs_register *reg)
 {
+    QCS_GROUP_FORWARD(reg, qcs_fuse_end(m));
     if (!reg) return QCS_BAD_ARGUMENTS;
     if (!reg->fusing) return QCS_BAD_ARGUMENTS;
     reg->fusing = 0;
@@ -398,5 +400,6 @@ extern "C" int qcs_fuse_end(qcs_register *reg)
 
 extern "C" unsigned long long qcs_fuse_pending(const qcs_register *reg)
 {
+    if (reg && reg->group) return qcs_fuse_pending(qcs_group_member(reg, 0));
     return reg ? (unsigned long long) reg->queue.size() : 0ull;
 }

@@ -85,6 +85,7 @@ k_dense_block(double *__restrict__ amp, uint64_t n_groups, const double *__restr
 
 extern "C" int qcs_apply_dense_block(qcs_register *reg, unsigned k, const double *u_interleaved)
 {
+    QCS_GROUP_FORWARD(reg, qcs_apply_dense_block(m, k, u_interleaved));
     if (!reg || !u_interleaved) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaSetDevice(reg->device));
     QCS_TRY(qcs_fuse_flush(reg));

@@ -113,6 +113,8 @@ k_gate_global_combine(double2 *__restrict__ mine, const double2 *__restrict__ th
 
 }  // namespace
 
+constexpr int kGatherMax = 4;      // doubles per rank in one small all-gather
+
 struct qcs_dist {
     ncclComm_t comm = nullptr;
     cudaStream_t comm_stream = nullptr;
@@ -121,7 +123,7 @@ struct qcs_dist {
     cudaEvent_t recv_done[2] = {nullptr, nullptr};
     cudaEvent_t buf_free[2] = {nullptr, nullptr};
     cudaEvent_t ready = nullptr;
-    double *d_gather = nullptr;     // world doubles
+    double *d_gather = nullptr;     // (world + 1) * kGatherMax doubles: receive area + send slot
     // global<->local exchange slices: kSlices buffers of world * 2^slice_bits amplitudes
     double2 *slice[3] = {nullptr, nullptr, nullptr};
     unsigned slice_bits = 0;
@@ -160,9 +162,9 @@ int qcs_dist_init(qcs_register *reg, const void *comm_id)
         QCS_CUDA(cudaEventCreateWithFlags(&d->buf_free[b], cudaEventDisableTiming));
     }
     QCS_CUDA(cudaEventCreateWithFlags(&d->ready, cudaEventDisableTiming));
-    QCS_CUDA(cudaMalloc((void **) &d->d_gather, (size_t) (reg->world + 1) * sizeof(double)));
-    QCS_CUDA(cudaMemset(d->d_gather, 0, (size_t) (reg->world + 1) * sizeof(double)));
-    QCS_CUDA(cudaHostAlloc((void **) &d->h_gather, (size_t) (reg->world + 1) * sizeof(double), cudaHostAllocDefault));
+    QCS_CUDA(cudaMalloc((void **) &d->d_gather, (size_t) (reg->world + 1) * kGatherMax * sizeof(double)));
+    QCS_CUDA(cudaMemset(d->d_gather, 0, (size_t) (reg->world + 1) * kGatherMax * sizeof(double)));
+    QCS_CUDA(cudaHostAlloc((void **) &d->h_gather, (size_t) (reg->world + 1) * kGatherMax * sizeof(double), cudaHostAllocDefault));
     return QCS_NO_ERROR;
 }
 
@@ -193,19 +195,26 @@ void qcs_dist_destroy(qcs_register *reg)
     reg->dist = nullptr;
 }
 
-int qcs_dist_allgather_double(qcs_register *reg, double mine, double *all_host)
+// every rank contributes `count` <= kGatherMax doubles; all_host[r * count + i] = rank r's i-th
+int qcs_dist_allgather_doubles(qcs_register *reg, const double *mine, int count, double *all_host)
 {
     qcs_dist *d = reg->dist;
-    if (!d) return QCS_BAD_ARGUMENTS;
-    d->h_gather[reg->world] = mine;
-    QCS_CUDA(cudaMemcpyAsync(d->d_gather + reg->world, d->h_gather + reg->world, sizeof(double),
+    if (!d || count < 1 || count > kGatherMax) return QCS_BAD_ARGUMENTS;
+    const size_t w = (size_t) reg->world * kGatherMax;                    // send slot behind the receive area
+    for (int i = 0; i < count; i++) d->h_gather[w + (size_t) i] = mine[i];
+    QCS_CUDA(cudaMemcpyAsync(d->d_gather + w, d->h_gather + w, (size_t) count * sizeof(double),
                              cudaMemcpyHostToDevice, reg->stream));
-    QCS_NCCL(g_nccl.AllGather(d->d_gather + reg->world, d->d_gather, 1, ncclDouble, d->comm, reg->stream));
-    QCS_CUDA(cudaMemcpyAsync(d->h_gather, d->d_gather, (size_t) reg->world * sizeof(double),
+    QCS_NCCL(g_nccl.AllGather(d->d_gather + w, d->d_gather, (size_t) count, ncclDouble, d->comm, reg->stream));
+    QCS_CUDA(cudaMemcpyAsync(d->h_gather, d->d_gather, (size_t) reg->world * (size_t) count * sizeof(double),
                              cudaMemcpyDeviceToHost, reg->stream));
     QCS_CUDA(cudaStreamSynchronize(reg->stream));
-    memcpy(all_host, d->h_gather, (size_t) reg->world * sizeof(double));
+    memcpy(all_host, d->h_gather, (size_t) reg->world * (size_t) count * sizeof(double));
     return QCS_NO_ERROR;
+}
+
+int qcs_dist_allgather_double(qcs_register *reg, double mine, double *all_host)
+{
+    return qcs_dist_allgather_doubles(reg, &mine, 1, all_host);
 }
 
 int qcs_dist_barrier(qcs_register *reg)

@@ -120,6 +120,7 @@ int qcs_k_gate_1q(qcs_register *reg, unsigned q, int c, const double *u_interlea
 
 extern "C" int qcs_apply_gate(qcs_register *reg, unsigned qubit_num, const double *u_interleaved)
 {
+    QCS_GROUP_FORWARD(reg, qcs_apply_gate(m, qubit_num, u_interleaved));
     if (!reg) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaSetDevice(reg->device));
     QCS_TRY(qcs_fuse_flush(reg));
@@ -129,6 +130,7 @@ extern "C" int qcs_apply_gate(qcs_register *reg, unsigned qubit_num, const doubl
 extern "C" int qcs_apply_controlled_gate(qcs_register *reg, unsigned c_qubit_num, unsigned qubit_num,
                                          const double *u_interleaved)
 {
+    QCS_GROUP_FORWARD(reg, qcs_apply_controlled_gate(m, c_qubit_num, qubit_num, u_interleaved));
     if (!reg) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaSetDevice(reg->device));
     QCS_TRY(qcs_fuse_flush(reg));

@@ -480,59 +480,93 @@ static int measure_scan_sequential(qcs_register *reg, double cum_in, double r, u
     return QCS_NO_ERROR;
 }
 
-// chunk / super-chunk summaries of amp[first .. first + limit) for the variate r (pass a huge r
-// for variate-independent summaries), then the exact walk.  bnd != nullptr: record the running sum
-// at the super-chunk boundaries instead of searching for r.
-static int parallel_scan(qcs_register *reg, uint64_t first, double cum_in, double r, uint64_t limit,
-                         int *found, uint64_t *index, double *cum_out, double *d_bnd, int *bad)
+// scratch of the parallel scan (lazily allocated, sized for the whole shard)
+struct scan_buffers {
+    pair64 *maps, *super_maps;
+    double *csum;
+    int *code, *super_code;
+};
+
+static int scan_scratch(qcs_register *reg, scan_buffers &b)
 {
-    const double2 *amp = reg->amp + first;
-    const uint64_t n_chunks = (limit + kChunk - 1) >> kChunkBits;
-    const uint64_t n_super = (n_chunks + kSuper - 1) >> kSuperBits;
+    const uint64_t cap_chunks = (reg->N_local + kChunk - 1) >> kChunkBits;
+    const uint64_t cap_super = (cap_chunks + kSuper - 1) >> kSuperBits;
     if (!reg->d_meas) {
-        const uint64_t cap_chunks = (reg->N_local + kChunk - 1) >> kChunkBits;
-        const uint64_t cap_super = (cap_chunks + kSuper - 1) >> kSuperBits;
         const size_t bytes = cap_chunks * (sizeof(double) + sizeof(int) + sizeof(pair64)) +
                              cap_super * (sizeof(int) + sizeof(pair64)) + 64;
         QCS_CUDA(cudaMalloc(&reg->d_meas, bytes));
     }
-    const uint64_t cap_chunks = (reg->N_local + kChunk - 1) >> kChunkBits;
-    const uint64_t cap_super = (cap_chunks + kSuper - 1) >> kSuperBits;
     unsigned char *at = (unsigned char *) reg->d_meas;
-    pair64 *maps = (pair64 *) at;            at += cap_chunks * sizeof(pair64);
-    pair64 *super_maps = (pair64 *) at;      at += cap_super * sizeof(pair64);
-    double *csum = (double *) at;            at += cap_chunks * sizeof(double);
-    int *code = (int *) at;                  at += cap_chunks * sizeof(int);
-    int *super_code = (int *) at;
+    b.maps = (pair64 *) at;            at += cap_chunks * sizeof(pair64);
+    b.super_maps = (pair64 *) at;      at += cap_super * sizeof(pair64);
+    b.csum = (double *) at;            at += cap_chunks * sizeof(double);
+    b.code = (int *) at;               at += cap_chunks * sizeof(int);
+    b.super_code = (int *) at;
+    return QCS_NO_ERROR;
+}
 
-    // rigorous relative margin: |sequential - exact| <= (N-1) u and the same for
-    // the tree sums, u = 2^-53; 2^(n+3-53) covers both with slack
-    const double delta = ldexp(1.0, (int) reg->n + 3 - 53);
+static unsigned scan_grid(const qcs_register *reg, uint64_t n_chunks)
+{
     uint64_t grid = n_chunks;
     const uint64_t cap = (uint64_t) reg->sm_count * 8;
     if (grid > cap) grid = cap;
+    return (unsigned) (grid < 1 ? 1 : grid);
+}
 
+// pass 1: per-chunk approximate sums of amp[first .. first + limit)
+static int scan_sums(qcs_register *reg, uint64_t first, uint64_t limit)
+{
+    scan_buffers b;
+    QCS_TRY(scan_scratch(reg, b));
+    const uint64_t n_chunks = (limit + kChunk - 1) >> kChunkBits;
     qcs_launch_begin(reg, QCS_K_REDUCE, 16.0 * (double) limit);
-    k_chunk_sums<<<(unsigned) grid, 256, 0, reg->stream>>>(amp, limit, n_chunks, csum);
-    QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_chunk_sums"));
+    k_chunk_sums<<<scan_grid(reg, n_chunks), 256, 0, reg->stream>>>(reg->amp + first, limit, n_chunks, b.csum);
+    return qcs_launch_end(reg, QCS_K_REDUCE, "k_chunk_sums");
+}
+
+// passes 2 and 3: classification against r given the (approximate) running sum before `first`, then
+// the (de, do) maps of the clean chunks and uniform super-chunks
+static int scan_maps(qcs_register *reg, uint64_t first, double approx_cum_in, double r, uint64_t limit)
+{
+    scan_buffers b;
+    QCS_TRY(scan_scratch(reg, b));
+    const double2 *amp = reg->amp + first;
+    const uint64_t n_chunks = (limit + kChunk - 1) >> kChunkBits;
+    const uint64_t n_super = (n_chunks + kSuper - 1) >> kSuperBits;
+    // rigorous relative margin: |sequential - exact| <= (N-1) u and the same for
+    // the tree sums, u = 2^-53; 2^(n+3-53) covers both with slack (n: ALL qubits of the register,
+    // so the margin also covers an approximate running sum handed over from the shards before)
+    const double delta = ldexp(1.0, (int) reg->n + 3 - 53);
     qcs_launch_begin(reg, QCS_K_REDUCE, 12.0 * (double) n_chunks);
-    k_classify<<<1, 1024, 0, reg->stream>>>(csum, n_chunks, cum_in, r, delta, code, super_code);
+    k_classify<<<1, 1024, 0, reg->stream>>>(b.csum, n_chunks, approx_cum_in, r, delta, b.code, b.super_code);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_classify"));
     qcs_launch_begin(reg, QCS_K_REDUCE, 16.0 * (double) limit * (r < 1.0 ? (r > 0.0 ? r : 0.0) : 1.0));
-    k_chunk_maps<<<(unsigned) grid, 128, 0, reg->stream>>>(amp, limit, n_chunks, code, maps);
+    k_chunk_maps<<<scan_grid(reg, n_chunks), 128, 0, reg->stream>>>(amp, limit, n_chunks, b.code, b.maps);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_chunk_maps"));
     qcs_launch_begin(reg, QCS_K_REDUCE, 20.0 * (double) n_chunks);
-    k_super_maps<<<(unsigned) ((n_super + 255) / 256), 256, 0, reg->stream>>>(n_chunks, n_super, code, super_code,
-                                                                              maps, super_maps);
-    QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_super_maps"));
+    k_super_maps<<<(unsigned) ((n_super + 255) / 256), 256, 0, reg->stream>>>(n_chunks, n_super, b.code, b.super_code,
+                                                                              b.maps, b.super_maps);
+    return qcs_launch_end(reg, QCS_K_REDUCE, "k_super_maps");
+}
+
+// pass 4: the exact walk from the exact running sum before `first`.  d_bnd != nullptr: record the
+// running sum at the super-chunk boundaries instead of searching for r.
+static int scan_walk(qcs_register *reg, uint64_t first, double cum_in, double r, uint64_t limit,
+                     int *found, uint64_t *index, double *cum_out, double *d_bnd, int *bad)
+{
+    scan_buffers b;
+    QCS_TRY(scan_scratch(reg, b));
+    const double2 *amp = reg->amp + first;
+    const uint64_t n_chunks = (limit + kChunk - 1) >> kChunkBits;
+    const uint64_t n_super = (n_chunks + kSuper - 1) >> kSuperBits;
     walk_result *d_res = (walk_result *) reg->d_small;
     qcs_launch_begin(reg, QCS_K_REDUCE, 20.0 * (double) n_super);
     if (d_bnd)
-        k_exact_walk<true><<<1, 1024, 0, reg->stream>>>(amp, limit, n_chunks, cum_in, r, code, super_code, maps,
-                                                        super_maps, d_res, d_bnd);
+        k_exact_walk<true><<<1, 1024, 0, reg->stream>>>(amp, limit, n_chunks, cum_in, r, b.code, b.super_code, b.maps,
+                                                        b.super_maps, d_res, d_bnd);
     else
-        k_exact_walk<false><<<1, 1024, 0, reg->stream>>>(amp, limit, n_chunks, cum_in, r, code, super_code, maps,
-                                                         super_maps, d_res, nullptr);
+        k_exact_walk<false><<<1, 1024, 0, reg->stream>>>(amp, limit, n_chunks, cum_in, r, b.code, b.super_code, b.maps,
+                                                         b.super_maps, d_res, nullptr);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_exact_walk"));
     QCS_CUDA(cudaMemcpyAsync(reg->h_small, d_res, sizeof(walk_result), cudaMemcpyDeviceToHost, reg->stream));
     QCS_CUDA(cudaStreamSynchronize(reg->stream));
@@ -542,6 +576,54 @@ static int parallel_scan(qcs_register *reg, uint64_t first, double cum_in, doubl
     *index = first + h->index;
     *cum_out = h->cum;
     return QCS_NO_ERROR;
+}
+
+// chunk / super-chunk summaries of amp[first .. first + limit) for the variate r (pass a huge r
+// for variate-independent summaries), then the exact walk
+static int parallel_scan(qcs_register *reg, uint64_t first, double cum_in, double r, uint64_t limit,
+                         int *found, uint64_t *index, double *cum_out, double *d_bnd, int *bad)
+{
+    QCS_TRY(scan_sums(reg, first, limit));
+    QCS_TRY(scan_maps(reg, first, cum_in, r, limit));
+    return scan_walk(reg, first, cum_in, r, limit, found, index, cum_out, d_bnd, bad);
+}
+
+// ---- the three parts on their own (sharded registers: api.cu runs parts 1 and 2 on all shards at once)
+bool qcs_k_scan_parallel_ok(const qcs_register *reg, uint64_t limit)
+{
+    return limit >= (1ull << 17) && !reg->opt_measure_sequential;
+}
+
+int qcs_k_scan_sums(qcs_register *reg, uint64_t limit, double *approx_total)
+{
+    QCS_TRY(scan_sums(reg, 0, limit));
+    scan_buffers b;
+    QCS_TRY(scan_scratch(reg, b));
+    const uint64_t n_chunks = (limit + kChunk - 1) >> kChunkBits;
+    if (n_chunks > 0xffffffffull) return QCS_BAD_ARGUMENTS;
+    qcs_launch_begin(reg, QCS_K_REDUCE, 8.0 * (double) n_chunks);
+    k_sum_partials<<<1, 1024, 0, reg->stream>>>(b.csum, (unsigned) n_chunks, (double *) reg->d_small);
+    QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_sum_partials"));
+    QCS_CUDA(cudaMemcpyAsync(reg->h_small, reg->d_small, sizeof(double), cudaMemcpyDeviceToHost, reg->stream));
+    QCS_CUDA(cudaStreamSynchronize(reg->stream));
+    *approx_total = *(double *) reg->h_small;
+    return QCS_NO_ERROR;
+}
+
+int qcs_k_scan_maps(qcs_register *reg, double approx_cum_in, double r, uint64_t limit)
+{
+    return scan_maps(reg, 0, approx_cum_in, r, limit);
+}
+
+int qcs_k_scan_walk(qcs_register *reg, double cum_in, double r, uint64_t limit, int *found, uint64_t *index,
+                    double *cum_out, int *bad)
+{
+    // qc_shor.c:286-289: a running sum that already reaches r stops at the first index
+    if (limit > 0 && cum_in >= r) {
+        *bad = 0;
+        return measure_scan_sequential(reg, cum_in, r, 1, found, index, cum_out);
+    }
+    return scan_walk(reg, 0, cum_in, r, limit, found, index, cum_out, nullptr, bad);
 }
 
 int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limit,
@@ -584,11 +666,28 @@ int qcs_k_sample_many(qcs_register *reg, uint64_t n_shots, const double *r, unsi
     int found = 0, bad = 0, rc = QCS_NO_ERROR;
     uint64_t index = 0;
     double total = 0.0, carry = 0.0;
-    // sharded: the running sum is handed from rank to rank in index order, once
-    for (int turn = 0; turn < reg->world && rc == QCS_NO_ERROR; turn++) {
+    // sharded: chunk sums and maps on all shards at once (an all-gather of the approximate totals gives
+    // every shard the running sum before it, to the accuracy the classification bounds need); only the
+    // walk that records the exact boundary sums is handed from rank to rank in index order, once
+    if (reg->world > 1) {
         double mine = 0.0;
-        if (turn == reg->rank) {
-            rc = parallel_scan(reg, 0, carry, 1e300, limit, &found, &index, &total, d_bnd, &bad);
+        rc = qcs_k_scan_sums(reg, limit, &mine);
+        std::vector<double> all((size_t) reg->world * 2);
+        const double pack[2] = {mine, (double) rc};
+        const int rc2 = qcs_dist_allgather_doubles(reg, pack, 2, all.data());
+        if (rc == QCS_NO_ERROR) rc = rc2;
+        double before = 0.0;
+        for (int s = 0; s < reg->world && rc == QCS_NO_ERROR; s++) {
+            if (all[(size_t) s * 2 + 1] != 0.0) rc = (int) all[(size_t) s * 2 + 1];
+            if (s < reg->rank) before += all[(size_t) s * 2];
+        }
+        if (rc == QCS_NO_ERROR) rc = scan_maps(reg, 0, before, 1e300, limit);
+    }
+    for (int turn = 0; turn < reg->world; turn++) {
+        double mine = 0.0;
+        if (turn == reg->rank && rc == QCS_NO_ERROR) {
+            rc = reg->world > 1 ? scan_walk(reg, 0, carry, 1e300, limit, &found, &index, &total, d_bnd, &bad)
+                                : parallel_scan(reg, 0, carry, 1e300, limit, &found, &index, &total, d_bnd, &bad);
             if (rc == QCS_NO_ERROR && !bad &&
                 (cudaMemcpyAsync(bnd.data(), d_bnd, bnd.size() * sizeof(double), cudaMemcpyDeviceToHost, reg->stream) != cudaSuccess ||
                  cudaStreamSynchronize(reg->stream) != cudaSuccess))
@@ -596,11 +695,16 @@ int qcs_k_sample_many(qcs_register *reg, uint64_t n_shots, const double *r, unsi
             mine = bad ? -1.0 : total;                   // a negative sum tells every rank to give up
         }
         if (reg->world > 1) {
-            std::vector<double> all((size_t) reg->world);
-            const int rc2 = qcs_dist_allgather_double(reg, rc == QCS_NO_ERROR ? mine : -1.0, all.data());
+            // an error on any shard is seen by all of them in the same all-gather
+            std::vector<double> all((size_t) reg->world * 2);
+            const double pack[2] = {rc == QCS_NO_ERROR ? mine : -1.0, (double) rc};
+            const int rc2 = qcs_dist_allgather_doubles(reg, pack, 2, all.data());
             if (rc == QCS_NO_ERROR) rc = rc2;
-            mine = all[(size_t) turn];
+            for (int s = 0; s < reg->world && rc == QCS_NO_ERROR; s++)
+                if (all[(size_t) s * 2 + 1] != 0.0) rc = (int) all[(size_t) s * 2 + 1];
+            mine = all[(size_t) turn * 2];
         }
+        if (rc != QCS_NO_ERROR) break;
         rank_end[(size_t) turn] = mine;
         carry = mine;
         if (mine < 0.0) bad = 1;

@@ -6,6 +6,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <functional>
 #include <stdint.h>
 #include <stdio.h>
 #include <vector>
@@ -13,6 +14,7 @@
 #include "../../include/qcs.h"
 
 struct qcs_dist;   // multi-GPU state (dist.cu)
+struct qcs_group;  // single-caller facade over the shards of all GPUs of the box (group.cu)
 struct qcs_peer;   // stitched peer-memory mapping of all shards (peer.cu)
 
 struct qcs_profile_slot {
@@ -44,6 +46,8 @@ struct qcs_register {
     void *d_small;          // 4 KiB device scratch (measurement result etc.)
     void *h_small;          // 4 KiB pinned host mirror
     void *d_meas;           // chunk summaries of the exact parallel measurement scan (lazy)
+    void *d_pair;           // ticket + per-block counters of an L2-paired sweep launch (lazy)
+    size_t d_pair_cap;      // bytes
 
     // options
     int opt_fusion;
@@ -58,6 +62,10 @@ struct qcs_register {
     int opt_global_run_bits;      // log2 of the contiguous run of the sweep over the global qubits (peer memory)
     int opt_min_run_bits;         // log2 of the shortest contiguous run (amplitudes) a strided tile may use
     int opt_measure_sequential;   // 1: always use the single-CTA sequential scan
+    int opt_l2_pair;              // 1: the last strided sweep and the contiguous sweep of a transform share one launch
+                                  // whose intermediate state stays in L2 (qft_pipeline.cu)
+    int opt_l2_pair_lag;          // tiles the second sweep of a pair trails the first by, beyond one block
+    long long opt_l2_pair_max_block;   // largest block (bytes) a paired launch may use
 
     // deferred gate stream (qcs_fuse_begin .. qcs_fuse_end)
     int fusing;
@@ -85,7 +93,25 @@ struct qcs_register {
     // amp == amp_all + rank * N_local
     qcs_peer *peer;
     double2 *amp_all;
+
+    // non-null: this handle is the facade of qcs_register_create_multi; it owns no device memory,
+    // every call is forwarded to the per-device shard registers (group.cu)
+    qcs_group *group;
 };
+
+// ---- single-caller multi-GPU facade: group.cu -------------------------------
+// run `job` on every shard register of the facade at once (one worker thread per device);
+// returns the first non-zero code in rank order
+int qcs_group_run(qcs_register *facade, const std::function<int(qcs_register *)> &job);
+int qcs_group_world(const qcs_register *facade);
+qcs_register *qcs_group_member(const qcs_register *facade, int rank);
+void qcs_group_destroy(qcs_register *facade);
+// first line of every entry point that works shard by shard
+#define QCS_GROUP_FORWARD(reg, call)                                                              \
+    do {                                                                                          \
+        if ((reg) && (reg)->group)                                                                \
+            return qcs_group_run((reg), [&](qcs_register *m) -> int { return (call); });          \
+    } while (0)
 
 // ---- error plumbing -------------------------------------------------------
 int qcs_map_cuda_error(cudaError_t e, const char *what, const char *file, int line);
@@ -132,6 +158,16 @@ int qcs_k_norm2_local(qcs_register *reg, double *out_host);
 // as in measure_state (qc_shor.c:283-292) restricted to [0, limit)
 int qcs_k_measure_scan(qcs_register *reg, double cum_in, double r, uint64_t limit,
                        int *found, uint64_t *index, double *cum_out);
+// the same scan in three parts, so that the shards of a sharded register can do everything except
+// the walk at the same time: (1) chunk sums and their total (approximate, for bounds only),
+// (2) classification + chunk / super-chunk maps given an APPROXIMATE running sum before the shard,
+// (3) the exact walk from the EXACT running sum before the shard.  *bad: an invariant failed, the
+// caller falls back to qcs_k_measure_scan.  false from qcs_k_scan_parallel_ok: use the plain scan.
+bool qcs_k_scan_parallel_ok(const qcs_register *reg, uint64_t limit);
+int qcs_k_scan_sums(qcs_register *reg, uint64_t limit, double *approx_total);
+int qcs_k_scan_maps(qcs_register *reg, double approx_cum_in, double r, uint64_t limit);
+int qcs_k_scan_walk(qcs_register *reg, double cum_in, double r, uint64_t limit, int *found, uint64_t *index,
+                    double *cum_out, int *bad);
 
 // many variates against one state; *handled = false: not applicable, use one scan per variate
 int qcs_k_sample_many(qcs_register *reg, uint64_t n_shots, const double *r, unsigned long long *indices, bool *handled);
@@ -165,6 +201,8 @@ int qcs_dist_gate_global(qcs_register *reg, unsigned q, int c, const double *u);
 // one sweep, exchange back, pipelined over slices of the shard
 int qcs_dist_top_stages(qcs_register *reg, unsigned lo, bool inverse, bool hadamard_only);
 int qcs_dist_allgather_double(qcs_register *reg, double mine, double *all_host);
+// `count` <= 4 doubles per rank: all_host[r * count + i]
+int qcs_dist_allgather_doubles(qcs_register *reg, const double *mine, int count, double *all_host);
 int qcs_dist_barrier(qcs_register *reg);
 // cross-rank barrier ordered on the register's stream (no host synchronisation): work queued
 // after it on any rank starts only when the work queued before it has finished on every rank

@@ -20,7 +20,8 @@ struct sweep_step {
     int r;          // number of stages in the step (radix 2^r)
     int j;          // stage index of the step's top bit (physical bit - lo)
     int low_phys;   // physical position of the step's lowest bit
-    int col_off;    // offset of the step's column-twiddle table (in double2)
+    int col_off;    // offset of the step's column-twiddle table (in double2; 2^s entries: the twiddle
+                    // depends on the tile-local bits below the step only)
     int notw;       // 1: no register bit lies below the step (y == 0): the external twiddle is 1
 };
 
@@ -35,7 +36,7 @@ struct sweep_desc {
     int a, g_lo, g_hi, t;   // tile = physical bits [0,a) U [g_lo,g_hi); t = a + g_hi - g_lo
     int lo;                 // lowest qubit of the transform (the reference's M_size)
     int n_steps;
-    int sw;                 // swizzle: phys(e) = e ^ ((e >> sw) & 7)
+    int sw;                 // swizzle: phys(e) = e ^ ((e >> sw) & 7); kSwizzleSplit3: the layout of tile_phys below
     int inverse;            // 1: inverse_QFT of the reference, 0: its adjoint
     int wcol_total;         // total column-twiddle entries
     int hadamard_only;      // 1: the stages are bare Hadamards (no phase gates): Walsh-Hadamard sweep
@@ -167,6 +168,20 @@ __device__ __forceinline__ void st256(double2 *p, double2 lo, double2 hi)
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(lo.x), "d"(lo.y), "d"(hi.x), "d"(hi.y) : "memory");
 }
 
+// Shared-memory position (in amplitudes) of tile-local element e.
+//   sw < kSwizzleSplit3 : e ^ ((e >> sw) & 7)  (sw = 28: linear)
+//   sw = kSwizzleSplit3 + t : contiguous 2^t tile brought in by TMA as a 3-D box {8 amplitudes} x
+//        {e >> 4} x {bit 3 of e} with the 128-byte hardware swizzle: bit 3 moves to the top of the
+//        tile address and the 16-byte chunk is XORed with bits 4..6 of e -- every radix-16 step of a
+//        2^12 tile, including the one on bits 0..3, then touches 8 distinct bank groups per quarter warp.
+constexpr int kSwizzleSplit3 = 64;
+__host__ __device__ __forceinline__ unsigned tile_phys(unsigned e, int sw)
+{
+    if (sw < kSwizzleSplit3) return e ^ ((e >> sw) & 7u);
+    const int t = sw - kSwizzleSplit3;
+    return ((e & 8u) << (t - 4)) | ((e >> 4) << 3) | ((e & 7u) ^ ((e >> 4) & 7u));
+}
+
 struct tile_geom {
     int a, g_lo, sw;
     __device__ __forceinline__ uint64_t spread(unsigned e) const
@@ -174,7 +189,7 @@ struct tile_geom {
         return (uint64_t) (e & ((1u << a) - 1u)) | ((uint64_t) (e >> a) << g_lo);
     }
     __device__ __forceinline__ int phys(int s) const { return s < a ? s : g_lo + (s - a); }
-    __device__ __forceinline__ unsigned swz(unsigned e) const { return e ^ ((e >> sw) & 7u); }
+    __device__ __forceinline__ unsigned swz(unsigned e) const { return tile_phys(e, sw); }
 };
 
 template <int R, bool INV, bool TW>
@@ -209,7 +224,7 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
                 if (INV) dif_inverse<R, true>(x);
                 else dit_forward<R, true>(x);
             } else {
-                const double2 w = cmul(wb, wcol[c]);
+                const double2 w = cmul(wb, wcol[c & low_mask]);      // the table is indexed by the tile bits below the step
                 if (INV) {
                     dif_inverse<R, true>(x);
                     external_twiddle<R>(x, w);
@@ -323,7 +338,7 @@ inline long conflict_cost(const sweep_desc &d, int sw, bool all_steps)
                 for (unsigned ln = 0; ln < lanes; ln++) {
                     const unsigned c = c0 + ln;
                     const unsigned e = (((c >> S.s) << (S.s + S.r)) | (c & ((1u << S.s) - 1u))) + ((unsigned) dd << S.s);
-                    const unsigned ph = e ^ ((e >> sw) & 7u);
+                    const unsigned ph = tile_phys(e, sw);
                     worst = std::max(worst, ++seen[ph & 7u]);
                 }
                 cost += (worst - 1) * ((reads ? 1 : 0) + (writes ? 1 : 0));
@@ -412,7 +427,7 @@ inline void plan_inverse(unsigned n_local, unsigned lo, unsigned hi, int T, int 
             S.j = (l - 1) - (int) lo;
             S.notw = S.low_phys <= (int) lo ? 1 : 0;
             S.col_off = off;
-            off += 1 << (d.t - S.r);
+            off += S.notw ? 0 : (1 << S.s);
             l -= S.r;
         }
         d.wcol_total = off;
@@ -439,8 +454,9 @@ inline void make_forward(std::vector<sweep_plan> &plans)
         int off = 0;
         for (int k = 0; k < p.d.n_steps; k++) {
             p.d.step[k].col_off = off;
-            off += 1 << (p.d.t - p.d.step[k].r);
+            off += p.d.step[k].notw ? 0 : (1 << p.d.step[k].s);
         }
+        p.d.wcol_total = off;
         p.d.sw = choose_swizzle(p.d);
     }
 }

@@ -59,11 +59,10 @@ k_qft_sweep(double2 *__restrict__ amp, uint64_t n_tiles, const sweep_desc P)
     // per-column part of the external twiddle: fixed for the whole kernel
     for (int k = 0; k < (P.hadamard_only ? 0 : P.n_steps); k++) {
         const sweep_step S = P.step[k];
-        const unsigned n_cols = 1u << (P.t - S.r);
-        for (unsigned c = threadIdx.x; c < n_cols; c += NT) {
-            const unsigned e_base = ((c >> S.s) << (S.s + S.r)) | (c & ((1u << S.s) - 1u));
-            uint64_t y = 0;
-            if (S.low_phys > P.lo) y = (G.spread(e_base) & ((1ull << S.low_phys) - 1ull)) >> P.lo;
+        if (S.notw) continue;
+        // one entry per value of the tile-local bits below the step (e_base = c for c < 2^s)
+        for (unsigned c = threadIdx.x; c < (1u << S.s); c += NT) {
+            const uint64_t y = (G.spread(c) & ((1ull << S.low_phys) - 1ull)) >> P.lo;
             wcol[S.col_off + c] = unit_phase(y, S.j, inv);
         }
     }
@@ -115,6 +114,9 @@ int launch_sweep(qcs_register *reg, const sweep_target &tg, const sweep_plan &p,
 int qcs_pipeline_tile_bits(const qcs_register *reg);
 bool qcs_pipeline_supports(const qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &p);
 int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &plan);
+bool qcs_pipeline_pair_supported(const qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &a,
+                                 const qft::sweep_plan &b);
+int qcs_pipeline_launch_pair(qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &a, const qft::sweep_plan &b);
 
 static int launch_plan_inner(qcs_register *reg, const sweep_target &tg, const sweep_plan &p);
 
@@ -142,6 +144,23 @@ static int launch_plan_inner(qcs_register *reg, const sweep_target &tg, const sw
     return launch_sweep<128, 4>(reg, tg, p, smem);
 }
 
+// a list of consecutive sweeps on one target: neighbours that can share an L2-paired launch do
+static int launch_plans(qcs_register *reg, const sweep_target &tg, const std::vector<sweep_plan> &plans)
+{
+    for (size_t k = 0; k < plans.size(); k++) {
+        if (k + 1 < plans.size() && reg->opt_pipeline && qcs_pipeline_pair_supported(reg, tg, plans[k], plans[k + 1])) {
+            reg->launch_stream = tg.stream;
+            const int rc = qcs_pipeline_launch_pair(reg, tg, plans[k], plans[k + 1]);
+            reg->launch_stream = nullptr;
+            QCS_TRY(rc);
+            k++;
+            continue;
+        }
+        QCS_TRY(launch_plan(reg, tg, plans[k]));
+    }
+    return QCS_NO_ERROR;
+}
+
 static int run_sweeps(qcs_register *reg, unsigned lo, unsigned hi, bool inverse, bool hadamard_only)
 {
     if (hi > reg->n_local) {
@@ -155,9 +174,9 @@ static int run_sweeps(qcs_register *reg, unsigned lo, unsigned hi, bool inverse,
     const sweep_target tg = {reg->amp, reg->n_local, reg->stream};
     for (sweep_plan &p : plans) {
         p.d.hadamard_only = hadamard_only ? 1 : 0;
-        QCS_TRY(launch_plan(reg, tg, p));
+        if (hadamard_only) p.d.wcol_total = 0;
     }
-    return QCS_NO_ERROR;
+    return launch_plans(reg, tg, plans);
 }
 
 int qcs_plan_hadamard_sweeps(const qcs_register *reg, unsigned lo, unsigned hi, std::vector<sweep_plan> &plans)
@@ -209,7 +228,7 @@ int qcs_fused_top_sweep(qcs_register *reg, double2 *buf, unsigned c, unsigned p,
     d.step[0].j = (int) (reg->n - 1) - (int) lo;
     d.step[0].col_off = 0;
     d.step[0].notw = 0;
-    d.wcol_total = 1 << (d.t - (int) p);
+    d.wcol_total = 1 << d.a;
     d.sw = 28;
     pl.n_tiles = 1ull << (nb - (unsigned) T);
     pl.stages = (int) p;

@@ -36,18 +36,40 @@ namespace {
 
 using namespace qft;
 
-// pipeline shapes (template parameters of the kernel): log2 tile size, ring depth,
-// consumer groups and threads per group
-struct pipe_params {
+// One sweep of a launch: its descriptor and how its tiles map to TMA boxes.
+struct phase_params {
     sweep_desc d;
-    uint64_t n_tiles;
     int lo_gap;             // g_lo - a (strided) or -1 (contiguous final sweep)
-    int prefetch;           // tiles ahead of the load that are prefetched into L2 (0: off)
     int n_boxes;            // TMA boxes per tile (a box has at most 256 rows)
     int box_rows;
     uint32_t box_bytes;
-    unsigned long long *timing;   // -DQCS_PIPE_TIMING builds only: per-CTA cycle counters
+    int wcol_base;          // where this phase's column-twiddle tables start in the kernel's table area
 };
+
+// A launch runs one sweep (tiles dealt round robin over the CTAs) or an L2-PAIRED couple of
+// sweeps A -> B: A is a strided sweep whose stage bits end at bit `blk`, B the contiguous final
+// sweep, so every block of 2^blk consecutive amplitudes is closed under both.  The tiles of both
+// sweeps are handed out through one ticket queue in the order
+//     A[0 .. lag),  then alternating  A[lag + i], B[i],  then the last B's,
+// (lag >= one block of tiles) so that B trails A by a little more than one block: what A wrote is
+// still in the 126 MB L2 when B reads it, and A's lines are overwritten by B's before they are ever
+// evicted -- the intermediate state never travels to HBM.  A B tile may only be loaded when every A
+// tile of its block has been stored: a counter per block, incremented by the store warp once its
+// bulk store has completed, polled by the producer.  A waiting tile depends only on tiles with
+// smaller tickets, which are held by running CTAs: no deadlock whatever the residency.
+struct pipe_params {
+    phase_params ph[2];
+    int n_phases;
+    uint64_t n_tiles;               // tiles per phase
+    int blk_tile_bits;              // pair: log2(tiles per block)
+    uint64_t lag;                   // pair: B trails A by this many tiles
+    unsigned long long *ticket;     // pair: the queue head
+    unsigned *done;                 // pair: stored A tiles per block
+    unsigned long long *timing;     // -DQCS_PIPE_TIMING builds only: per-CTA cycle counters
+};
+
+constexpr uint64_t kNoItem = ~0ull;
+constexpr uint64_t kPhaseB = 1ull << 62;
 
 // Role timing (where do the producer, the store issuer and the consumer groups spend their
 // cycles) is compiled in only with -DQCS_PIPE_TIMING and switched on by the environment
@@ -104,11 +126,6 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2)
 {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
@@ -119,24 +136,48 @@ __device__ __forceinline__ void group_barrier(int group, int threads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(threads) : "memory");
 }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 template <int TB>
-__device__ __forceinline__ void tile_coords(const pipe_params &P, uint64_t tix, int &c0, int &c1, int &c2)
+__device__ __forceinline__ void tile_coords(const phase_params &Q, uint64_t tix, int &c0, int &c1, int &c2)
 {
-    if (P.lo_gap >= 0) {
-        c0 = (int) ((tix & ((1ull << P.lo_gap) - 1ull)) << (P.d.a + 1));   // doubles
+    if (Q.lo_gap >= 0) {
+        c0 = (int) ((tix & ((1ull << Q.lo_gap) - 1ull)) << (Q.d.a + 1));   // doubles
         c1 = 0;
-        c2 = (int) (tix >> P.lo_gap);
+        c2 = (int) (tix >> Q.lo_gap);
     } else {
         c0 = 0;
-        c1 = (int) (tix << (TB - 3));                                       // rows of 8 amplitudes
+        c1 = (int) (tix << (Q.d.sw >= kSwizzleSplit3 ? TB - 4 : TB - 3));   // rows of 8 amplitudes (split view: pairs of rows)
         c2 = 0;
     }
 }
 
+// first amplitude of tile tix
+template <int TB>
+__device__ __forceinline__ uint64_t tile_base(const phase_params &Q, uint64_t tix)
+{
+    return Q.lo_gap >= 0 ? (((tix >> Q.lo_gap) << Q.d.g_hi) | ((tix & ((1ull << Q.lo_gap) - 1ull)) << Q.d.a)) : (tix << TB);
+}
+
+// the t-th ticket of a paired launch -> phase bit | tile index within the phase
+__device__ __forceinline__ uint64_t pair_item(const pipe_params &P, uint64_t t)
+{
+    const uint64_t na = P.n_tiles, lag = P.lag;
+    if (t >= 2 * na) return kNoItem;
+    if (t < lag) return t;
+    const uint64_t v = t - lag, pairs = na - lag;
+    if (v < 2 * pairs) return (v & 1ull) ? (kPhaseB | (v >> 1)) : (lag + (v >> 1));
+    return kPhaseB | (pairs + (v - 2 * pairs));
+}
+
 template <int TB, int STAGES, int GROUPS, int GT>
 __global__ void __launch_bounds__(64 + GROUPS * GT, 1)
-k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
+k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, const pipe_params P)
 {
     static_assert(STAGES % GROUPS == 0, "a ring stage must always be consumed by the same group");
     constexpr int kThreads = 64 + GROUPS * GT;
@@ -145,17 +186,15 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
     // STAGES tiles; the 128-byte swizzle of the final sweep needs 1024-byte alignment
     double2 *stage_buf = (double2 *) (smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     double2 *wcol = stage_buf + (size_t) STAGES * (1u << TB);
-    double2 *wbase = wcol + P.d.wcol_total;                                 // [GROUPS][kMaxSteps]
-    uint64_t *bars = (uint64_t *) (wbase + GROUPS * kMaxSteps);
+    const int wcol_all = P.ph[0].d.wcol_total + (P.n_phases > 1 ? P.ph[1].d.wcol_total : 0);
+    double2 *wbase = wcol + wcol_all;                                       // [STAGES][kMaxSteps]: per-tile twiddle bases
+    uint64_t *bars = (uint64_t *) (wbase + STAGES * kMaxSteps);
     uint64_t *full = bars, *computed = bars + STAGES, *empty = bars + 2 * STAGES;
-    diag_gate *sdiag = (diag_gate *) (bars + 3 * STAGES);
+    uint64_t *s_item = bars + 3 * STAGES;                                   // [STAGES]: what the stage holds
+    diag_gate *sdiag = (diag_gate *) (s_item + STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    tile_geom G;
-    G.a = P.d.a;
-    G.g_lo = P.d.g_lo;
-    G.sw = P.d.sw;
-    const bool inv = P.d.inverse != 0;
+    const bool paired = P.n_phases > 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -164,72 +203,127 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
             mbar_init(&empty[s], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap0) : "memory");
+        if (paired) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap1) : "memory");
     }
-    // per-column part of the external twiddle: fixed for the whole kernel
-    if (!P.d.hadamard_only) {
-        for (int k = 0; k < P.d.n_steps; k++) {
-            const sweep_step S = P.d.step[k];
-            const unsigned n_cols = 1u << (TB - S.r);
-            for (unsigned c = threadIdx.x; c < n_cols; c += kThreads) {
-                const unsigned e_base = ((c >> S.s) << (S.s + S.r)) | (c & ((1u << S.s) - 1u));
-                uint64_t y = 0;
-                if (S.low_phys > P.d.lo) y = (G.spread(e_base) & ((1ull << S.low_phys) - 1ull)) >> P.d.lo;
-                wcol[S.col_off + c] = unit_phase(y, S.j, inv);
+    // per-column part of the external twiddle: fixed for the whole kernel; one entry per value of
+    // the tile-local bits below the step
+    for (int ph = 0; ph < P.n_phases; ph++) {
+        const phase_params &Q = P.ph[ph];
+        if (Q.d.hadamard_only) continue;
+        tile_geom G;
+        G.a = Q.d.a;
+        G.g_lo = Q.d.g_lo;
+        G.sw = Q.d.sw;
+        for (int k = 0; k < Q.d.n_steps; k++) {
+            const sweep_step S = Q.d.step[k];
+            if (S.notw) continue;
+            for (unsigned c = threadIdx.x; c < (1u << S.s); c += kThreads) {
+                const uint64_t y = (G.spread(c) & ((1ull << S.low_phys) - 1ull)) >> Q.d.lo;
+                wcol[Q.wcol_base + S.col_off + c] = unit_phase(y, S.j, Q.d.inverse != 0);
             }
         }
     }
-    for (int i = threadIdx.x; i < P.d.n_diag; i += kThreads) sdiag[i] = P.d.diag[i];
+    for (int i = threadIdx.x; i < P.ph[0].d.n_diag; i += kThreads) sdiag[i] = P.ph[0].d.diag[i];
     __syncthreads();
 
-    // this CTA's tiles: tix = blockIdx.x + k * gridDim.x, k = 0 .. my_tiles-1
-    const uint64_t my_tiles = P.n_tiles > blockIdx.x ? (P.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
     if (warp == 0) {
-        // ---------------- producer ----------------
-        if (lane == 0) {
-            int c0, c1, c2;
-            // optional L2 prefetch a few tiles ahead of the shared-memory ring
-            for (uint64_t k = 0; k < (uint64_t) P.prefetch && k < my_tiles; k++) {
-                tile_coords<TB>(P, tile_number(P.d, blockIdx.x + k * gridDim.x), c0, c1, c2);
-                for (int b = 0; b < P.n_boxes; b++) tma_prefetch_3d(&tmap, c0, c1 + b * P.box_rows, c2);
-            }
-            for (uint64_t k = 0; k < my_tiles; k++) {
-                const int s = (int) (k % STAGES);
-                const uint32_t round = (uint32_t) (k / STAGES);
-                if (P.prefetch && k + P.prefetch < my_tiles) {
-                    tile_coords<TB>(P, tile_number(P.d, blockIdx.x + (k + P.prefetch) * gridDim.x), c0, c1, c2);
-                    for (int b = 0; b < P.n_boxes; b++) tma_prefetch_3d(&tmap, c0, c1 + b * P.box_rows, c2);
-                }
+        // ---------------- producer: the whole warp walks the items; lane 0 owns barriers and TMA,
+        // lanes < n_steps compute the tile's twiddle bases ----------------
+        uint64_t next = kNoItem;
+        if (paired && lane == 0) next = pair_item(P, atomicAdd(P.ticket, 1ull));
+        int sentinels = 0;
+        for (uint64_t k = 0;; k++) {
+            const int s = (int) (k % STAGES);
+            const uint32_t round = (uint32_t) (k / STAGES);
+            uint64_t item = kNoItem;
+            if (lane == 0) {
                 const long long t0 = QCS_TICK(P);
                 mbar_wait(&empty[s], (round & 1u) ^ 1u);
                 QCS_TIMING_ADD(P, 0, QCS_TICK(P) - t0);
-                tile_coords<TB>(P, tile_number(P.d, blockIdx.x + k * gridDim.x), c0, c1, c2);
+                if (paired) {
+                    item = next;
+                } else {
+                    const uint64_t idx = blockIdx.x + k * gridDim.x;
+                    item = idx < P.n_tiles ? idx : kNoItem;
+                }
+            }
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item == kNoItem) {
+                // every group finds one sentinel at its next turn and leaves
+                if (lane == 0) {
+                    s_item[s] = kNoItem;
+                    mbar_arrive(&full[s]);
+                }
+                if (++sentinels == GROUPS) break;
+                continue;
+            }
+            const int ph = (item & kPhaseB) ? 1 : 0;
+            const phase_params &Q = P.ph[ph];
+            const uint64_t tix = tile_number(Q.d, item & (kPhaseB - 1ull));
+            if (!Q.d.hadamard_only && lane < Q.d.n_steps) {
+                const sweep_step S = Q.d.step[lane];
+                const uint64_t base = tile_base<TB>(Q, tix);
+                uint64_t y = 0;
+                if (S.low_phys > Q.d.lo) y = (base & ((1ull << S.low_phys) - 1ull)) >> Q.d.lo;
+                wbase[s * kMaxSteps + lane] = unit_phase(y + Q.d.y_const, S.j, Q.d.inverse != 0);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                s_item[s] = item;
+                if (ph == 1) {
+                    // all A tiles of the block must be in L2 / memory
+                    const unsigned *flag = P.done + ((item & (kPhaseB - 1ull)) >> P.blk_tile_bits);
+                    const unsigned need = 1u << P.blk_tile_bits;
+                    const long long tw = QCS_TICK(P);
+                    while (ld_acquire_gpu(flag) < need) __nanosleep(200);
+                    QCS_TIMING_ADD(P, 10, QCS_TICK(P) - tw);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                int c0, c1, c2;
+                tile_coords<TB>(Q, tix, c0, c1, c2);
                 mbar_expect_tx(&full[s], kTileBytes);
                 unsigned char *dst = (unsigned char *) (stage_buf + (size_t) s * (1u << TB));
-                for (int b = 0; b < P.n_boxes; b++)
-                    tma_load_3d(dst + (size_t) b * P.box_bytes, &tmap, &full[s], c0, c1 + b * P.box_rows, c2);
+                const CUtensorMap *map = ph ? &tmap1 : &tmap0;
+                for (int b = 0; b < Q.n_boxes; b++)
+                    tma_load_3d(dst + (size_t) b * Q.box_bytes, map, &full[s], c0, c1 + b * Q.box_rows, c2);
+                // the next ticket travels while this tile loads
+                if (paired) next = pair_item(P, atomicAdd(P.ticket, 1ull));
             }
         }
     } else if (warp == 1) {
         // ---------------- store issuer ----------------
         if (lane == 0) {
-            for (uint64_t k = 0; k < my_tiles; k++) {
+            for (uint64_t k = 0;; k++) {
                 const int s = (int) (k % STAGES);
                 const uint32_t round = (uint32_t) (k / STAGES);
                 const long long t0 = QCS_TICK(P);
                 mbar_wait(&computed[s], round & 1u);
                 const long long t1 = QCS_TICK(P);
+                const uint64_t item = s_item[s];
+                if (item == kNoItem) break;
+                const int ph = (item & kPhaseB) ? 1 : 0;
+                const phase_params &Q = P.ph[ph];
+                const uint64_t idx = item & (kPhaseB - 1ull);
                 int c0, c1, c2;
-                tile_coords<TB>(P, tile_number(P.d, blockIdx.x + k * gridDim.x), c0, c1, c2);
+                tile_coords<TB>(Q, tile_number(Q.d, idx), c0, c1, c2);
                 const unsigned char *src = (const unsigned char *) (stage_buf + (size_t) s * (1u << TB));
-                for (int b = 0; b < P.n_boxes; b++)
-                    tma_store_3d(&tmap, src + (size_t) b * P.box_bytes, c0, c1 + b * P.box_rows, c2);
+                const CUtensorMap *map = ph ? &tmap1 : &tmap0;
+                for (int b = 0; b < Q.n_boxes; b++)
+                    tma_store_3d(map, src + (size_t) b * Q.box_bytes, c0, c1 + b * Q.box_rows, c2);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 QCS_TIMING_ADD(P, 1, t1 - t0);               // waiting for a computed tile
                 QCS_TIMING_ADD(P, 2, QCS_TICK(P) - t1);      // the store reading shared memory
                 mbar_arrive(&empty[s]);
+                if (paired && ph == 0) {
+                    // publish the tile to the B tiles of its block as soon as it has been written.  (Not
+                    // deferred to the next store: the next tile of this CTA may be a B tile waiting for it.)
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __threadfence();
+                    atomicAdd(P.done + (idx >> P.blk_tile_bits), 1u);
+                }
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
@@ -237,42 +331,47 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap, const pipe_params P)
         // ---------------- consumers ----------------
         const int group = (warp - 2) / (GT / 32);
         const unsigned tig = threadIdx.x - 64 - group * GT;
-        double2 *my_wbase = wbase + group * kMaxSteps;
-        const int lo_gap = P.lo_gap;
-        for (uint64_t k = group; k < my_tiles; k += GROUPS) {
+        uint64_t n_done = 0;
+        for (uint64_t k = group;; k += GROUPS) {
             const int s = (int) (k % STAGES);
             const uint32_t round = (uint32_t) (k / STAGES);
-            const uint64_t tix = tile_number(P.d, blockIdx.x + k * gridDim.x);
-            const uint64_t base = lo_gap >= 0 ? (((tix >> lo_gap) << P.d.g_hi) | ((tix & ((1ull << lo_gap) - 1ull)) << P.d.a))
-                                              : (tix << TB);
-            if (!P.d.hadamard_only && tig < (unsigned) P.d.n_steps) {
-                const sweep_step S = P.d.step[tig];
-                uint64_t y = 0;
-                if (S.low_phys > P.d.lo) y = (base & ((1ull << S.low_phys) - 1ull)) >> P.d.lo;
-                my_wbase[tig] = unit_phase(y + P.d.y_const, S.j, inv);
-            }
-            group_barrier(group, GT);
             double2 *tile = stage_buf + (size_t) s * (1u << TB);
             const long long t0 = QCS_TICK(P);
             mbar_wait(&full[s], round & 1u);
             const long long t1 = QCS_TICK(P);
-            for (int st = 0; st < P.d.n_steps; st++) {
-                const sweep_step S = P.d.step[st];
-                const bool last = st == P.d.n_steps - 1;
-                const double2 wb = my_wbase[st];
-                if (P.d.hadamard_only) dispatch_step<true, false>(nullptr, tile, wcol + S.col_off, wb, G, S, TB, base, false, false, last, P.d.scale, tig, GT, sdiag, P.d.n_diag, P.d.index_or);
-                else if (inv) dispatch_step<true>(nullptr, tile, wcol + S.col_off, wb, G, S, TB, base, false, false, last, P.d.scale, tig, GT);
-                else dispatch_step<false>(nullptr, tile, wcol + S.col_off, wb, G, S, TB, base, false, false, last, P.d.scale, tig, GT);
+            const uint64_t item = s_item[s];
+            if (item == kNoItem) {
+                if (tig == 0) mbar_arrive(&computed[s]);     // lets the store issuer see the sentinel
+                break;
+            }
+            const int ph = (item & kPhaseB) ? 1 : 0;
+            const phase_params &Q = P.ph[ph];
+            const uint64_t tix = tile_number(Q.d, item & (kPhaseB - 1ull));
+            const uint64_t base = tile_base<TB>(Q, tix);
+            tile_geom G;
+            G.a = Q.d.a;
+            G.g_lo = Q.d.g_lo;
+            G.sw = Q.d.sw;
+            const bool inv = Q.d.inverse != 0;
+            const double2 *my_wcol = wcol + Q.wcol_base;
+            for (int st = 0; st < Q.d.n_steps; st++) {
+                const sweep_step S = Q.d.step[st];
+                const bool last = st == Q.d.n_steps - 1;
+                const double2 wb = wbase[s * kMaxSteps + st];
+                if (Q.d.hadamard_only) dispatch_step<true, false>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT, sdiag, Q.d.n_diag, Q.d.index_or);
+                else if (inv) dispatch_step<true>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT);
+                else dispatch_step<false>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT);
                 if (last) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
                 group_barrier(group, GT);
             }
+            n_done++;
             if (tig == 0) {
                 mbar_arrive(&computed[s]);
                 QCS_TIMING_ADD(P, 4 + 2 * group, t1 - t0);              // waiting for the load
                 QCS_TIMING_ADD(P, 5 + 2 * group, QCS_TICK(P) - t1);     // the steps
             }
         }
-        if (tig == 0 && group == 0) QCS_TIMING_SET(P, 3, my_tiles);
+        if (tig == 0) QCS_TIMING_ADD(P, 3, n_done);
     }
 }
 
@@ -314,70 +413,59 @@ constexpr pipe_shape kShapes[] = {
 };
 constexpr int kNumShapes = (int) (sizeof kShapes / sizeof kShapes[0]);
 
-size_t pipe_smem(const pipe_shape &sh, const qft::sweep_desc &d)
+const pipe_shape &shape_of(const qcs_register *reg)
 {
-    return (size_t) sh.stages * ((size_t) 16 << sh.tb) + 16 * (size_t) d.wcol_total + 16 * (size_t) sh.groups * kMaxSteps +
-           8 * 3 * (size_t) sh.stages + sizeof(diag_gate) * (size_t) d.n_diag + 1024;
+    return kShapes[reg->opt_pipe_shape >= 0 && reg->opt_pipe_shape < kNumShapes ? reg->opt_pipe_shape : 0];
+}
+
+size_t pipe_smem(const pipe_shape &sh, int wcol_entries, int n_diag)
+{
+    return (size_t) sh.stages * ((size_t) 16 << sh.tb) + 16 * (size_t) wcol_entries + 16 * (size_t) sh.stages * kMaxSteps +
+           8 * 4 * (size_t) sh.stages + sizeof(diag_gate) * (size_t) n_diag + 1024;
 }
 
 template <int TB, int STAGES, int GROUPS, int GT>
-int launch_shape(qcs_register *reg, const CUtensorMap &tmap, const pipe_params &P, size_t smem, const qft::sweep_target &tg)
+int launch_shape(qcs_register *reg, const CUtensorMap &tmap0, const CUtensorMap &tmap1, const pipe_params &P, size_t smem,
+                 const qft::sweep_target &tg)
 {
     auto kern = k_qft_sweep_tma<TB, STAGES, GROUPS, GT>;
     QCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     uint64_t grid = (uint64_t) reg->sm_count;
     if (tg.max_ctas > 0 && grid > (uint64_t) tg.max_ctas) grid = (uint64_t) tg.max_ctas;
     if (grid > P.n_tiles) grid = P.n_tiles;
+    // a paired launch moves the state through HBM once (read by A, written by B) and does two sweeps' work
     qcs_launch_begin(reg, tg.kind, tg.bytes > 0.0 ? tg.bytes : 32.0 * (double) (P.n_tiles << TB));
-    kern<<<(unsigned) grid, 64 + GROUPS * GT, smem, tg.stream>>>(tmap, P);
+    kern<<<(unsigned) grid, 64 + GROUPS * GT, smem, tg.stream>>>(tmap0, tmap1, P);
     return qcs_launch_end(reg, tg.kind, "k_qft_sweep_tma");
 }
 
-}  // namespace
-
-static int launch_by_shape(qcs_register *reg, int shape_id, const CUtensorMap &tmap, const pipe_params &P, size_t smem,
-                           const qft::sweep_target &tg);
-
-int qcs_pipeline_tile_bits(const qcs_register *reg)
+int launch_by_shape(qcs_register *reg, int shape_id, const CUtensorMap &tmap0, const CUtensorMap &tmap1, const pipe_params &P,
+                    size_t smem, const qft::sweep_target &tg)
 {
-    const int v = reg->opt_pipe_shape >= 0 && reg->opt_pipe_shape < kNumShapes ? reg->opt_pipe_shape : 0;
-    return kShapes[v].tb;
+    switch (shape_id) {
+        case 1: return launch_shape<11, 6, 3, 128>(reg, tmap0, tmap1, P, smem, tg);
+        case 2: return launch_shape<11, 6, 6, 64>(reg, tmap0, tmap1, P, smem, tg);
+        case 3: return launch_shape<12, 3, 1, 256>(reg, tmap0, tmap1, P, smem, tg);
+        case 4: return launch_shape<12, 3, 3, 64>(reg, tmap0, tmap1, P, smem, tg);
+        case 5: return launch_shape<11, 6, 2, 128>(reg, tmap0, tmap1, P, smem, tg);
+        default: return launch_shape<12, 3, 3, 128>(reg, tmap0, tmap1, P, smem, tg);
+    }
 }
 
-// true when the pipelined kernel can run this sweep
-bool qcs_pipeline_supports(const qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &p)
-{
-    const pipe_shape sh = kShapes[reg->opt_pipe_shape >= 0 && reg->opt_pipe_shape < kNumShapes ? reg->opt_pipe_shape : 0];
-    if (p.d.t != sh.tb || tg.n_bits < (unsigned) sh.tb + 3) return false;
-    const bool strided = p.d.g_lo > p.d.a;
-    // a TMA box row is 2^(a+1) doubles (32 B .. 2 KiB); coordinates are 32-bit
-    if (strided && (p.d.a < 1 || p.d.a > 7 || p.d.g_lo + 1 > 31)) return false;
-    // the linear layout TMA writes for a strided tile must make every step conflict-free; the
-    // contiguous sweep takes the 128-byte hardware swizzle (conflict-free for every step except a
-    // radix-16 step on bits 0..3, which is 2-way conflicted)
-    if (strided && conflict_cost(p.d, 28, true) != 0) return false;
-    return pipe_smem(sh, p.d) <= reg->smem_optin;
-}
-
-int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &plan)
+// tensor map + box geometry of one sweep
+int encode_phase(const pipe_shape &sh, const qft::sweep_target &tg, const qft::sweep_plan &plan, phase_params &Q, CUtensorMap &tmap)
 {
     encode_fn_t encode = get_encode();
     if (!encode) {
         fprintf(stderr, "qcs: cuTensorMapEncodeTiled is unavailable\n");
         return QCS_UNKNOWN_ERROR;
     }
-    const int shape_id = reg->opt_pipe_shape >= 0 && reg->opt_pipe_shape < kNumShapes ? reg->opt_pipe_shape : 0;
-    const pipe_shape sh = kShapes[shape_id];
-    pipe_params P;
-    P.d = plan.d;
-    P.n_tiles = plan.n_tiles;
-    P.prefetch = reg->opt_prefetch_tiles;
-    CUtensorMap tmap;
+    Q.d = plan.d;
     cuuint64_t dims[3], strides[2];
     cuuint32_t box[3], estr[3] = {1, 1, 1};
     CUtensorMapSwizzle swz;
     const bool strided = plan.d.g_lo > plan.d.a;
-    unsigned rows;
+    unsigned rows = 0;
     if (strided) {
         const int g = plan.d.g_hi - plan.d.g_lo;
         rows = 1u << g;
@@ -388,25 +476,47 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
         strides[1] = 16ull << plan.d.g_hi;
         box[0] = 2u << plan.d.a;
         swz = CU_TENSOR_MAP_SWIZZLE_NONE;
-        P.lo_gap = plan.d.g_lo - plan.d.a;
-        P.d.sw = 28;                                         // no XOR
+        Q.lo_gap = plan.d.g_lo - plan.d.a;
+        Q.d.sw = 28;                                         // no XOR
     } else {
-        rows = 1u << (sh.tb - 3);
-        dims[0] = 16;                                        // 128 B rows
-        dims[1] = (1ull << tg.n_bits) >> 3;
-        dims[2] = 1;
-        strides[0] = 128;
-        strides[1] = 128ull * dims[1];
-        box[0] = 16;
+        // contiguous tile, 128 B rows with the 128-byte hardware swizzle.  Two views of the same 2^tb
+        // amplitudes; the one whose shared-memory layout gives this sweep's steps fewer bank conflicts:
+        //   plain : rows e >> 3                                   -> phys(e) = e ^ ((e >> 3) & 7)
+        //   split : {8 amplitudes} x {e >> 4} x {bit 3 of e}      -> tile_phys(e, kSwizzleSplit3 + tb)
+        Q.lo_gap = -1;
         swz = CU_TENSOR_MAP_SWIZZLE_128B;
-        P.lo_gap = -1;
-        P.d.sw = 3;
+        dims[0] = 16;
+        box[0] = 16;
+        static const bool no_split = getenv("QCS_NO_SPLIT3") != nullptr;      // experiments only
+        const bool split = !no_split && sh.tb >= 5 && sh.tb - 4 <= 8 &&
+                           conflict_cost(plan.d, kSwizzleSplit3 + sh.tb, true) < conflict_cost(plan.d, 3, true);
+        if (split) {
+            dims[1] = (1ull << tg.n_bits) >> 4;
+            dims[2] = 2;
+            strides[0] = 256;
+            strides[1] = 128;
+            Q.d.sw = kSwizzleSplit3 + sh.tb;
+            Q.box_rows = 1 << (sh.tb - 4);
+            Q.n_boxes = 1;
+            Q.box_bytes = 16u << sh.tb;
+            box[1] = (cuuint32_t) Q.box_rows;
+            box[2] = 2;
+        } else {
+            rows = 1u << (sh.tb - 3);
+            dims[1] = (1ull << tg.n_bits) >> 3;
+            dims[2] = 1;
+            strides[0] = 128;
+            strides[1] = 128ull * dims[1];
+            Q.d.sw = 3;
+        }
     }
-    P.box_rows = rows < 256u ? (int) rows : 256;             // a box dimension is at most 256
-    P.n_boxes = (int) (rows / (unsigned) P.box_rows);
-    P.box_bytes = (uint32_t) (((size_t) 16 << sh.tb) / (size_t) P.n_boxes);
-    box[1] = (cuuint32_t) P.box_rows;
-    box[2] = 1;
+    if (Q.lo_gap >= 0 || Q.d.sw == 3) {
+        Q.box_rows = rows < 256u ? (int) rows : 256;         // a box dimension is at most 256
+        Q.n_boxes = (int) (rows / (unsigned) Q.box_rows);
+        Q.box_bytes = (uint32_t) (((size_t) 16 << sh.tb) / (size_t) Q.n_boxes);
+        box[1] = (cuuint32_t) Q.box_rows;
+        box[2] = 1;
+    }
     // 128 B rows: promoting the requests to 256 B would fetch a neighbour's half-line with every row
     // (measured at n = 30: 21.2-21.4 ms for every promotion setting -- not a lever)
     const CUtensorMapL2promotion promo = (strided && plan.d.a <= 3) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
@@ -417,8 +527,13 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
         fprintf(stderr, "qcs: cuTensorMapEncodeTiled failed (%d)\n", (int) cr);
         return QCS_UNKNOWN_ERROR;
     }
-    const size_t smem = pipe_smem(sh, P.d);
-    // -DQCS_PIPE_TIMING builds: QCS_PIPE_TIMING=1 prints where the roles of the pipeline spend their cycles
+    return QCS_NO_ERROR;
+}
+
+// -DQCS_PIPE_TIMING builds: QCS_PIPE_TIMING=1 prints where the roles of the pipeline spend their cycles
+int run_launch(qcs_register *reg, const pipe_shape &sh, int shape_id, const CUtensorMap &tmap0, const CUtensorMap &tmap1,
+               pipe_params &P, size_t smem, const qft::sweep_target &tg)
+{
 #ifdef QCS_PIPE_TIMING
     static const bool timing_on = getenv("QCS_PIPE_TIMING") != nullptr;
 #else
@@ -429,7 +544,7 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
         QCS_CUDA(cudaMalloc((void **) &P.timing, 16 * 8 * (size_t) reg->sm_count));
         QCS_CUDA(cudaMemsetAsync(P.timing, 0, 16 * 8 * (size_t) reg->sm_count, tg.stream));
     }
-    const int rc = launch_by_shape(reg, shape_id, tmap, P, smem, tg);
+    const int rc = launch_by_shape(reg, shape_id, tmap0, tmap1, P, smem, tg);
     if (timing_on && rc == QCS_NO_ERROR) {
         std::vector<unsigned long long> h(16 * (size_t) reg->sm_count);
         QCS_CUDA(cudaMemcpyAsync(h.data(), P.timing, h.size() * 8, cudaMemcpyDeviceToHost, tg.stream));
@@ -437,10 +552,11 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
         double sum[16] = {0};
         for (size_t i = 0; i < h.size(); i++) sum[i % 16] += (double) h[i];
         const double tiles = sum[3] > 0 ? sum[3] : 1;
-        fprintf(stderr, "qcs pipe timing (cycles per tile, avg over CTAs) shape %d a=%d g=[%d,%d) steps=%d: producer wait empty %.0f | "
-                "store wait computed %.0f, store read %.0f |", shape_id, plan.d.a, plan.d.g_lo, plan.d.g_hi, plan.d.n_steps,
-                sum[0] / tiles, sum[1] / tiles, sum[2] / tiles);
-        for (int g = 0; g < sh.groups && g < 6; g++)
+        const sweep_desc &d = P.ph[0].d;
+        fprintf(stderr, "qcs pipe timing (cycles per tile, avg over CTAs) shape %d phases %d a=%d g=[%d,%d) steps=%d: producer wait empty %.0f, "
+                "wait dependency %.0f | store wait computed %.0f, store read %.0f |", shape_id, P.n_phases, d.a, d.g_lo, d.g_hi,
+                d.n_steps, sum[0] / tiles, sum[10] / tiles, sum[1] / tiles, sum[2] / tiles);
+        for (int g = 0; g < sh.groups && g < 3; g++)
             fprintf(stderr, " g%d wait load %.0f steps %.0f;", g, sum[4 + 2 * g] / tiles * sh.groups, sum[5 + 2 * g] / tiles * sh.groups);
         fprintf(stderr, "\n");
         cudaFree(P.timing);
@@ -448,15 +564,87 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
     return rc;
 }
 
-static int launch_by_shape(qcs_register *reg, int shape_id, const CUtensorMap &tmap, const pipe_params &P, size_t smem,
-                           const qft::sweep_target &tg)
+}  // namespace
+
+int qcs_pipeline_tile_bits(const qcs_register *reg) { return shape_of(reg).tb; }
+
+// true when the pipelined kernel can run this sweep
+bool qcs_pipeline_supports(const qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &p)
 {
-    switch (shape_id) {
-        case 1: return launch_shape<11, 6, 3, 128>(reg, tmap, P, smem, tg);
-        case 2: return launch_shape<11, 6, 6, 64>(reg, tmap, P, smem, tg);
-        case 3: return launch_shape<12, 3, 1, 256>(reg, tmap, P, smem, tg);
-        case 4: return launch_shape<12, 3, 3, 64>(reg, tmap, P, smem, tg);
-        case 5: return launch_shape<11, 6, 2, 128>(reg, tmap, P, smem, tg);
-        default: return launch_shape<12, 3, 3, 128>(reg, tmap, P, smem, tg);
+    const pipe_shape sh = shape_of(reg);
+    if (p.d.t != sh.tb || tg.n_bits < (unsigned) sh.tb + 3) return false;
+    const bool strided = p.d.g_lo > p.d.a;
+    // a TMA box row is 2^(a+1) doubles (32 B .. 2 KiB); coordinates are 32-bit
+    if (strided && (p.d.a < 1 || p.d.a > 7 || p.d.g_lo + 1 > 31)) return false;
+    // the linear layout TMA writes for a strided tile must make every step conflict-free; the
+    // contiguous sweep takes the 128-byte hardware swizzle (conflict-free for every step except a
+    // radix-16 step on bits 0..3, which is 2-way conflicted)
+    if (strided && conflict_cost(p.d, 28, true) != 0) return false;
+    return pipe_smem(sh, p.d.wcol_total, p.d.n_diag) <= reg->smem_optin;
+}
+
+int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &plan)
+{
+    const pipe_shape sh = shape_of(reg);
+    const int shape_id = reg->opt_pipe_shape >= 0 && reg->opt_pipe_shape < kNumShapes ? reg->opt_pipe_shape : 0;
+    pipe_params P = {};
+    CUtensorMap tmap;
+    QCS_TRY(encode_phase(sh, tg, plan, P.ph[0], tmap));
+    P.ph[0].wcol_base = 0;
+    P.n_phases = 1;
+    P.n_tiles = plan.n_tiles;
+    return run_launch(reg, sh, shape_id, tmap, tmap, P, pipe_smem(sh, plan.d.wcol_total, plan.d.n_diag), tg);
+}
+
+// Can the consecutive sweeps a -> b run as one L2-paired launch?  One of them must be the contiguous
+// sweep (tile = bits [0, tb)), the other the strided sweep whose stage bits start at bit tb (inverse
+// transform: strided then contiguous; forward transform: the mirror image).
+bool qcs_pipeline_pair_supported(const qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &a,
+                                 const qft::sweep_plan &b)
+{
+    const pipe_shape sh = shape_of(reg);
+    if (!reg->opt_l2_pair || !qcs_pipeline_supports(reg, tg, a) || !qcs_pipeline_supports(reg, tg, b)) return false;
+    const bool a_strided = a.d.g_lo > a.d.a, b_strided = b.d.g_lo > b.d.a;
+    if (a_strided == b_strided) return false;
+    const qft::sweep_plan &st = a_strided ? a : b;
+    if (st.d.g_lo != sh.tb || a.n_tiles != b.n_tiles) return false;             // its stage bits start where the contiguous tile ends
+    if (a.d.n_diag || b.d.n_diag || a.d.slice_bits || b.d.slice_bits || a.d.tile_first || b.d.tile_first) return false;
+    if (st.d.g_hi - sh.tb > 20 || (uint64_t) a.n_tiles < (2ull << (st.d.g_hi - sh.tb))) return false;   // at least two blocks
+    if ((16ull << st.d.g_hi) > (uint64_t) reg->opt_l2_pair_max_block) return false;   // a few blocks must fit the L2
+    return pipe_smem(sh, a.d.wcol_total + b.d.wcol_total, 0) <= reg->smem_optin;
+}
+
+int qcs_pipeline_launch_pair(qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &a, const qft::sweep_plan &b)
+{
+    const pipe_shape sh = shape_of(reg);
+    const int shape_id = reg->opt_pipe_shape >= 0 && reg->opt_pipe_shape < kNumShapes ? reg->opt_pipe_shape : 0;
+    pipe_params P = {};
+    CUtensorMap tmap0, tmap1;
+    QCS_TRY(encode_phase(sh, tg, a, P.ph[0], tmap0));
+    QCS_TRY(encode_phase(sh, tg, b, P.ph[1], tmap1));
+    P.ph[0].wcol_base = 0;
+    P.ph[1].wcol_base = a.d.wcol_total;
+    P.n_phases = 2;
+    P.n_tiles = a.n_tiles;
+    P.blk_tile_bits = (a.d.g_lo > a.d.a ? a.d.g_hi : b.d.g_hi) - sh.tb;
+    const uint64_t per_block = 1ull << P.blk_tile_bits;
+    const uint64_t n_blocks = a.n_tiles >> P.blk_tile_bits;
+    // B trails A by one block plus what the chip has in flight (every CTA up to `stages` tiles)
+    uint64_t lag = per_block + (uint64_t) reg->opt_l2_pair_lag;
+    if (lag > a.n_tiles) lag = a.n_tiles;
+    P.lag = lag;
+    // queue head + one counter per block, zeroed in stream order
+    const size_t need = 8 + 4 * (size_t) n_blocks;
+    if (need > reg->d_pair_cap) {
+        QCS_CUDA(cudaStreamSynchronize(tg.stream));
+        if (reg->d_pair) QCS_CUDA(cudaFree(reg->d_pair));
+        reg->d_pair = nullptr;
+        reg->d_pair_cap = 0;
+        QCS_CUDA(cudaMalloc(&reg->d_pair, need));
+        reg->d_pair_cap = need;
     }
+    QCS_CUDA(cudaMemsetAsync(reg->d_pair, 0, need, tg.stream));
+    P.ticket = (unsigned long long *) reg->d_pair;
+    P.done = (unsigned *) ((unsigned char *) reg->d_pair + 8);
+    return run_launch(reg, sh, shape_id, tmap0, tmap1, P, pipe_smem(sh, a.d.wcol_total + b.d.wcol_total, 0), tg);
 }

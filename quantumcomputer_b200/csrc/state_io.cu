@@ -58,6 +58,7 @@ struct pinned_pair {
 
 extern "C" int qcs_save_state(qcs_register *reg, const char *path)
 {
+    QCS_GROUP_FORWARD(reg, qcs_save_state(m, path));
     if (!reg || !path) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaSetDevice(reg->device));
     QCS_TRY(qcs_fuse_flush(reg));
@@ -101,6 +102,7 @@ extern "C" int qcs_save_state(qcs_register *reg, const char *path)
 
 extern "C" int qcs_load_state(qcs_register *reg, const char *path)
 {
+    QCS_GROUP_FORWARD(reg, qcs_load_state(m, path));
     if (!reg || !path) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaSetDevice(reg->device));
     QCS_TRY(qcs_fuse_flush(reg));

@@ -5,7 +5,8 @@
  * plus  -f trial_int  (the spelling the reference documents but does not
  * parse, qc_shor.c:26,1177,1185), -s seed (the reference seeds with time(NULL),
  * qc_shor.c:1299), -r (robust classical post-processing), -x (gate-by-gate
- * reference-order kernels instead of fused sweeps), -d device.
+ * reference-order kernels instead of fused sweeps), -d device, -g n_gpus (the
+ * register sharded over the first n_gpus devices of the box: qcs_register_create_multi).
  * All state lives on the GPU; this file only makes the three calls the
  * reference's find_period makes into the gate path (qc_shor.c:922-928).
  */
@@ -19,7 +20,7 @@
 #include "shor_classical.h"
 
 static const char *USAGE =
-    "Usage: ./qc_shor_b200 -C num -L L_reg_size -M M_reg_size [-a|-f trial_int] [-v] [-V] [-s seed] [-r] [-x] [-d device]\n";
+    "Usage: ./qc_shor_b200 -C num -L L_reg_size -M M_reg_size [-a|-f trial_int] [-v] [-V] [-s seed] [-r] [-x] [-d device] [-g n_gpus]\n";
 
 static void issue_warnings(unsigned C, int L, int M)
 {
@@ -33,12 +34,12 @@ static void issue_warnings(unsigned C, int L, int M)
 int main(int argc, char *argv[])
 {
     unsigned C = 0, trial = 0;
-    int L = 0, M = 0, have_C = 0, have_L = 0, have_M = 0, device = -1, exact = 0;
+    int L = 0, M = 0, have_C = 0, have_L = 0, have_M = 0, device = -1, exact = 0, n_gpus = 1;
     unsigned long seed = (unsigned long) time(NULL);
     qcsh_options opt = {QCSH_VERBATIM, 0, 0, 0, 0.0};
     int arg;
 
-    while ((arg = getopt(argc, argv, "C:L:M:a:f:vVs:rxd:")) != -1) {
+    while ((arg = getopt(argc, argv, "C:L:M:a:f:vVs:rxd:g:")) != -1) {
         switch (arg) {
             case 'C': C = (unsigned) atoi(optarg); have_C = 1; break;
             case 'L': L = atoi(optarg); have_L = 1; break;
@@ -51,6 +52,7 @@ int main(int argc, char *argv[])
             case 'r': opt.mode = QCSH_ROBUST; break;
             case 'x': exact = 1; break;
             case 'd': device = atoi(optarg); break;
+            case 'g': n_gpus = atoi(optarg); break;
             default: fputs(USAGE, stdout); return QCS_BAD_ARGUMENTS;
         }
     }
@@ -71,7 +73,7 @@ int main(int argc, char *argv[])
     qcsh_rng_seed(&rng, seed);
 
     qcs_register *reg = NULL;
-    int rc = qcs_register_create(&reg, L, M, device);
+    int rc = n_gpus > 1 ? qcs_register_create_multi(&reg, L, M, n_gpus) : qcs_register_create(&reg, L, M, device);
     if (rc != QCS_NO_ERROR) {
         fprintf(stderr, "Error: %s.\n", rc == QCS_INSUFFICIENT_MEMORY ? "Insufficient memory" : qcs_error_string(rc));
         return rc;

@@ -301,6 +301,37 @@ int main(int argc, char **argv)
 
 
 
+
+    if (quick == 6) {
+        // which property of the first sweep's tiles is slow: the number of rows (pages touched per
+        // tile), the stride, or the 128 B row itself?  k_tile_rmw always moves 2^12-amplitude tiles:
+        // rows = 2^(12 - a)
+        struct { int a, g_lo; } pats[] = {{3, 12}, {3, 16}, {3, 17}, {3, 18}, {3, 19}, {3, 20}, {3, 21}, {4, 17}, {4, 18}, {4, 20},
+                                          {4, 21}, {4, 22}, {5, 23}, {2, 20}, {2, 12}};
+        const char *modes[] = {"read ", "rmw  ", "write"};
+        for (auto &pt : pats) {
+            for (int mode = 0; mode < 3; mode++) {
+                cudaEvent_t a, b;
+                CK(cudaEventCreate(&a));
+                CK(cudaEventCreate(&b));
+                float best = 1e30f;
+                for (int rep = 0; rep < 3; rep++) {
+                    CK(cudaEventRecord(a));
+                    k_tile_rmw<<<sms * 2, 256>>>(buf, 30, pt.a, pt.g_lo, mode);
+                    CK(cudaEventRecord(b));
+                    CK(cudaEventSynchronize(b));
+                    CK(cudaGetLastError());
+                    float ms;
+                    CK(cudaEventElapsedTime(&ms, a, b));
+                    if (ms < best) best = ms;
+                }
+                const double bytes = (double) total_bytes * (mode == 1 ? 2.0 : 1.0);
+                printf("rows %4d x %4d B, stride %8.0f KiB (%6.1f pages of 2 MiB) %s: %8.3f ms = %7.1f GB/s\n", 1 << (12 - pt.a), 16 << pt.a,
+                       (double) (16ull << pt.g_lo) / 1024.0, (double) (16ull << pt.g_lo) / 2097152.0, modes[mode], best, bytes / best / 1e6);
+            }
+        }
+        return 0;
+    }
     if (quick == 5) {
         struct { int a, g_lo; const char *what; } pats[] = {
             {3, 21, "128 B rows, stride 32 MiB"},
