@@ -32,6 +32,11 @@ $(LIB): $(CU_OBJS)
 	@mkdir -p $(PKG)/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(CU_OBJS) -ldl
 
+# development build with the pipeline's role timing compiled in (QCS_LIB_PATH=build/timing/libqcs.so QCS_PIPE_TIMING=1)
+timing:
+	@mkdir -p build/timing
+	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --fmad=true -DQCS_PIPE_TIMING -shared -o build/timing/libqcs.so $(CU_SRCS) -ldl
+
 host: $(HOSTBIN) $(HOSTLIB)
 
 # the classical half as a shared object, so tests can drive it through ctypes
@@ -51,4 +56,4 @@ clean:
 	rm -rf build $(PKG)/lib $(PKG)/bin
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib host oracle clean
+.PHONY: all lib host oracle clean timing

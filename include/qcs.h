@@ -103,7 +103,13 @@ enum {
      * first by one block plus QCS_OPT_L2_PAIR_LAG tiles (default 444 = 3 tiles per SM). */
     QCS_OPT_L2_PAIR = 12,
     QCS_OPT_L2_PAIR_LAG = 13,
-    QCS_OPT_L2_PAIR_MAX_BLOCK = 14
+    QCS_OPT_L2_PAIR_MAX_BLOCK = 14,
+    /* 1 (default): the TMA loads and stores of a paired launch carry L2 eviction-priority hints
+     * (evict_last for what the second sweep reads, evict_first for the rest) */
+    QCS_OPT_L2_PAIR_HINTS = 15,
+    /* 1: the last step of every tile of a pipelined sweep stores straight from registers to global
+     * memory (ld/st unit) instead of going back through shared memory and a TMA store */
+    QCS_OPT_DIRECT_STORE = 16
 };
 
 /* kernel classes reported by qcs_profile_get */

@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libqcs.so")
+# QCS_LIB_PATH: development builds of the same library (e.g. the -DQCS_PIPE_TIMING build of `make timing`)
+LIB_PATH = os.environ.get("QCS_LIB_PATH") or os.path.join(_HERE, "lib", "libqcs.so")
 
 _u = C.c_uint
 _ull = C.c_ulonglong

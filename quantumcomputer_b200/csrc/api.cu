@@ -199,6 +199,8 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->d_pair = nullptr;
     reg->d_pair_cap = 0;
     reg->opt_l2_pair = 1;
+    reg->opt_l2_pair_hints = 1;
+    reg->opt_direct_store = 0;
     reg->opt_l2_pair_lag = 3 * 148;
     reg->opt_l2_pair_max_block = 32ll << 20;
     reg->fusing = 0;
@@ -354,6 +356,8 @@ extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
             if (value < 0 || value > (1 << 20)) return QCS_BAD_ARGUMENTS;
             reg->opt_l2_pair_lag = (int) value;
             return QCS_NO_ERROR;
+        case QCS_OPT_L2_PAIR_HINTS: reg->opt_l2_pair_hints = value != 0; return QCS_NO_ERROR;
+        case QCS_OPT_DIRECT_STORE: reg->opt_direct_store = value != 0; return QCS_NO_ERROR;
         case QCS_OPT_L2_PAIR_MAX_BLOCK:
             if (value < (1 << 20)) return QCS_BAD_ARGUMENTS;
             reg->opt_l2_pair_max_block = value;
@@ -381,6 +385,8 @@ extern "C" long long qcs_get_option(const qcs_register *reg, int option)
         case QCS_OPT_L2_PAIR: return reg->opt_l2_pair;
         case QCS_OPT_L2_PAIR_LAG: return reg->opt_l2_pair_lag;
         case QCS_OPT_L2_PAIR_MAX_BLOCK: return reg->opt_l2_pair_max_block;
+        case QCS_OPT_L2_PAIR_HINTS: return reg->opt_l2_pair_hints;
+        case QCS_OPT_DIRECT_STORE: return reg->opt_direct_store;
         default: return -1;
     }
 }

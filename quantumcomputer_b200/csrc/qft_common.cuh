@@ -36,7 +36,7 @@ struct sweep_desc {
     int a, g_lo, g_hi, t;   // tile = physical bits [0,a) U [g_lo,g_hi); t = a + g_hi - g_lo
     int lo;                 // lowest qubit of the transform (the reference's M_size)
     int n_steps;
-    int sw;                 // swizzle: phys(e) = e ^ ((e >> sw) & 7); kSwizzleSplit3: the layout of tile_phys below
+    int sw;                 // swizzle: phys(e) = e ^ ((e >> sw) & 7)
     int inverse;            // 1: inverse_QFT of the reference, 0: its adjoint
     int wcol_total;         // total column-twiddle entries
     int hadamard_only;      // 1: the stages are bare Hadamards (no phase gates): Walsh-Hadamard sweep
@@ -168,19 +168,8 @@ __device__ __forceinline__ void st256(double2 *p, double2 lo, double2 hi)
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(lo.x), "d"(lo.y), "d"(hi.x), "d"(hi.y) : "memory");
 }
 
-// Shared-memory position (in amplitudes) of tile-local element e.
-//   sw < kSwizzleSplit3 : e ^ ((e >> sw) & 7)  (sw = 28: linear)
-//   sw = kSwizzleSplit3 + t : contiguous 2^t tile brought in by TMA as a 3-D box {8 amplitudes} x
-//        {e >> 4} x {bit 3 of e} with the 128-byte hardware swizzle: bit 3 moves to the top of the
-//        tile address and the 16-byte chunk is XORed with bits 4..6 of e -- every radix-16 step of a
-//        2^12 tile, including the one on bits 0..3, then touches 8 distinct bank groups per quarter warp.
-constexpr int kSwizzleSplit3 = 64;
-__host__ __device__ __forceinline__ unsigned tile_phys(unsigned e, int sw)
-{
-    if (sw < kSwizzleSplit3) return e ^ ((e >> sw) & 7u);
-    const int t = sw - kSwizzleSplit3;
-    return ((e & 8u) << (t - 4)) | ((e >> 4) << 3) | ((e & 7u) ^ ((e >> 4) & 7u));
-}
+// Shared-memory position (in amplitudes) of tile-local element e: e ^ ((e >> sw) & 7); sw = 28: linear
+__host__ __device__ __forceinline__ unsigned tile_phys(unsigned e, int sw) { return e ^ ((e >> sw) & 7u); }
 
 struct tile_geom {
     int a, g_lo, sw;
@@ -192,7 +181,9 @@ struct tile_geom {
     __device__ __forceinline__ unsigned swz(unsigned e) const { return tile_phys(e, sw); }
 };
 
-template <int R, bool INV, bool TW>
+// LIN: the tile is laid out linearly in shared memory (strided sweeps of the pipelined kernel): the R
+// elements of a column are `stride` apart, one multiply-add per address instead of the swizzle arithmetic
+template <int R, bool INV, bool TW, bool LIN = false>
 __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__restrict__ tile,
                                          const double2 *__restrict__ wcol, double2 wb, const tile_geom G,
                                          const sweep_step S, int t, uint64_t base, bool from_global,
@@ -202,6 +193,7 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
 {
     const unsigned n_cols = 1u << (t - S.r);
     const unsigned low_mask = (1u << S.s) - 1u;
+    const unsigned lin_stride = 1u << S.s;
     for (unsigned c = tid; c < n_cols; c += nthreads) {
         const unsigned e_base = ((c >> S.s) << (S.s + S.r)) | (c & low_mask);
         double2 *g = amp + base + G.spread(e_base);
@@ -215,6 +207,10 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
 #pragma unroll
                 for (int d = 0; d < R; d++) x[d] = g[(uint64_t) d * g_stride];
             }
+        } else if (LIN) {
+            const double2 *col = tile + e_base;
+#pragma unroll
+            for (int d = 0; d < R; d++) x[d] = col[(unsigned) d * lin_stride];
         } else {
 #pragma unroll
             for (int d = 0; d < R; d++) x[d] = tile[G.swz(e_base + ((unsigned) d << S.s))];
@@ -268,6 +264,10 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
 #pragma unroll
                 for (int d = 0; d < R; d++) g[(uint64_t) d * g_stride] = x[d];
             }
+        } else if (LIN) {
+            double2 *col = tile + e_base;
+#pragma unroll
+            for (int d = 0; d < R; d++) col[(unsigned) d * lin_stride] = x[d];
         } else {
 #pragma unroll
             for (int d = 0; d < R; d++) tile[G.swz(e_base + ((unsigned) d << S.s))] = x[d];
@@ -275,7 +275,7 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
     }
 }
 
-template <bool INV, bool TW = true>
+template <bool INV, bool TW = true, bool LIN = false>
 __device__ __forceinline__ void dispatch_step(double2 *amp, double2 *tile, const double2 *wcol, double2 wb,
                                               const tile_geom G, const sweep_step S, int t, uint64_t base,
                                               bool from_global, bool to_global, bool apply_scale, double scale,
@@ -283,10 +283,10 @@ __device__ __forceinline__ void dispatch_step(double2 *amp, double2 *tile, const
                                               int n_diag = 0, uint64_t index_or = 0)
 {
     switch (S.r) {
-        case 4: run_step<16, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
-        case 3: run_step<8, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
-        case 2: run_step<4, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
-        default: run_step<2, INV, TW>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
+        case 4: run_step<16, INV, TW, LIN>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
+        case 3: run_step<8, INV, TW, LIN>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
+        case 2: run_step<4, INV, TW, LIN>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
+        default: run_step<2, INV, TW, LIN>(amp, tile, wcol, wb, G, S, t, base, from_global, to_global, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
     }
 }
 
@@ -456,6 +456,7 @@ inline void make_forward(std::vector<sweep_plan> &plans)
             p.d.step[k].col_off = off;
             off += p.d.step[k].notw ? 0 : (1 << p.d.step[k].s);
         }
+        p.d.wcol_total = off;
         p.d.wcol_total = off;
         p.d.sw = choose_swizzle(p.d);
     }

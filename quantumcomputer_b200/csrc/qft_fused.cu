@@ -144,11 +144,29 @@ static int launch_plan_inner(qcs_register *reg, const sweep_target &tg, const sw
     return launch_sweep<128, 4>(reg, tg, p, smem);
 }
 
-// a list of consecutive sweeps on one target: neighbours that can share an L2-paired launch do
+// a list of consecutive sweeps on one target: neighbours that can share an L2-paired launch do.
+// Pairs are formed from the contiguous sweep outwards (it is the last sweep of an inverse transform
+// and the first of a forward one), so that it always has a partner.
 static int launch_plans(qcs_register *reg, const sweep_target &tg, const std::vector<sweep_plan> &plans)
 {
-    for (size_t k = 0; k < plans.size(); k++) {
-        if (k + 1 < plans.size() && reg->opt_pipeline && qcs_pipeline_pair_supported(reg, tg, plans[k], plans[k + 1])) {
+    const size_t n = plans.size();
+    std::vector<int> with_next(n, 0);
+    if (reg->opt_pipeline && n >= 2) {
+        const bool contiguous_last = !(plans[n - 1].d.g_lo > plans[n - 1].d.a);
+        if (contiguous_last) {
+            for (size_t k = n - 1; k >= 1; ) {
+                if (qcs_pipeline_pair_supported(reg, tg, plans[k - 1], plans[k])) { with_next[k - 1] = 1; if (k < 2) break; k -= 2; }
+                else { k -= 1; }
+            }
+        } else {
+            for (size_t k = 0; k + 1 < n; ) {
+                if (qcs_pipeline_pair_supported(reg, tg, plans[k], plans[k + 1])) { with_next[k] = 1; k += 2; }
+                else { k += 1; }
+            }
+        }
+    }
+    for (size_t k = 0; k < n; k++) {
+        if (with_next[k]) {
             reg->launch_stream = tg.stream;
             const int rc = qcs_pipeline_launch_pair(reg, tg, plans[k], plans[k + 1]);
             reg->launch_stream = nullptr;

@@ -44,11 +44,15 @@ struct phase_params {
     int box_rows;
     uint32_t box_bytes;
     int wcol_base;          // where this phase's column-twiddle tables start in the kernel's table area
+    int inb_pos, inb_bits;  // paired launch: the tile-number bits [inb_pos, inb_pos + inb_bits) count the tiles
+                            // inside one block, the others (in order) number the block
 };
 
 // A launch runs one sweep (tiles dealt round robin over the CTAs) or an L2-PAIRED couple of
-// sweeps A -> B: A is a strided sweep whose stage bits end at bit `blk`, B the contiguous final
-// sweep, so every block of 2^blk consecutive amplitudes is closed under both.  The tiles of both
+// consecutive sweeps A -> B whose tiles have the same low run: the amplitudes fall into BLOCKS that
+// are closed under both sweeps (strided sweep + contiguous final sweep: 2^g_hi consecutive
+// amplitudes; two strided sweeps with stage bits [l, m) and [m, h): the low run x bits [l, h)), a few
+// MiB each, with as many tiles of A as of B.  The tiles of both
 // sweeps are handed out through one ticket queue in the order
 //     A[0 .. lag),  then alternating  A[lag + i], B[i],  then the last B's,
 // (lag >= one block of tiles) so that B trails A by a little more than one block: what A wrote is
@@ -63,6 +67,13 @@ struct pipe_params {
     uint64_t n_tiles;               // tiles per phase
     int blk_tile_bits;              // pair: log2(tiles per block)
     uint64_t lag;                   // pair: B trails A by this many tiles
+    int l2_hints;                   // pair: eviction-priority hints on the TMA loads and stores
+    double2 *amp;                   // the target array (direct stores)
+    int direct_store;               // 1: the last step of a tile writes straight from registers to global memory
+                                    // (ld/st unit) instead of back to the stage + TMA store: the TMA unit of an SM
+                                    // moves about 22 B/clk, loads and stores together (tools/ubench_tma.cu); with
+                                    // the stores on the other path it only carries the loads, and a stage is free
+                                    // again as soon as its last step has read it
     unsigned long long *ticket;     // pair: the queue head
     unsigned *done;                 // pair: stored A tiles per block
     unsigned long long *timing;     // -DQCS_PIPE_TIMING builds only: per-CTA cycle counters
@@ -126,6 +137,29 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// the same with an L2 eviction-priority hint (paired launches: what the second sweep will read is kept,
+// what nobody reads again leaves first)
+__device__ __forceinline__ uint64_t l2_policy(bool keep)
+{
+    uint64_t pol;
+    if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_3d_hint(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::
+            "r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap *map, const void *src, int c0, int c1, int c2, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2)
 {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
@@ -152,7 +186,7 @@ __device__ __forceinline__ void tile_coords(const phase_params &Q, uint64_t tix,
         c2 = (int) (tix >> Q.lo_gap);
     } else {
         c0 = 0;
-        c1 = (int) (tix << (Q.d.sw >= kSwizzleSplit3 ? TB - 4 : TB - 3));   // rows of 8 amplitudes (split view: pairs of rows)
+        c1 = (int) (tix << (TB - 3));                                       // rows of 8 amplitudes
         c2 = 0;
     }
 }
@@ -164,7 +198,14 @@ __device__ __forceinline__ uint64_t tile_base(const phase_params &Q, uint64_t ti
     return Q.lo_gap >= 0 ? (((tix >> Q.lo_gap) << Q.d.g_hi) | ((tix & ((1ull << Q.lo_gap) - 1ull)) << Q.d.a)) : (tix << TB);
 }
 
-// the t-th ticket of a paired launch -> phase bit | tile index within the phase
+// item of a paired launch (block-major: block * tiles_per_block + tile in block) -> tile number
+__device__ __forceinline__ uint64_t pair_tile(const pipe_params &P, const phase_params &Q, uint64_t idx)
+{
+    const uint64_t inb = idx & ((1ull << P.blk_tile_bits) - 1ull), blk = idx >> P.blk_tile_bits;
+    return ((blk >> Q.inb_pos) << (Q.inb_pos + Q.inb_bits)) | (inb << Q.inb_pos) | (blk & ((1ull << Q.inb_pos) - 1ull));
+}
+
+// the t-th ticket of a paired launch -> phase bit | item within the phase
 __device__ __forceinline__ uint64_t pair_item(const pipe_params &P, uint64_t t)
 {
     const uint64_t na = P.n_tiles, lag = P.lag;
@@ -175,7 +216,12 @@ __device__ __forceinline__ uint64_t pair_item(const pipe_params &P, uint64_t t)
     return kPhaseB | (pairs + (v - 2 * pairs));
 }
 
-template <int TB, int STAGES, int GROUPS, int GT>
+// MODE: what the stages are -- kWalsh: bare Hadamards (+ diagonal gates riding along), kInverse: the
+// reference's inverse_QFT stages, kForward: their adjoint.  One instantiation per mode keeps the code of
+// a launch small (the instruction cache holds about 40 KiB).
+enum { kWalsh = 0, kInverse = 1, kForward = 2 };
+
+template <int TB, int STAGES, int GROUPS, int GT, int MODE>
 __global__ void __launch_bounds__(64 + GROUPS * GT, 1)
 k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, const pipe_params P)
 {
@@ -232,6 +278,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
         // lanes < n_steps compute the tile's twiddle bases ----------------
         uint64_t next = kNoItem;
         if (paired && lane == 0) next = pair_item(P, atomicAdd(P.ticket, 1ull));
+        const uint64_t pol_stream = l2_policy(false);
         int sentinels = 0;
         for (uint64_t k = 0;; k++) {
             const int s = (int) (k % STAGES);
@@ -260,7 +307,8 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             }
             const int ph = (item & kPhaseB) ? 1 : 0;
             const phase_params &Q = P.ph[ph];
-            const uint64_t tix = tile_number(Q.d, item & (kPhaseB - 1ull));
+            const uint64_t idx = item & (kPhaseB - 1ull);
+            const uint64_t tix = paired ? pair_tile(P, Q, idx) : tile_number(Q.d, idx);
             if (!Q.d.hadamard_only && lane < Q.d.n_steps) {
                 const sweep_step S = Q.d.step[lane];
                 const uint64_t base = tile_base<TB>(Q, tix);
@@ -273,7 +321,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
                 s_item[s] = item;
                 if (ph == 1) {
                     // all A tiles of the block must be in L2 / memory
-                    const unsigned *flag = P.done + ((item & (kPhaseB - 1ull)) >> P.blk_tile_bits);
+                    const unsigned *flag = P.done + (idx >> P.blk_tile_bits);
                     const unsigned need = 1u << P.blk_tile_bits;
                     const long long tw = QCS_TICK(P);
                     while (ld_acquire_gpu(flag) < need) __nanosleep(200);
@@ -285,15 +333,22 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
                 mbar_expect_tx(&full[s], kTileBytes);
                 unsigned char *dst = (unsigned char *) (stage_buf + (size_t) s * (1u << TB));
                 const CUtensorMap *map = ph ? &tmap1 : &tmap0;
-                for (int b = 0; b < Q.n_boxes; b++)
-                    tma_load_3d(dst + (size_t) b * Q.box_bytes, map, &full[s], c0, c1 + b * Q.box_rows, c2);
+                if (paired && P.l2_hints) {
+                    // A's input and B's input (A's output, read for the last time) may leave the L2 first
+                    for (int b = 0; b < Q.n_boxes; b++)
+                        tma_load_3d_hint(dst + (size_t) b * Q.box_bytes, map, &full[s], c0, c1 + b * Q.box_rows, c2, pol_stream);
+                } else {
+                    for (int b = 0; b < Q.n_boxes; b++)
+                        tma_load_3d(dst + (size_t) b * Q.box_bytes, map, &full[s], c0, c1 + b * Q.box_rows, c2);
+                }
                 // the next ticket travels while this tile loads
                 if (paired) next = pair_item(P, atomicAdd(P.ticket, 1ull));
             }
         }
     } else if (warp == 1) {
-        // ---------------- store issuer ----------------
-        if (lane == 0) {
+        // ---------------- store issuer (idle when the consumers store directly) ----------------
+        if (lane == 0 && !P.direct_store) {
+            const uint64_t pol_keep = l2_policy(true), pol_stream = l2_policy(false);
             for (uint64_t k = 0;; k++) {
                 const int s = (int) (k % STAGES);
                 const uint32_t round = (uint32_t) (k / STAGES);
@@ -306,11 +361,18 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
                 const phase_params &Q = P.ph[ph];
                 const uint64_t idx = item & (kPhaseB - 1ull);
                 int c0, c1, c2;
-                tile_coords<TB>(Q, tile_number(Q.d, idx), c0, c1, c2);
+                tile_coords<TB>(Q, paired ? pair_tile(P, Q, idx) : tile_number(Q.d, idx), c0, c1, c2);
                 const unsigned char *src = (const unsigned char *) (stage_buf + (size_t) s * (1u << TB));
                 const CUtensorMap *map = ph ? &tmap1 : &tmap0;
-                for (int b = 0; b < Q.n_boxes; b++)
-                    tma_store_3d(map, src + (size_t) b * Q.box_bytes, c0, c1 + b * Q.box_rows, c2);
+                if (paired && P.l2_hints) {
+                    // A's output stays in the L2 until B has read it; B's output is final
+                    const uint64_t pol = ph == 0 ? pol_keep : pol_stream;
+                    for (int b = 0; b < Q.n_boxes; b++)
+                        tma_store_3d_hint(map, src + (size_t) b * Q.box_bytes, c0, c1 + b * Q.box_rows, c2, pol);
+                } else {
+                    for (int b = 0; b < Q.n_boxes; b++)
+                        tma_store_3d(map, src + (size_t) b * Q.box_bytes, c0, c1 + b * Q.box_rows, c2);
+                }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 QCS_TIMING_ADD(P, 1, t1 - t0);               // waiting for a computed tile
@@ -341,32 +403,45 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             const long long t1 = QCS_TICK(P);
             const uint64_t item = s_item[s];
             if (item == kNoItem) {
-                if (tig == 0) mbar_arrive(&computed[s]);     // lets the store issuer see the sentinel
+                if (tig == 0 && !P.direct_store) mbar_arrive(&computed[s]);     // lets the store issuer see the sentinel
                 break;
             }
             const int ph = (item & kPhaseB) ? 1 : 0;
             const phase_params &Q = P.ph[ph];
-            const uint64_t tix = tile_number(Q.d, item & (kPhaseB - 1ull));
+            const uint64_t tix = paired ? pair_tile(P, Q, item & (kPhaseB - 1ull)) : tile_number(Q.d, item & (kPhaseB - 1ull));
             const uint64_t base = tile_base<TB>(Q, tix);
             tile_geom G;
             G.a = Q.d.a;
             G.g_lo = Q.d.g_lo;
             G.sw = Q.d.sw;
-            const bool inv = Q.d.inverse != 0;
             const double2 *my_wcol = wcol + Q.wcol_base;
             for (int st = 0; st < Q.d.n_steps; st++) {
                 const sweep_step S = Q.d.step[st];
                 const bool last = st == Q.d.n_steps - 1;
+                const bool out = last && P.direct_store;        // straight to global memory
                 const double2 wb = wbase[s * kMaxSteps + st];
-                if (Q.d.hadamard_only) dispatch_step<true, false>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT, sdiag, Q.d.n_diag, Q.d.index_or);
-                else if (inv) dispatch_step<true>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT);
-                else dispatch_step<false>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT);
-                if (last) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
+                // strided tiles lie linearly in shared memory, the contiguous one carries the 128-byte swizzle
+                if (Q.lo_gap >= 0) {
+                    if (MODE == kWalsh) dispatch_step<true, false, true>(P.amp, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, out, last, Q.d.scale, tig, GT, sdiag, Q.d.n_diag, Q.d.index_or);
+                    else dispatch_step<MODE == kInverse, true, true>(P.amp, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, out, last, Q.d.scale, tig, GT);
+                } else {
+                    if (MODE == kWalsh) dispatch_step<true, false, false>(P.amp, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, out, last, Q.d.scale, tig, GT, sdiag, Q.d.n_diag, Q.d.index_or);
+                    else dispatch_step<MODE == kInverse, true, false>(P.amp, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, out, last, Q.d.scale, tig, GT);
+                }
+                if (last && !P.direct_store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
+                // paired launch, direct stores: every thread's part of the A tile is performed at GPU scope before
+                // the block counter moves
+                if (out && paired && ph == 0) __threadfence();
                 group_barrier(group, GT);
             }
             n_done++;
             if (tig == 0) {
-                mbar_arrive(&computed[s]);
+                if (P.direct_store) {
+                    mbar_arrive(&empty[s]);                  // the stage has been read for the last time
+                    if (paired && ph == 0) atomicAdd(P.done + ((item & (kPhaseB - 1ull)) >> P.blk_tile_bits), 1u);
+                } else {
+                    mbar_arrive(&computed[s]);
+                }
                 QCS_TIMING_ADD(P, 4 + 2 * group, t1 - t0);              // waiting for the load
                 QCS_TIMING_ADD(P, 5 + 2 * group, QCS_TICK(P) - t1);     // the steps
             }
@@ -424,11 +499,11 @@ size_t pipe_smem(const pipe_shape &sh, int wcol_entries, int n_diag)
            8 * 4 * (size_t) sh.stages + sizeof(diag_gate) * (size_t) n_diag + 1024;
 }
 
-template <int TB, int STAGES, int GROUPS, int GT>
-int launch_shape(qcs_register *reg, const CUtensorMap &tmap0, const CUtensorMap &tmap1, const pipe_params &P, size_t smem,
-                 const qft::sweep_target &tg)
+template <int TB, int STAGES, int GROUPS, int GT, int MODE>
+int launch_mode(qcs_register *reg, const CUtensorMap &tmap0, const CUtensorMap &tmap1, const pipe_params &P, size_t smem,
+                const qft::sweep_target &tg)
 {
-    auto kern = k_qft_sweep_tma<TB, STAGES, GROUPS, GT>;
+    auto kern = k_qft_sweep_tma<TB, STAGES, GROUPS, GT, MODE>;
     QCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     uint64_t grid = (uint64_t) reg->sm_count;
     if (tg.max_ctas > 0 && grid > (uint64_t) tg.max_ctas) grid = (uint64_t) tg.max_ctas;
@@ -437,6 +512,16 @@ int launch_shape(qcs_register *reg, const CUtensorMap &tmap0, const CUtensorMap 
     qcs_launch_begin(reg, tg.kind, tg.bytes > 0.0 ? tg.bytes : 32.0 * (double) (P.n_tiles << TB));
     kern<<<(unsigned) grid, 64 + GROUPS * GT, smem, tg.stream>>>(tmap0, tmap1, P);
     return qcs_launch_end(reg, tg.kind, "k_qft_sweep_tma");
+}
+
+template <int TB, int STAGES, int GROUPS, int GT>
+int launch_shape(qcs_register *reg, const CUtensorMap &tmap0, const CUtensorMap &tmap1, const pipe_params &P, size_t smem,
+                 const qft::sweep_target &tg)
+{
+    // both sweeps of a paired launch belong to the same transform: one mode
+    if (P.ph[0].d.hadamard_only) return launch_mode<TB, STAGES, GROUPS, GT, kWalsh>(reg, tmap0, tmap1, P, smem, tg);
+    if (P.ph[0].d.inverse) return launch_mode<TB, STAGES, GROUPS, GT, kInverse>(reg, tmap0, tmap1, P, smem, tg);
+    return launch_mode<TB, STAGES, GROUPS, GT, kForward>(reg, tmap0, tmap1, P, smem, tg);
 }
 
 int launch_by_shape(qcs_register *reg, int shape_id, const CUtensorMap &tmap0, const CUtensorMap &tmap1, const pipe_params &P,
@@ -479,44 +564,22 @@ int encode_phase(const pipe_shape &sh, const qft::sweep_target &tg, const qft::s
         Q.lo_gap = plan.d.g_lo - plan.d.a;
         Q.d.sw = 28;                                         // no XOR
     } else {
-        // contiguous tile, 128 B rows with the 128-byte hardware swizzle.  Two views of the same 2^tb
-        // amplitudes; the one whose shared-memory layout gives this sweep's steps fewer bank conflicts:
-        //   plain : rows e >> 3                                   -> phys(e) = e ^ ((e >> 3) & 7)
-        //   split : {8 amplitudes} x {e >> 4} x {bit 3 of e}      -> tile_phys(e, kSwizzleSplit3 + tb)
-        Q.lo_gap = -1;
-        swz = CU_TENSOR_MAP_SWIZZLE_128B;
-        dims[0] = 16;
+        rows = 1u << (sh.tb - 3);
+        dims[0] = 16;                                        // 128 B rows
+        dims[1] = (1ull << tg.n_bits) >> 3;
+        dims[2] = 1;
+        strides[0] = 128;
+        strides[1] = 128ull * dims[1];
         box[0] = 16;
-        static const bool no_split = getenv("QCS_NO_SPLIT3") != nullptr;      // experiments only
-        const bool split = !no_split && sh.tb >= 5 && sh.tb - 4 <= 8 &&
-                           conflict_cost(plan.d, kSwizzleSplit3 + sh.tb, true) < conflict_cost(plan.d, 3, true);
-        if (split) {
-            dims[1] = (1ull << tg.n_bits) >> 4;
-            dims[2] = 2;
-            strides[0] = 256;
-            strides[1] = 128;
-            Q.d.sw = kSwizzleSplit3 + sh.tb;
-            Q.box_rows = 1 << (sh.tb - 4);
-            Q.n_boxes = 1;
-            Q.box_bytes = 16u << sh.tb;
-            box[1] = (cuuint32_t) Q.box_rows;
-            box[2] = 2;
-        } else {
-            rows = 1u << (sh.tb - 3);
-            dims[1] = (1ull << tg.n_bits) >> 3;
-            dims[2] = 1;
-            strides[0] = 128;
-            strides[1] = 128ull * dims[1];
-            Q.d.sw = 3;
-        }
+        swz = CU_TENSOR_MAP_SWIZZLE_128B;
+        Q.lo_gap = -1;
+        Q.d.sw = 3;
     }
-    if (Q.lo_gap >= 0 || Q.d.sw == 3) {
-        Q.box_rows = rows < 256u ? (int) rows : 256;         // a box dimension is at most 256
-        Q.n_boxes = (int) (rows / (unsigned) Q.box_rows);
-        Q.box_bytes = (uint32_t) (((size_t) 16 << sh.tb) / (size_t) Q.n_boxes);
-        box[1] = (cuuint32_t) Q.box_rows;
-        box[2] = 1;
-    }
+    Q.box_rows = rows < 256u ? (int) rows : 256;             // a box dimension is at most 256
+    Q.n_boxes = (int) (rows / (unsigned) Q.box_rows);
+    Q.box_bytes = (uint32_t) (((size_t) 16 << sh.tb) / (size_t) Q.n_boxes);
+    box[1] = (cuuint32_t) Q.box_rows;
+    box[2] = 1;
     // 128 B rows: promoting the requests to 256 B would fetch a neighbour's half-line with every row
     // (measured at n = 30: 21.2-21.4 ms for every promotion setting -- not a lever)
     const CUtensorMapL2promotion promo = (strided && plan.d.a <= 3) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
@@ -593,24 +656,51 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
     P.ph[0].wcol_base = 0;
     P.n_phases = 1;
     P.n_tiles = plan.n_tiles;
+    P.amp = tg.amp;
+    P.direct_store = reg->opt_direct_store && plan.d.n_diag == 0;
     return run_launch(reg, sh, shape_id, tmap, tmap, P, pipe_smem(sh, plan.d.wcol_total, plan.d.n_diag), tg);
 }
 
-// Can the consecutive sweeps a -> b run as one L2-paired launch?  One of them must be the contiguous
-// sweep (tile = bits [0, tb)), the other the strided sweep whose stage bits start at bit tb (inverse
-// transform: strided then contiguous; forward transform: the mirror image).
+// block geometry of the pair a -> b (either order of the two sweeps); false: not a pair
+//   * one contiguous sweep (tile = bits [0, tb)) and the strided sweep whose stage bits start at tb:
+//     blocks of 2^g_hi consecutive amplitudes, tile-number bits [0, g) count inside the block
+//   * two strided sweeps with the same low run a and g stage bits each, [l, m) and [m, h):
+//     blocks = low run x bits [l, h); in both tile numbers the bits [l - a, l - a + g) count inside the block
+static bool pair_geometry(const pipe_shape &sh, const qft::sweep_plan &a, const qft::sweep_plan &b, int &inb_pos, int &inb_bits,
+                          uint64_t &block_bytes)
+{
+    const bool a_strided = a.d.g_lo > a.d.a, b_strided = b.d.g_lo > b.d.a;
+    if (a.n_tiles != b.n_tiles) return false;
+    if (a_strided != b_strided) {
+        const qft::sweep_plan &st = a_strided ? a : b;
+        if (st.d.g_lo != sh.tb) return false;
+        inb_pos = 0;
+        inb_bits = st.d.g_hi - st.d.g_lo;
+        block_bytes = 16ull << st.d.g_hi;
+        return true;
+    }
+    if (!a_strided) return false;
+    const qft::sweep_plan &hi = a.d.g_lo > b.d.g_lo ? a : b, &lo = a.d.g_lo > b.d.g_lo ? b : a;
+    if (hi.d.g_lo != lo.d.g_hi || hi.d.a != lo.d.a) return false;
+    if (hi.d.g_hi - hi.d.g_lo != lo.d.g_hi - lo.d.g_lo) return false;
+    inb_pos = lo.d.g_lo - lo.d.a;
+    inb_bits = lo.d.g_hi - lo.d.g_lo;
+    block_bytes = 16ull << (lo.d.a + 2 * inb_bits);
+    return true;
+}
+
+// Can the consecutive sweeps a -> b run as one L2-paired launch?
 bool qcs_pipeline_pair_supported(const qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &a,
                                  const qft::sweep_plan &b)
 {
     const pipe_shape sh = shape_of(reg);
     if (!reg->opt_l2_pair || !qcs_pipeline_supports(reg, tg, a) || !qcs_pipeline_supports(reg, tg, b)) return false;
-    const bool a_strided = a.d.g_lo > a.d.a, b_strided = b.d.g_lo > b.d.a;
-    if (a_strided == b_strided) return false;
-    const qft::sweep_plan &st = a_strided ? a : b;
-    if (st.d.g_lo != sh.tb || a.n_tiles != b.n_tiles) return false;             // its stage bits start where the contiguous tile ends
+    int inb_pos, inb_bits;
+    uint64_t block_bytes;
+    if (!pair_geometry(sh, a, b, inb_pos, inb_bits, block_bytes)) return false;
     if (a.d.n_diag || b.d.n_diag || a.d.slice_bits || b.d.slice_bits || a.d.tile_first || b.d.tile_first) return false;
-    if (st.d.g_hi - sh.tb > 20 || (uint64_t) a.n_tiles < (2ull << (st.d.g_hi - sh.tb))) return false;   // at least two blocks
-    if ((16ull << st.d.g_hi) > (uint64_t) reg->opt_l2_pair_max_block) return false;   // a few blocks must fit the L2
+    if (inb_bits > 20 || (uint64_t) a.n_tiles < (2ull << inb_bits)) return false;          // at least two blocks
+    if (block_bytes > (uint64_t) reg->opt_l2_pair_max_block) return false;                  // a few blocks must fit the L2
     return pipe_smem(sh, a.d.wcol_total + b.d.wcol_total, 0) <= reg->smem_optin;
 }
 
@@ -626,13 +716,21 @@ int qcs_pipeline_launch_pair(qcs_register *reg, const qft::sweep_target &tg, con
     P.ph[1].wcol_base = a.d.wcol_total;
     P.n_phases = 2;
     P.n_tiles = a.n_tiles;
-    P.blk_tile_bits = (a.d.g_lo > a.d.a ? a.d.g_hi : b.d.g_hi) - sh.tb;
+    int inb_pos = 0, inb_bits = 0;
+    uint64_t block_bytes = 0;
+    if (!pair_geometry(sh, a, b, inb_pos, inb_bits, block_bytes)) return QCS_BAD_ARGUMENTS;
+    P.ph[0].inb_pos = P.ph[1].inb_pos = inb_pos;
+    P.ph[0].inb_bits = P.ph[1].inb_bits = inb_bits;
+    P.blk_tile_bits = inb_bits;
     const uint64_t per_block = 1ull << P.blk_tile_bits;
     const uint64_t n_blocks = a.n_tiles >> P.blk_tile_bits;
     // B trails A by one block plus what the chip has in flight (every CTA up to `stages` tiles)
     uint64_t lag = per_block + (uint64_t) reg->opt_l2_pair_lag;
     if (lag > a.n_tiles) lag = a.n_tiles;
     P.lag = lag;
+    P.l2_hints = reg->opt_l2_pair_hints;
+    P.amp = tg.amp;
+    P.direct_store = reg->opt_direct_store;
     // queue head + one counter per block, zeroed in stream order
     const size_t need = 8 + 4 * (size_t) n_blocks;
     if (need > reg->d_pair_cap) {

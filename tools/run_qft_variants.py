@@ -1,6 +1,6 @@
 """Time the inverse QFT at n qubits under a few option settings (one JSON line each).
 
-    python tools/run_qft_variants.py [n] [steps]
+    python tools/run_qft_variants.py [n] [steps] [lag,lag,...]      (QCS_NO_SPLIT3=1: plain layout of the contiguous sweep)
 """
 import json
 import math
@@ -23,11 +23,11 @@ def bitrev(x, bits):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-    variants = [("pair off", {q.OPT_L2_PAIR: 0}),
-                ("pair lag 444", {q.OPT_L2_PAIR: 1}),
-                ("pair lag 148", {q.OPT_L2_PAIR: 1, q.OPT_L2_PAIR_LAG: 148}),
-                ("pair lag 0", {q.OPT_L2_PAIR: 1, q.OPT_L2_PAIR_LAG: 0}),
-                ("pair lag 1024", {q.OPT_L2_PAIR: 1, q.OPT_L2_PAIR_LAG: 1024})]
+    lags = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [444]
+    variants = [("pair off", {q.OPT_L2_PAIR: 0, q.OPT_DIRECT_STORE: 0})]
+    variants += [(f"pair lag {lag}", {q.OPT_L2_PAIR: 1, q.OPT_L2_PAIR_LAG: lag, q.OPT_DIRECT_STORE: 0}) for lag in lags]
+    variants += [("direct store, pair off", {q.OPT_L2_PAIR: 0, q.OPT_DIRECT_STORE: 1})]
+    variants += [(f"direct store, pair lag {lag}", {q.OPT_L2_PAIR: 1, q.OPT_L2_PAIR_LAG: lag, q.OPT_DIRECT_STORE: 1}) for lag in lags]
     N = 1 << n
     with q.Register(n, 0) as reg:
         for name, opts in variants:
