@@ -98,7 +98,7 @@ enum {
     QCS_OPT_OVERLAP_SLICES = 10,
     QCS_OPT_GLOBAL_SMS = 11,
     /* 1 (default): the last strided sweep and the contiguous sweep of a fused transform run as ONE
-     * launch over blocks of <= QCS_OPT_L2_PAIR_MAX_BLOCK bytes (default 32 MiB) whose intermediate
+     * launch over blocks of <= QCS_OPT_L2_PAIR_MAX_BLOCK bytes (default 16 MiB) whose intermediate
      * state stays in the 126 MB L2: the pair reads and writes HBM once.  The second sweep trails the
      * first by one block plus QCS_OPT_L2_PAIR_LAG tiles (default 444 = 3 tiles per SM). */
     QCS_OPT_L2_PAIR = 12,

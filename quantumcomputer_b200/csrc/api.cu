@@ -197,12 +197,13 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->opt_prefetch_tiles = 0;     // measured: L2 prefetch slows the sweep down (profiles/README.md)
     reg->d_meas = nullptr;
     reg->d_pair = nullptr;
+    reg->d_dense = nullptr;
     reg->d_pair_cap = 0;
     reg->opt_l2_pair = 1;
     reg->opt_l2_pair_hints = 1;
     reg->opt_direct_store = 0;
     reg->opt_l2_pair_lag = 3 * 148;
-    reg->opt_l2_pair_max_block = 32ll << 20;
+    reg->opt_l2_pair_max_block = 16ll << 20;     // measured: 32 MiB blocks (n = 30) no longer stay in the L2 (profiles/README.md)
     reg->fusing = 0;
     reg->d_diag = nullptr;
     reg->d_diag_cap = 0;
@@ -240,14 +241,21 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     if (world > 1) {
         rc = qcs_dist_init(reg, comm_id);
         if (rc != QCS_NO_ERROR) { qcs_register_destroy(reg); return rc; }
-        // one address range over all shards (peer.cu); every rank must have it or none
-        const bool mine = qcs_peer_try_alloc(reg, comm_id);
+        // one address range over all shards (peer.cu); every rank must have it or none.  First agree
+        // that every rank can try at all (a rank that opted out would never answer the exchange) ...
         std::vector<double> flags((size_t) world);
-        rc = qcs_dist_allgather_double(reg, mine ? 1.0 : 0.0, flags.data());
+        rc = qcs_dist_allgather_double(reg, qcs_peer_can(reg) ? 1.0 : 0.0, flags.data());
         if (rc != QCS_NO_ERROR) { qcs_register_destroy(reg); return rc; }
         bool all = true;
         for (double f : flags) all = all && f != 0.0;
-        if (!all && mine) qcs_peer_free(reg);
+        if (all) {
+            // ... then that every rank succeeded
+            const bool mine = qcs_peer_try_alloc(reg, comm_id);
+            rc = qcs_dist_allgather_double(reg, mine ? 1.0 : 0.0, flags.data());
+            if (rc != QCS_NO_ERROR) { qcs_register_destroy(reg); return rc; }
+            for (double f : flags) all = all && f != 0.0;
+            if (!all && mine) qcs_peer_free(reg);
+        }
     }
     if (!reg->amp) {
         e = cudaMalloc((void **) &reg->amp, reg->N_local * sizeof(double2));
@@ -292,6 +300,7 @@ extern "C" void qcs_register_destroy(qcs_register *reg)
     if (reg->d_small) cudaFree(reg->d_small);
     if (reg->d_meas) cudaFree(reg->d_meas);
     if (reg->d_pair) cudaFree(reg->d_pair);
+    if (reg->d_dense) cudaFree(reg->d_dense);
     if (reg->d_diag) cudaFree(reg->d_diag);
     if (reg->h_small) cudaFreeHost(reg->h_small);
     if (reg->stream) cudaStreamDestroy(reg->stream);

@@ -112,10 +112,12 @@ extern "C" int qcs_apply_dense_block(qcs_register *reg, unsigned k, const double
                 const int g = lane >> 2, t = lane & 3;
                 frag[(size_t) (mt * KS + s) * 32 + lane] = real[(size_t) (OUT * g + mt) * K2 + PIECE * t + s];
             }
-    double *d_frag = nullptr;
-    QCS_CUDA(cudaMalloc((void **) &d_frag, frag.size() * sizeof(double)));
+    // the fragment buffer lives in the handle (8 KiB covers k = 4): no allocation, no host
+    // synchronisation per call.  The copy is stream-ordered behind the previous call's kernel, and a
+    // pageable source is staged by the runtime before cudaMemcpyAsync returns, so `frag` may go.
+    if (!reg->d_dense) QCS_CUDA(cudaMalloc(&reg->d_dense, 1024 * sizeof(double)));
+    double *d_frag = (double *) reg->d_dense;
     QCS_CUDA(cudaMemcpyAsync(d_frag, frag.data(), frag.size() * sizeof(double), cudaMemcpyHostToDevice, reg->stream));
-    QCS_CUDA(cudaStreamSynchronize(reg->stream));          // frag is a host temporary
     const uint64_t n_groups = reg->N_local >> k;
     uint64_t grid = (n_groups / 8 + 7) / 8;
     const uint64_t cap = (uint64_t) reg->sm_count * 8;
@@ -124,8 +126,5 @@ extern "C" int qcs_apply_dense_block(qcs_register *reg, unsigned k, const double
     qcs_launch_begin(reg, QCS_K_DENSE_BLOCK, 32.0 * (double) reg->N_local);
     if (k == 4) k_dense_block<32><<<(unsigned) grid, 256, 0, reg->stream>>>((double *) reg->amp, n_groups, d_frag);
     else k_dense_block<16><<<(unsigned) grid, 256, 0, reg->stream>>>((double *) reg->amp, n_groups, d_frag);
-    int rc = qcs_launch_end(reg, QCS_K_DENSE_BLOCK, "k_dense_block");
-    cudaStreamSynchronize(reg->stream);
-    cudaFree(d_frag);
-    return rc;
+    return qcs_launch_end(reg, QCS_K_DENSE_BLOCK, "k_dense_block");
 }

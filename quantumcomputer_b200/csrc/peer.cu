@@ -151,7 +151,14 @@ void *serve_fd(void *p)
         if (poll(&pf, 1, 30000) <= 0) break;             // a peer gave up: stop waiting for the rest
         const int c = accept(a->listen_fd, nullptr, nullptr);
         if (c < 0) break;
-        send_fd(c, a->my_fd);
+        // the descriptor gives read/write access to the shard: only a process of the same user gets it
+        ucred cred = {};
+        socklen_t cl = sizeof cred;
+        if (getsockopt(c, SOL_SOCKET, SO_PEERCRED, &cred, &cl) == 0 && cred.uid == geteuid()) {
+            send_fd(c, a->my_fd);
+        } else {
+            k--;                                         // not one of the peers: keep waiting for them
+        }
         close(c);
     }
     return nullptr;
@@ -206,6 +213,23 @@ void release(qcs_peer *p)
 }
 
 }  // namespace
+
+// Can this rank take part in a stitched mapping at all?  No side effects; the ranks agree on the
+// answer (api.cu) BEFORE the descriptor exchange, so that a rank that cannot never leaves the
+// others waiting on its socket.
+bool qcs_peer_can(const qcs_register *reg)
+{
+    if (getenv("QCS_NO_PEER_MEMORY")) return false;
+    if (!load_driver()) return false;
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = reg->device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t gran = 0;
+    if (g_drv.MemGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) return false;
+    return ((size_t) reg->N_local * sizeof(double2)) % gran == 0;
+}
 
 // Tries to build the stitched mapping.  Returns true and sets reg->peer / amp / amp_all on
 // success; false (nothing allocated) otherwise.  Collective over the ranks only through the

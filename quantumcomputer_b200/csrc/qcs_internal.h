@@ -46,6 +46,7 @@ struct qcs_register {
     void *d_small;          // 4 KiB device scratch (measurement result etc.)
     void *h_small;          // 4 KiB pinned host mirror
     void *d_meas;           // chunk summaries of the exact parallel measurement scan (lazy)
+    void *d_dense;          // A-fragment buffer of qcs_apply_dense_block (lazy, 8 KiB)
     void *d_pair;           // ticket + per-block counters of an L2-paired sweep launch (lazy)
     size_t d_pair_cap;      // bytes
 
@@ -214,5 +215,6 @@ cudaStream_t qcs_dist_side_stream(qcs_register *reg);       // second stream of 
 int qcs_dist_slice_event(qcs_register *reg, int j, cudaEvent_t *ev);
 
 // ---- peer memory: peer.cu ----------------------------------------------------
+bool qcs_peer_can(const qcs_register *reg);
 bool qcs_peer_try_alloc(qcs_register *reg, const void *comm_id);
 void qcs_peer_free(qcs_register *reg);

@@ -508,8 +508,9 @@ int launch_mode(qcs_register *reg, const CUtensorMap &tmap0, const CUtensorMap &
     uint64_t grid = (uint64_t) reg->sm_count;
     if (tg.max_ctas > 0 && grid > (uint64_t) tg.max_ctas) grid = (uint64_t) tg.max_ctas;
     if (grid > P.n_tiles) grid = P.n_tiles;
-    // a paired launch moves the state through HBM once (read by A, written by B) and does two sweeps' work
-    qcs_launch_begin(reg, tg.kind, tg.bytes > 0.0 ? tg.bytes : 32.0 * (double) (P.n_tiles << TB));
+    // algorithmic bytes = sweeps made x 32 B per amplitude; a paired launch makes two sweeps
+    // (its DRAM traffic is lower: the intermediate state stays in the L2)
+    qcs_launch_begin(reg, tg.kind, tg.bytes > 0.0 ? tg.bytes : 32.0 * (double) P.n_phases * (double) (P.n_tiles << TB));
     kern<<<(unsigned) grid, 64 + GROUPS * GT, smem, tg.stream>>>(tmap0, tmap1, P);
     return qcs_launch_end(reg, tg.kind, "k_qft_sweep_tma");
 }
