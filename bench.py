@@ -492,15 +492,13 @@ def north_star_block(q, ranks, args, peak, peak_src):
     return out
 
 
-def run_shor(q, ranks, args):
+def shor_block(q, ranks, args, with_n30=True):
     """BASELINE configs[0] / [1]: wall time of the quantum half of find_period (qc_shor.c:922-928:
     reset_register, quantum_computation, measure_state) through the C ABI, beside the reference's
     own time for the same calls on the host, the measured index compared run by run; plus one
     n = 30 quantum_computation (L = 18, M = 12) for the throughput of the modular-exponentiation sweep."""
     from quantumcomputer_b200.workloads import mt19937_uniforms
     import numpy as np
-    if ranks.world != 1:
-        raise SystemExit("--workload shor is a single-GPU workload")
     import oracle
     if not oracle.have_restatement():
         oracle.build()
@@ -549,6 +547,8 @@ def run_shor(q, ranks, args):
                       "cpu_ms_per_find_period": 1e3 * float(np.median(t_cpu)), "cpu_runs": cpu_runs,
                       "cpu_kind": "reference" if use_ref else "port", "cpu_cores": 1,
                       "measured_indices_identical": got[:cpu_runs] == want, "indices": got[:8]})
+    if not with_n30:
+        return {"find_period": cases, "parity": {"ok": bool(all(c["measured_indices_identical"] for c in cases))}}
     # ---- n = 30: the modular exponentiation as one block-local sweep
     L, M, Cn, a = 18, 12, 4087, 7                                 # 4087 = 61 * 67 < 2^12
     with q.Register(L, M, device=ranks.local_rank) as reg:
@@ -585,10 +585,60 @@ def run_shor(q, ranks, args):
                          "bytes_model": "32 * 2^n * C / 2^M B per launch (read + write the rows f < C of every block)"},
             "kernels": per_class, "gpu_launches": int(launches),
             "find_period": cases, "parity": {"ok": bool(ok)}}
+    return line
+
+
+def run_shor(q, ranks, args):
+    if ranks.world != 1:
+        raise SystemExit("--workload shor is a single-GPU workload")
+    line = shor_block(q, ranks, args)
     print(json.dumps(line), flush=True)
     ranks.close()
-    if not ok:
+    if not line["parity"]["ok"]:
         raise SystemExit(3)
+
+
+def layered_block(q, ranks, args, peak, peak_src):
+    """BASELINE configs[3] in the default run: the layered H / C-phase circuit at n = 33 on one GPU,
+    issued gate by gate inside qcs_fuse_begin / qcs_fuse_end; checked by applying the inverse circuit."""
+    import numpy as np
+    from quantumcomputer_b200.workloads import apply_gates, layered_circuit
+    n, layers = 33, args.layers
+    circuit = layered_circuit(n, layers)
+    inverse = [g if g[0] == "h" else ("cp", g[1], g[2], -g[3]) for g in reversed(circuit)]
+    with q.Register(n, 0, device=ranks.local_rank) as reg:
+        apply_tuning(q, reg, args)
+        reg.fill_synthetic(SEED)
+        reg.scale(1.0 / math.sqrt(reg.norm2()))
+        nl = reg.local_states
+        probes = [0, 1, nl - 1, nl // 2 + 9, nl // 3, (nl // 7) * 5, 123456789, nl // 5 + 1]
+        before = np.array([reg.get_state(i, 1)[0] for i in probes])
+
+        def one_step():
+            with reg.fused():
+                apply_gates(reg, circuit)
+
+        steps = max(1, min(args.steps, 3))
+        ms, prof, launches, _ = timed_steps(q, reg, ranks, one_step, steps, 1, False)
+        norm_out = reg.norm2()
+        # undo the (steps + 1) applications: the round trip restores the state
+        for _ in range(steps + 1):
+            with reg.fused():
+                apply_gates(reg, inverse)
+        after = np.array([reg.get_state(i, 1)[0] for i in probes])
+        err = float(np.max(np.abs(after - before))) * math.sqrt(float(1 << n))
+    gates = len(circuit)
+    return {"workload": f"layered circuit (BASELINE configs[3]): {layers} layers of H on every qubit + C-phase on "
+                        f"(q, (q+1+d) mod n), n={n}, {gates} gates per step, gate by gate inside qcs_fuse_begin/end",
+            "qubits": n, "gates_per_step": gates, "steps": steps, "warmup": 1, "ms_per_step": ms / steps,
+            "gates_per_sec": gates * steps / (ms * 1e-3), "gpu_launches": int(launches),
+            "parity": {"ok": bool(err <= 1e-11 and abs(norm_out - 1.0) < 1e-10),
+                       "round_trip_max_rel_err": err, "norm_after": norm_out,
+                       "what": "circuit^steps followed by its inverse^steps restores 8 probed amplitudes"},
+            "roofline": roofline_from_profile(prof, n, 1, False, peak, peak_src),
+            "kernels": {kk: {"launches": v[0], "ms": round(v[1], 4),
+                             "GBps": round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] > 0 else None}
+                        for kk, v in prof.items() if v[0]}}
 
 
 def run_ours(args):
@@ -659,7 +709,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         local = reg.local_states
-        pinned = q.PinnedBuffer(2 * local)
+        pinned = q.PinnedBuffer(2 * local, device=local_rank)       # pages next to this rank's GPU
         reg.get_state(0, local, out=pinned.array)          # a normalised host-resident input
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         ranks.barrier(reg)
@@ -731,6 +781,19 @@ def run_ours(args):
             if not ns["parity"]["ok"]:
                 line["error"] = "north_star parity check failed"
 
+    # ---- the other single-GPU configs of BASELINE.json, in the same run (N = 1 only)
+    if circuit is None and world == 1 and not args.qubits and not args.no_configs:
+        blocks = {}
+        try:
+            blocks["shor"] = shor_block(q, ranks, args, with_n30=False)
+            blocks["layered_n33"] = layered_block(q, ranks, args, peak, peak_src)
+        except Exception as exc:                       # never take the headline line down
+            blocks["error"] = repr(exc)
+        line["configs"] = blocks
+        for name in ("shor", "layered_n33"):
+            if name in blocks and not blocks[name]["parity"]["ok"]:
+                line["error"] = f"{name} parity check failed"
+
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
@@ -765,6 +828,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity block")
     ap.add_argument("--no-north-star", action="store_true", help="skip the n = 33/34/35 block")
+    ap.add_argument("--no-configs", action="store_true", help="skip the Shor cfg1/cfg2 and layered n = 33 blocks (N = 1)")
     ap.add_argument("--north-star-steps", type=int, default=5)
     ap.add_argument("--l2-pair", type=int, default=-1)
     ap.add_argument("--keep-permuted", type=int, default=-1)

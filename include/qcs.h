@@ -317,6 +317,9 @@ unsigned long long qcs_modpow2k(unsigned a, unsigned k, unsigned C);
 
 /* pinned host memory for qcs_get_state / qcs_set_state */
 int qcs_host_alloc(void **ptr, size_t bytes);
+/* the same, with the pages placed on the NUMA node next to `device` (host <-> device copies of
+ * several GPUs then do not share one memory controller / socket link) */
+int qcs_host_alloc_near(void **ptr, size_t bytes, int device);
 int qcs_host_free(void *ptr);
 
 /* ---- measurement of the engine itself ----------------------------------- */

@@ -114,9 +114,13 @@ def comm_unique_id():
 class PinnedBuffer:
     """Page-locked host memory viewed as a numpy float64 array."""
 
-    def __init__(self, n_doubles):
+    def __init__(self, n_doubles, device=-1):
+        """device >= 0: pages on the NUMA node next to that GPU (qcs_host_alloc_near)."""
         self._ptr = C.c_void_p()
-        _check(lib().qcs_host_alloc(C.byref(self._ptr), n_doubles * 8), "qcs_host_alloc")
+        if device >= 0:
+            _check(lib().qcs_host_alloc_near(C.byref(self._ptr), n_doubles * 8, device), "qcs_host_alloc_near")
+        else:
+            _check(lib().qcs_host_alloc(C.byref(self._ptr), n_doubles * 8), "qcs_host_alloc")
         arr_t = C.c_double * n_doubles
         self.array = np.frombuffer(arr_t.from_address(self._ptr.value), dtype=np.float64)
 

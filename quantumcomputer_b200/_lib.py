@@ -68,6 +68,7 @@ SIGNATURES = [
     ("qcs_int_pow", _u, [_u, _u]),
     ("qcs_modpow2k", _ull, [_u, _u, _u]),
     ("qcs_host_alloc", C.c_int, [C.POINTER(_vp), C.c_size_t]),
+    ("qcs_host_alloc_near", C.c_int, [C.POINTER(_vp), C.c_size_t, C.c_int]),
     ("qcs_host_free", C.c_int, [_vp]),
     ("qcs_timer_start", C.c_int, [_vp]),
     ("qcs_timer_stop", C.c_int, [_vp, _dp]),

@@ -2,8 +2,10 @@
 // (local vs. global qubits), composite operators and bookkeeping.
 #include "qcs_internal.h"
 
+#include <ctype.h>
 #include <math.h>
 #include <new>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -119,6 +121,46 @@ extern "C" int qcs_host_alloc(void **ptr, size_t bytes)
 {
     if (!ptr) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return QCS_NO_ERROR;
+}
+
+// Pinned memory close to a device: pages are placed on the NUMA node of the CPU that allocates
+// them, so the calling thread is moved onto the CPUs next to the device's PCIe root (sysfs) for the
+// duration of the allocation.  Falls back to qcs_host_alloc wherever the topology cannot be read.
+extern "C" int qcs_host_alloc_near(void **ptr, size_t bytes, int device)
+{
+    if (!ptr) return QCS_BAD_ARGUMENTS;
+    cpu_set_t old_set, near_set;
+    bool moved = false;
+    char bdf[32] = {0};
+    if (device >= 0 && cudaDeviceGetPCIBusId(bdf, (int) sizeof bdf, device) == cudaSuccess &&
+        sched_getaffinity(0, sizeof old_set, &old_set) == 0) {
+        for (char *c = bdf; *c; c++) *c = (char) tolower(*c);
+        char path[128];
+        snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bdf);
+        FILE *f = fopen(path, "r");
+        if (f) {
+            char list[4096] = {0};
+            if (fgets(list, (int) sizeof list, f)) {
+                CPU_ZERO(&near_set);
+                int n_set = 0;
+                for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+                    int a = 0, b = 0;
+                    const int k = sscanf(tok, "%d-%d", &a, &b);
+                    if (k == 1) b = a;
+                    if (k >= 1)
+                        for (int cpu = a; cpu <= b && cpu < CPU_SETSIZE; cpu++)
+                            if (CPU_ISSET(cpu, &old_set)) { CPU_SET(cpu, &near_set); n_set++; }
+                }
+                if (n_set > 0 && sched_setaffinity(0, sizeof near_set, &near_set) == 0) moved = true;
+            }
+            fclose(f);
+        }
+    }
+    // pinning populates the pages now, on the node of the CPU this thread runs on
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+    if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+    if (e != cudaSuccess) return qcs_map_cuda_error(e, "cudaHostAlloc", __FILE__, __LINE__);
     return QCS_NO_ERROR;
 }
 
@@ -640,7 +682,7 @@ static int locate_state(qcs_register *reg, double r, uint64_t *out_index)
         // super-chunk maps.  Only the exact running sum is handed from shard to shard in index order,
         // one packed all-gather {sum, found, index, error code} per shard.
         const uint64_t limit = reg->rank == reg->world - 1 ? reg->N_local - 1 : reg->N_local;
-        const bool parallel = qcs_k_scan_parallel_ok(reg, limit);
+        const bool parallel = qcs_k_scan_parallel_ok(reg, reg->N_local);     // the same decision on every shard (limit differs on the last one)
         std::vector<double> all((size_t) reg->world * 4);
         int rc = QCS_NO_ERROR;
         if (parallel) {
