@@ -38,18 +38,20 @@ def qft_gate_count(n):
 
 def profiled_traffic(n):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the tile-sweep kernel from the
-    committed `ncu --set full` capture of the same workload (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_qft_sweep_tma_t12_n30.csv")
+    committed `ncu --set full` capture of the same workload (profiles/, summarised by
+    tools/ncu_summary.py), or None.  Not measured in this run: the line says so."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_qft_sweeps_n30.csv")
     if n != 30 or not os.path.exists(path):
         return None, None
     try:
         import csv
         with open(path) as f:
             rows = list(csv.reader(f))
-        hdr = rows[0]
+        hdr, units = rows[0], rows[1]
         rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-        per = [float(r[rd]) + float(r[wr]) for r in rows[2:] if len(r) > wr]
-        return 1e9 * sum(per) / len(per), os.path.relpath(path, ROOT)
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        per = [float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]] for r in rows[2:] if len(r) > wr]
+        return sum(per) / len(per), os.path.relpath(path, ROOT)
     except Exception:
         return None, None
 

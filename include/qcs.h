@@ -315,6 +315,10 @@ unsigned qcs_int_pow(unsigned base, unsigned power);
 /* a^(2^k) mod C */
 unsigned long long qcs_modpow2k(unsigned a, unsigned k, unsigned C);
 
+/* Host-only self-check of the L2-paired launch bookkeeping (ticket order, block closure) for the sweeps
+ * of an inverse transform on qubits [lo, hi) of a 2^n_qubits shard: pairs checked, or < 0 on a violation */
+long long qcs_pair_selfcheck(unsigned n_qubits, unsigned lo, unsigned hi, int lag_tiles);
+
 /* pinned host memory for qcs_get_state / qcs_set_state */
 int qcs_host_alloc(void **ptr, size_t bytes);
 /* the same, with the pages placed on the NUMA node next to `device` (host <-> device copies of

@@ -59,6 +59,7 @@ SIGNATURES = [
     ("qcs_load_state", C.c_int, [_vp, C.c_char_p]),
     ("qcs_schedule_describe", C.c_int, [_u, C.c_int, C.c_int, _ull, _vp, _vp, _vp, _vp, _ull]),
     ("qcs_plan_describe", C.c_int, [_u, _u, _u, C.c_int, C.c_int, _vp, _ull]),
+    ("qcs_pair_selfcheck", C.c_longlong, [_u, _u, _u, C.c_int]),
     ("qcs_fuse_begin", C.c_int, [_vp]),
     ("qcs_fuse_end", C.c_int, [_vp]),
     ("qcs_fuse_pending", _ull, [_vp]),

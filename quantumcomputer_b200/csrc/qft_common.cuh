@@ -194,6 +194,9 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
     const unsigned n_cols = 1u << (t - S.r);
     const unsigned low_mask = (1u << S.s) - 1u;
     const unsigned lin_stride = 1u << S.s;
+    // XOR swizzle e ^ ((e >> sw) & 7): a step whose digit lies above bit sw + 3 does not change the XOR
+    // term, so its elements are lin_stride apart behind the swizzled column base
+    const bool swz_linear = !LIN && S.s >= G.sw + 3;
     for (unsigned c = tid; c < n_cols; c += nthreads) {
         const unsigned e_base = ((c >> S.s) << (S.s + S.r)) | (c & low_mask);
         double2 *g = amp + base + G.spread(e_base);
@@ -208,9 +211,20 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
                 for (int d = 0; d < R; d++) x[d] = g[(uint64_t) d * g_stride];
             }
         } else if (LIN) {
+            // a running pointer: one add per element
             const double2 *col = tile + e_base;
 #pragma unroll
-            for (int d = 0; d < R; d++) x[d] = col[(unsigned) d * lin_stride];
+            for (int d = 0; d < R; d++) {
+                x[d] = *col;
+                col += lin_stride;
+            }
+        } else if (swz_linear) {
+            const double2 *col = tile + G.swz(e_base);
+#pragma unroll
+            for (int d = 0; d < R; d++) {
+                x[d] = *col;
+                col += lin_stride;
+            }
         } else {
 #pragma unroll
             for (int d = 0; d < R; d++) x[d] = tile[G.swz(e_base + ((unsigned) d << S.s))];
@@ -267,7 +281,17 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
         } else if (LIN) {
             double2 *col = tile + e_base;
 #pragma unroll
-            for (int d = 0; d < R; d++) col[(unsigned) d * lin_stride] = x[d];
+            for (int d = 0; d < R; d++) {
+                *col = x[d];
+                col += lin_stride;
+            }
+        } else if (swz_linear) {
+            double2 *col = tile + G.swz(e_base);
+#pragma unroll
+            for (int d = 0; d < R; d++) {
+                *col = x[d];
+                col += lin_stride;
+            }
         } else {
 #pragma unroll
             for (int d = 0; d < R; d++) tile[G.swz(e_base + ((unsigned) d << S.s))] = x[d];

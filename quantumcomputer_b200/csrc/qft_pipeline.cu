@@ -193,20 +193,20 @@ __device__ __forceinline__ void tile_coords(const phase_params &Q, uint64_t tix,
 
 // first amplitude of tile tix
 template <int TB>
-__device__ __forceinline__ uint64_t tile_base(const phase_params &Q, uint64_t tix)
+__host__ __device__ __forceinline__ uint64_t tile_base(const phase_params &Q, uint64_t tix)
 {
     return Q.lo_gap >= 0 ? (((tix >> Q.lo_gap) << Q.d.g_hi) | ((tix & ((1ull << Q.lo_gap) - 1ull)) << Q.d.a)) : (tix << TB);
 }
 
 // item of a paired launch (block-major: block * tiles_per_block + tile in block) -> tile number
-__device__ __forceinline__ uint64_t pair_tile(const pipe_params &P, const phase_params &Q, uint64_t idx)
+__host__ __device__ __forceinline__ uint64_t pair_tile(const pipe_params &P, const phase_params &Q, uint64_t idx)
 {
     const uint64_t inb = idx & ((1ull << P.blk_tile_bits) - 1ull), blk = idx >> P.blk_tile_bits;
     return ((blk >> Q.inb_pos) << (Q.inb_pos + Q.inb_bits)) | (inb << Q.inb_pos) | (blk & ((1ull << Q.inb_pos) - 1ull));
 }
 
 // the t-th ticket of a paired launch -> phase bit | item within the phase
-__device__ __forceinline__ uint64_t pair_item(const pipe_params &P, uint64_t t)
+__host__ __device__ __forceinline__ uint64_t pair_item(const pipe_params &P, uint64_t t)
 {
     const uint64_t na = P.n_tiles, lag = P.lag;
     if (t >= 2 * na) return kNoItem;
@@ -244,7 +244,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], 2);          // the producer's expect_tx and its arrive once the tile's bases are written
             mbar_init(&computed[s], 1);
             mbar_init(&empty[s], 1);
         }
@@ -301,6 +301,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
                 if (lane == 0) {
                     s_item[s] = kNoItem;
                     mbar_arrive(&full[s]);
+                    mbar_arrive(&full[s]);
                 }
                 if (++sentinels == GROUPS) break;
                 continue;
@@ -309,16 +310,8 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             const phase_params &Q = P.ph[ph];
             const uint64_t idx = item & (kPhaseB - 1ull);
             const uint64_t tix = paired ? pair_tile(P, Q, idx) : tile_number(Q.d, idx);
-            if (!Q.d.hadamard_only && lane < Q.d.n_steps) {
-                const sweep_step S = Q.d.step[lane];
-                const uint64_t base = tile_base<TB>(Q, tix);
-                uint64_t y = 0;
-                if (S.low_phys > Q.d.lo) y = (base & ((1ull << S.low_phys) - 1ull)) >> Q.d.lo;
-                wbase[s * kMaxSteps + lane] = unit_phase(y + Q.d.y_const, S.j, Q.d.inverse != 0);
-            }
-            __syncwarp();
+            // the loads go out first; the tile's twiddle bases are computed while they travel
             if (lane == 0) {
-                s_item[s] = item;
                 if (ph == 1) {
                     // all A tiles of the block must be in L2 / memory
                     const unsigned *flag = P.done + (idx >> P.blk_tile_bits);
@@ -343,6 +336,18 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
                 }
                 // the next ticket travels while this tile loads
                 if (paired) next = pair_item(P, atomicAdd(P.ticket, 1ull));
+            }
+            if (!Q.d.hadamard_only && lane < Q.d.n_steps) {
+                const sweep_step S = Q.d.step[lane];
+                const uint64_t base = tile_base<TB>(Q, tix);
+                uint64_t y = 0;
+                if (S.low_phys > Q.d.lo) y = (base & ((1ull << S.low_phys) - 1ull)) >> Q.d.lo;
+                wbase[s * kMaxSteps + lane] = unit_phase(y + Q.d.y_const, S.j, Q.d.inverse != 0);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                s_item[s] = item;
+                mbar_arrive(&full[s]);           // second arrival: what the consumers read besides the tile is in place
             }
         }
     } else if (warp == 1) {
@@ -746,4 +751,99 @@ int qcs_pipeline_launch_pair(qcs_register *reg, const qft::sweep_target &tg, con
     P.ticket = (unsigned long long *) reg->d_pair;
     P.done = (unsigned *) ((unsigned char *) reg->d_pair + 8);
     return run_launch(reg, sh, shape_id, tmap0, tmap1, P, pipe_smem(sh, a.d.wcol_total + b.d.wcol_total, 0), tg);
+}
+
+
+// Host-only self-check of the paired-launch bookkeeping for tests (no device work): plans the inverse
+// transform on qubits [lo, hi) of an n_qubits shard with the default shape, pairs the sweeps the way
+// launch_plans does, and verifies for every pair that
+//   * the ticket order hands out every tile of both sweeps exactly once, and a tile of the second sweep
+//     only after `lag` >= one block of tiles of the first sweep were handed out before the first tile of
+//     its block's successor ... precisely: after every first-sweep tile of its own block;
+//   * in sampled blocks, the tiles of the first sweep and the tiles of the second sweep cover exactly the
+//     same set of amplitudes (the block is closed under both sweeps).
+// Returns the number of pairs checked (>= 0) or a negative number describing the first violation.
+extern "C" long long qcs_pair_selfcheck(unsigned n_qubits, unsigned lo, unsigned hi, int lag_tiles)
+{
+    if (n_qubits < 15 || n_qubits > 40 || lo >= hi || hi > n_qubits) return -1;
+    qcs_register fake = {};
+    fake.n = fake.n_local = n_qubits;
+    fake.N = fake.N_local = 1ull << n_qubits;
+    fake.world = 1;
+    fake.opt_pipeline = 1;
+    fake.opt_pipe_shape = -1;
+    fake.opt_min_run_bits = 3;
+    fake.opt_l2_pair = 1;
+    fake.opt_l2_pair_lag = lag_tiles;
+    fake.opt_l2_pair_max_block = 16ll << 20;
+    fake.smem_optin = 232448;
+    const pipe_shape sh = shape_of(&fake);
+    std::vector<qft::sweep_plan> plans;
+    qft::plan_inverse(n_qubits, lo, hi, sh.tb, fake.opt_min_run_bits, plans);
+    const qft::sweep_target tg = {nullptr, n_qubits, nullptr};
+    long long pairs = 0;
+    for (size_t k = 0; k + 1 < plans.size(); k++) {
+        if (!qcs_pipeline_pair_supported(&fake, tg, plans[k], plans[k + 1])) continue;
+        const qft::sweep_plan &a = plans[k], &b = plans[k + 1];
+        pipe_params P = {};
+        int inb_pos = 0, inb_bits = 0;
+        uint64_t block_bytes = 0;
+        if (!pair_geometry(sh, a, b, inb_pos, inb_bits, block_bytes)) return -2;
+        const qft::sweep_plan *pl[2] = {&a, &b};
+        for (int ph = 0; ph < 2; ph++) {
+            P.ph[ph].d = pl[ph]->d;
+            P.ph[ph].lo_gap = pl[ph]->d.g_lo > pl[ph]->d.a ? pl[ph]->d.g_lo - pl[ph]->d.a : -1;
+            P.ph[ph].inb_pos = inb_pos;
+            P.ph[ph].inb_bits = inb_bits;
+        }
+        P.n_phases = 2;
+        P.n_tiles = a.n_tiles;
+        P.blk_tile_bits = inb_bits;
+        const uint64_t per_block = 1ull << inb_bits;
+        P.lag = per_block + (uint64_t) lag_tiles;
+        if (P.lag > P.n_tiles) P.lag = P.n_tiles;
+        // --- ticket order (on a truncated problem so the check stays cheap: the order only depends on n_tiles and lag)
+        const uint64_t n_tiles_checked = P.n_tiles > (1ull << 16) ? (1ull << 16) : P.n_tiles;
+        pipe_params Pq = P;
+        Pq.n_tiles = n_tiles_checked;
+        if (Pq.lag > Pq.n_tiles) Pq.lag = Pq.n_tiles;
+        std::vector<unsigned char> seen_a((size_t) n_tiles_checked, 0), seen_b((size_t) n_tiles_checked, 0);
+        std::vector<uint64_t> done_a((size_t) (n_tiles_checked >> inb_bits) + 1, 0);
+        for (uint64_t t = 0; t < 2 * n_tiles_checked; t++) {
+            const uint64_t item = pair_item(Pq, t);
+            if (item == kNoItem) return -3;
+            const uint64_t idx = item & (kPhaseB - 1ull);
+            if (idx >= n_tiles_checked) return -4;
+            if (item & kPhaseB) {
+                if (seen_b[(size_t) idx]++) return -5;
+                if (done_a[(size_t) (idx >> inb_bits)] != per_block) return -6;      // a B tile before its block's A tiles
+            } else {
+                if (seen_a[(size_t) idx]++) return -7;
+                done_a[(size_t) (idx >> inb_bits)]++;
+            }
+        }
+        if (pair_item(Pq, 2 * n_tiles_checked) != kNoItem) return -8;
+        // --- block closure in a few blocks: XOR / sum fingerprints of the amplitude sets of both sweeps
+        const uint64_t n_blocks = P.n_tiles >> inb_bits;
+        const uint64_t sample[4] = {0, 1 % n_blocks, n_blocks / 2, n_blocks - 1};
+        for (uint64_t blk : sample) {
+            uint64_t fp[2][2] = {{0, 0}, {0, 0}};
+            for (int ph = 0; ph < 2; ph++) {
+                const phase_params &Q = P.ph[ph];
+                for (uint64_t inb = 0; inb < per_block; inb++) {
+                    const uint64_t tix = pair_tile(P, Q, (blk << inb_bits) | inb);
+                    const uint64_t base = sh.tb == 12 ? tile_base<12>(Q, tix) : tile_base<11>(Q, tix);
+                    for (unsigned e = 0; e < (1u << sh.tb); e++) {
+                        const uint64_t i = base + ((uint64_t) (e & ((1u << Q.d.a) - 1u)) | ((uint64_t) (e >> Q.d.a) << Q.d.g_lo));
+                        fp[ph][0] ^= i * 0x9E3779B97F4A7C15ull;
+                        fp[ph][1] += i * i + 1;
+                    }
+                }
+            }
+            if (fp[0][0] != fp[1][0] || fp[0][1] != fp[1][1]) return -9;
+        }
+        pairs++;
+        k++;
+    }
+    return pairs;
 }

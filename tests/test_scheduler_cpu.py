@@ -163,3 +163,16 @@ def test_sweep_counts_of_the_benchmark_sizes(qcs):
     assert len(qcs.plan_describe(33, tile_bits=11, min_run_bits=4)) == 5
     with pytest.raises(qcs.QcsError):
         qcs.plan_describe(10, 5, 5)
+
+
+@pytest.mark.parametrize("n,lo,expect_pairs", [(24, 0, 1), (28, 0, 1), (30, 0, 0), (31, 0, 1), (33, 0, 2), (35, 0, 2), (36, 0, 2),
+                                               (33, 5, None), (27, 4, None)])
+def test_l2_paired_launch_bookkeeping(qcs, n, lo, expect_pairs):
+    """Host-only check of the paired-sweep launch (qft_pipeline.cu): the ticket order hands out every tile
+    of both sweeps once and a second-sweep tile only after all first-sweep tiles of its block, and the tiles
+    of both sweeps of a block cover the same amplitudes -- for several lags."""
+    for lag in (0, 7, 148, 444, 100000):
+        got = qcs.lib().qcs_pair_selfcheck(n, lo, n, lag)
+        assert got >= 0, (n, lo, lag, got)
+        if expect_pairs is not None:
+            assert got == expect_pairs, (n, lag, got)
