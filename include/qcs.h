@@ -107,9 +107,10 @@ enum {
     /* 1 (default): the TMA loads and stores of a paired launch carry L2 eviction-priority hints
      * (evict_last for what the second sweep reads, evict_first for the rest) */
     QCS_OPT_L2_PAIR_HINTS = 15,
-    /* 1: the last step of every tile of a pipelined sweep stores straight from registers to global
-     * memory (ld/st unit) instead of going back through shared memory and a TMA store */
-    QCS_OPT_DIRECT_STORE = 16
+    /* 16: reserved (direct stores from registers were measured slower and removed) */
+    /* 1 (default): a contiguous 2^12 tile whose steps are radix-16 at bits 8, 4, 0 is held in the
+     * split-3 shared-memory layout (bank-conflict free; qft_common.cuh); 0: plain 128-byte swizzle */
+    QCS_OPT_SPLIT3 = 17
 };
 
 /* kernel classes reported by qcs_profile_get */

@@ -18,7 +18,8 @@ NO_ERROR, INSUFFICIENT_MEMORY, BAD_ARGUMENTS, PERIOD_NOT_FOUND, UNKNOWN_ERROR = 
 POW_VERBATIM, POW_MODULAR = 0, 1
 OPT_FUSION, OPT_PROFILE, OPT_TILE_BITS, OPT_MEASURE_SEQUENTIAL, OPT_PIPELINE, OPT_PREFETCH_TILES = 1, 2, 3, 4, 5, 6
 OPT_PIPE_SHAPE, OPT_MIN_RUN_BITS, OPT_GLOBAL_RUN_BITS, OPT_OVERLAP_SLICES, OPT_GLOBAL_SMS = 7, 8, 9, 10, 11
-OPT_L2_PAIR, OPT_L2_PAIR_LAG, OPT_L2_PAIR_MAX_BLOCK, OPT_L2_PAIR_HINTS, OPT_DIRECT_STORE = 12, 13, 14, 15, 16
+OPT_L2_PAIR, OPT_L2_PAIR_LAG, OPT_L2_PAIR_MAX_BLOCK, OPT_L2_PAIR_HINTS = 12, 13, 14, 15
+OPT_SPLIT3 = 17
 KERNEL_CLASSES = ["hadamard", "cphase", "amodc", "fill", "reduce", "tile_sweep",
                   "modexp_sweep", "exchange", "scale", "dense_block", "diag_multi", "global_sweep", "gate_1q"]
 

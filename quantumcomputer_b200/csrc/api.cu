@@ -243,7 +243,7 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->d_pair_cap = 0;
     reg->opt_l2_pair = 1;
     reg->opt_l2_pair_hints = 1;
-    reg->opt_direct_store = 0;
+    reg->opt_split3 = 1;
     reg->opt_l2_pair_lag = 3 * 148;
     reg->opt_l2_pair_max_block = 16ll << 20;     // measured: 32 MiB blocks (n = 30) no longer stay in the L2 (profiles/README.md)
     reg->fusing = 0;
@@ -408,7 +408,7 @@ extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
             reg->opt_l2_pair_lag = (int) value;
             return QCS_NO_ERROR;
         case QCS_OPT_L2_PAIR_HINTS: reg->opt_l2_pair_hints = value != 0; return QCS_NO_ERROR;
-        case QCS_OPT_DIRECT_STORE: reg->opt_direct_store = value != 0; return QCS_NO_ERROR;
+        case QCS_OPT_SPLIT3: reg->opt_split3 = value != 0; return QCS_NO_ERROR;
         case QCS_OPT_L2_PAIR_MAX_BLOCK:
             if (value < (1 << 20)) return QCS_BAD_ARGUMENTS;
             reg->opt_l2_pair_max_block = value;
@@ -437,7 +437,7 @@ extern "C" long long qcs_get_option(const qcs_register *reg, int option)
         case QCS_OPT_L2_PAIR_LAG: return reg->opt_l2_pair_lag;
         case QCS_OPT_L2_PAIR_MAX_BLOCK: return reg->opt_l2_pair_max_block;
         case QCS_OPT_L2_PAIR_HINTS: return reg->opt_l2_pair_hints;
-        case QCS_OPT_DIRECT_STORE: return reg->opt_direct_store;
+        case QCS_OPT_SPLIT3: return reg->opt_split3;
         default: return -1;
     }
 }

@@ -65,7 +65,7 @@ struct qcs_register {
     int opt_measure_sequential;   // 1: always use the single-CTA sequential scan
     int opt_l2_pair;              // 1: the last strided sweep and the contiguous sweep of a transform share one launch
                                   // whose intermediate state stays in L2 (qft_pipeline.cu)
-    int opt_direct_store;         // 1: pipelined sweeps store their last step straight from registers (no TMA store)
+    int opt_split3;               // 1: contiguous 2^12 tiles of radix-16 steps use the conflict-free split-3 layout
     int opt_l2_pair_hints;        // 1: L2 eviction-priority hints on the TMA traffic of a paired launch
     int opt_l2_pair_lag;          // tiles the second sweep of a pair trails the first by, beyond one block
     long long opt_l2_pair_max_block;   // largest block (bytes) a paired launch may use

@@ -171,6 +171,26 @@ __device__ __forceinline__ void st256(double2 *p, double2 lo, double2 hi)
 // Shared-memory position (in amplitudes) of tile-local element e: e ^ ((e >> sw) & 7); sw = 28: linear
 __host__ __device__ __forceinline__ unsigned tile_phys(unsigned e, int sw) { return e ^ ((e >> sw) & 7u); }
 
+// The SPLIT-3 layout of a contiguous 2^t tile: TMA brings it in as a 3-D box {8 amplitudes} x {e >> 4} x
+// {bit 3 of e} with the 128-byte hardware swizzle, so bit 3 of the index moves to the top of the tile
+// address and the 16-byte chunk is XORed with bits 4..6 of e.  Every radix-16 step -- also the one on bits
+// 0..3, which the plain swizzle e ^ ((e >> 3) & 7) serves with a 2-way bank conflict -- then touches 8
+// distinct bank groups per quarter warp.  The map is GF(2)-linear: phys(e_base | d << s) = phys(e_base) ^ phys(d << s).
+constexpr int kSwizzleSplit3 = 64;          // sweep_desc::sw value that selects it
+__host__ __device__ __forceinline__ unsigned split3_phys(unsigned e, int t)
+{
+    return ((e & 8u) << (t - 4)) | ((e >> 4) << 3) | ((e & 7u) ^ ((e >> 4) & 7u));
+}
+// offset (amplitudes, t = 12) of element d of a radix-16 column behind tile + (phys(e_base) ^ (d & 7)):
+//   digit at bits 8..11: phys(d << 8) = d << 7                       (no XOR part)
+//   digit at bits 4..7 : phys(d << 4) = (d << 3) | (d & 7)           -> XOR part d & 7, rest d << 3
+//   digit at bits 0..3 : phys(d)      = ((d & 8) << 8) | (d & 7)     -> XOR part d & 7, rest (d & 8) << 8
+template <int SPLIT>
+__host__ __device__ __forceinline__ constexpr unsigned split3_offset(int d)
+{
+    return SPLIT == 8 ? ((unsigned) d << 7) : SPLIT == 4 ? ((unsigned) d << 3) : (((unsigned) d & 8u) << 8);
+}
+
 struct tile_geom {
     int a, g_lo, sw;
     __device__ __forceinline__ uint64_t spread(unsigned e) const
@@ -183,7 +203,10 @@ struct tile_geom {
 
 // LIN: the tile is laid out linearly in shared memory (strided sweeps of the pipelined kernel): the R
 // elements of a column are `stride` apart, one multiply-add per address instead of the swizzle arithmetic
-template <int R, bool INV, bool TW, bool LIN = false>
+// SPLIT >= 0: radix-16 step with its digit at the compile-time position SPLIT (0, 4 or 8) of a
+// contiguous 2^12 tile held in the split-3 layout (split3_phys): every address is the column's base
+// XOR a 3-bit constant plus a compile-time offset -- eight XORs per column instead of arithmetic per element
+template <int R, bool INV, bool TW, bool LIN = false, int SPLIT = -1>
 __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__restrict__ tile,
                                          const double2 *__restrict__ wcol, double2 wb, const tile_geom G,
                                          const sweep_step S, int t, uint64_t base, bool from_global,
@@ -202,7 +225,14 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
         double2 *g = amp + base + G.spread(e_base);
         const uint64_t g_stride = 1ull << G.phys(S.s);
         double2 x[R];
-        if (from_global) {
+        // split-3 layout: elements j = d & 7 sit behind tile + (phys(e_base) ^ j) at compile-time offsets
+        unsigned sp_base = 0;
+        if (SPLIT >= 0) sp_base = split3_phys(e_base, 12);
+        if (SPLIT >= 0) {
+#pragma unroll
+            for (int d = 0; d < R; d++)
+                x[d] = tile[(sp_base ^ (unsigned) (SPLIT == 8 ? 0 : (d & 7))) + split3_offset<SPLIT>(d)];
+        } else if (from_global) {
             if (S.s == 0 && R >= 2) {
 #pragma unroll
                 for (int d = 0; d < R; d += 2) x[d] = ld256_lo(g + d, x[d + 1]);
@@ -270,7 +300,11 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
                 }
             }
         }
-        if (to_global) {
+        if (SPLIT >= 0) {
+#pragma unroll
+            for (int d = 0; d < R; d++)
+                tile[(sp_base ^ (unsigned) (SPLIT == 8 ? 0 : (d & 7))) + split3_offset<SPLIT>(d)] = x[d];
+        } else if (to_global) {
             if (S.s == 0 && R >= 2) {
 #pragma unroll
                 for (int d = 0; d < R; d += 2) st256(g + d, x[d], x[d + 1]);
@@ -296,6 +330,20 @@ __device__ __forceinline__ void run_step(double2 *__restrict__ amp, double2 *__r
 #pragma unroll
             for (int d = 0; d < R; d++) tile[G.swz(e_base + ((unsigned) d << S.s))] = x[d];
         }
+    }
+}
+
+// radix-16 step of a split-3 tile (t = 12), digit at bit 8, 4 or 0
+template <bool INV, bool TW>
+__device__ __forceinline__ void dispatch_split3(double2 *tile, const double2 *wcol, double2 wb, const tile_geom G,
+                                                const sweep_step S, uint64_t base, bool apply_scale, double scale,
+                                                unsigned tid, unsigned nthreads, const diag_gate *diag = nullptr,
+                                                int n_diag = 0, uint64_t index_or = 0)
+{
+    switch (S.s) {
+        case 8: run_step<16, INV, TW, false, 8>(nullptr, tile, wcol, wb, G, S, 12, base, false, false, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
+        case 4: run_step<16, INV, TW, false, 4>(nullptr, tile, wcol, wb, G, S, 12, base, false, false, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
+        default: run_step<16, INV, TW, false, 0>(nullptr, tile, wcol, wb, G, S, 12, base, false, false, apply_scale, scale, tid, nthreads, diag, n_diag, index_or); break;
     }
 }
 
@@ -362,7 +410,7 @@ inline long conflict_cost(const sweep_desc &d, int sw, bool all_steps)
                 for (unsigned ln = 0; ln < lanes; ln++) {
                     const unsigned c = c0 + ln;
                     const unsigned e = (((c >> S.s) << (S.s + S.r)) | (c & ((1u << S.s) - 1u))) + ((unsigned) dd << S.s);
-                    const unsigned ph = tile_phys(e, sw);
+                    const unsigned ph = sw >= kSwizzleSplit3 ? split3_phys(e, sw - kSwizzleSplit3) : tile_phys(e, sw);
                     worst = std::max(worst, ++seen[ph & 7u]);
                 }
                 cost += (worst - 1) * ((reads ? 1 : 0) + (writes ? 1 : 0));

@@ -68,12 +68,6 @@ struct pipe_params {
     int blk_tile_bits;              // pair: log2(tiles per block)
     uint64_t lag;                   // pair: B trails A by this many tiles
     int l2_hints;                   // pair: eviction-priority hints on the TMA loads and stores
-    double2 *amp;                   // the target array (direct stores)
-    int direct_store;               // 1: the last step of a tile writes straight from registers to global memory
-                                    // (ld/st unit) instead of back to the stage + TMA store: the TMA unit of an SM
-                                    // moves about 22 B/clk, loads and stores together (tools/ubench_tma.cu); with
-                                    // the stores on the other path it only carries the loads, and a stage is free
-                                    // again as soon as its last step has read it
     unsigned long long *ticket;     // pair: the queue head
     unsigned *done;                 // pair: stored A tiles per block
     unsigned long long *timing;     // -DQCS_PIPE_TIMING builds only: per-CTA cycle counters
@@ -186,7 +180,7 @@ __device__ __forceinline__ void tile_coords(const phase_params &Q, uint64_t tix,
         c2 = (int) (tix >> Q.lo_gap);
     } else {
         c0 = 0;
-        c1 = (int) (tix << (TB - 3));                                       // rows of 8 amplitudes
+        c1 = (int) (tix << (Q.d.sw == kSwizzleSplit3 ? TB - 4 : TB - 3));     // rows of 8 amplitudes (split-3 view: pairs of rows)
         c2 = 0;
     }
 }
@@ -221,7 +215,7 @@ __host__ __device__ __forceinline__ uint64_t pair_item(const pipe_params &P, uin
 // a launch small (the instruction cache holds about 40 KiB).
 enum { kWalsh = 0, kInverse = 1, kForward = 2 };
 
-template <int TB, int STAGES, int GROUPS, int GT, int MODE>
+template <int TB, int STAGES, int GROUPS, int GT, int MODE, bool PAIRED>
 __global__ void __launch_bounds__(64 + GROUPS * GT, 1)
 k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, const pipe_params P)
 {
@@ -232,7 +226,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     // STAGES tiles; the 128-byte swizzle of the final sweep needs 1024-byte alignment
     double2 *stage_buf = (double2 *) (smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     double2 *wcol = stage_buf + (size_t) STAGES * (1u << TB);
-    const int wcol_all = P.ph[0].d.wcol_total + (P.n_phases > 1 ? P.ph[1].d.wcol_total : 0);
+    const int wcol_all = P.ph[0].d.wcol_total + (PAIRED ? P.ph[1].d.wcol_total : 0);
     double2 *wbase = wcol + wcol_all;                                       // [STAGES][kMaxSteps]: per-tile twiddle bases
     uint64_t *bars = (uint64_t *) (wbase + STAGES * kMaxSteps);
     uint64_t *full = bars, *computed = bars + STAGES, *empty = bars + 2 * STAGES;
@@ -240,7 +234,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     diag_gate *sdiag = (diag_gate *) (s_item + STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool paired = P.n_phases > 1;
+    constexpr bool paired = PAIRED;       // compile time: a single sweep's descriptor then sits at fixed constant-bank offsets
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -254,7 +248,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     }
     // per-column part of the external twiddle: fixed for the whole kernel; one entry per value of
     // the tile-local bits below the step
-    for (int ph = 0; ph < P.n_phases; ph++) {
+    for (int ph = 0; ph < (PAIRED ? 2 : 1); ph++) {
         const phase_params &Q = P.ph[ph];
         if (Q.d.hadamard_only) continue;
         tile_geom G;
@@ -306,8 +300,8 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
                 if (++sentinels == GROUPS) break;
                 continue;
             }
-            const int ph = (item & kPhaseB) ? 1 : 0;
-            const phase_params &Q = P.ph[ph];
+            const int ph = (PAIRED && (item & kPhaseB)) ? 1 : 0;
+            const phase_params &Q = PAIRED ? P.ph[ph] : P.ph[0];
             const uint64_t idx = item & (kPhaseB - 1ull);
             const uint64_t tix = paired ? pair_tile(P, Q, idx) : tile_number(Q.d, idx);
             // the loads go out first; the tile's twiddle bases are computed while they travel
@@ -351,8 +345,8 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ---------------- store issuer (idle when the consumers store directly) ----------------
-        if (lane == 0 && !P.direct_store) {
+        // ---------------- store issuer ----------------
+        if (lane == 0) {
             const uint64_t pol_keep = l2_policy(true), pol_stream = l2_policy(false);
             for (uint64_t k = 0;; k++) {
                 const int s = (int) (k % STAGES);
@@ -362,8 +356,8 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
                 const long long t1 = QCS_TICK(P);
                 const uint64_t item = s_item[s];
                 if (item == kNoItem) break;
-                const int ph = (item & kPhaseB) ? 1 : 0;
-                const phase_params &Q = P.ph[ph];
+                const int ph = (PAIRED && (item & kPhaseB)) ? 1 : 0;
+                const phase_params &Q = PAIRED ? P.ph[ph] : P.ph[0];
                 const uint64_t idx = item & (kPhaseB - 1ull);
                 int c0, c1, c2;
                 tile_coords<TB>(Q, paired ? pair_tile(P, Q, idx) : tile_number(Q.d, idx), c0, c1, c2);
@@ -408,11 +402,11 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             const long long t1 = QCS_TICK(P);
             const uint64_t item = s_item[s];
             if (item == kNoItem) {
-                if (tig == 0 && !P.direct_store) mbar_arrive(&computed[s]);     // lets the store issuer see the sentinel
+                if (tig == 0) mbar_arrive(&computed[s]);     // lets the store issuer see the sentinel
                 break;
             }
-            const int ph = (item & kPhaseB) ? 1 : 0;
-            const phase_params &Q = P.ph[ph];
+            const int ph = (PAIRED && (item & kPhaseB)) ? 1 : 0;
+            const phase_params &Q = PAIRED ? P.ph[ph] : P.ph[0];
             const uint64_t tix = paired ? pair_tile(P, Q, item & (kPhaseB - 1ull)) : tile_number(Q.d, item & (kPhaseB - 1ull));
             const uint64_t base = tile_base<TB>(Q, tix);
             tile_geom G;
@@ -423,30 +417,25 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             for (int st = 0; st < Q.d.n_steps; st++) {
                 const sweep_step S = Q.d.step[st];
                 const bool last = st == Q.d.n_steps - 1;
-                const bool out = last && P.direct_store;        // straight to global memory
                 const double2 wb = wbase[s * kMaxSteps + st];
                 // strided tiles lie linearly in shared memory, the contiguous one carries the 128-byte swizzle
                 if (Q.lo_gap >= 0) {
-                    if (MODE == kWalsh) dispatch_step<true, false, true>(P.amp, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, out, last, Q.d.scale, tig, GT, sdiag, Q.d.n_diag, Q.d.index_or);
-                    else dispatch_step<MODE == kInverse, true, true>(P.amp, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, out, last, Q.d.scale, tig, GT);
+                    if (MODE == kWalsh) dispatch_step<true, false, true>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT, sdiag, Q.d.n_diag, Q.d.index_or);
+                    else dispatch_step<MODE == kInverse, true, true>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT);
+                } else if (TB == 12 && Q.d.sw == kSwizzleSplit3) {
+                    // contiguous tile in the split-3 layout: radix-16 steps at bits 8, 4, 0
+                    if (MODE == kWalsh) dispatch_split3<true, false>(tile, my_wcol + S.col_off, wb, G, S, base, last, Q.d.scale, tig, GT, sdiag, Q.d.n_diag, Q.d.index_or);
+                    else dispatch_split3<MODE == kInverse, true>(tile, my_wcol + S.col_off, wb, G, S, base, last, Q.d.scale, tig, GT);
                 } else {
-                    if (MODE == kWalsh) dispatch_step<true, false, false>(P.amp, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, out, last, Q.d.scale, tig, GT, sdiag, Q.d.n_diag, Q.d.index_or);
-                    else dispatch_step<MODE == kInverse, true, false>(P.amp, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, out, last, Q.d.scale, tig, GT);
+                    if (MODE == kWalsh) dispatch_step<true, false, false>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT, sdiag, Q.d.n_diag, Q.d.index_or);
+                    else dispatch_step<MODE == kInverse, true, false>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT);
                 }
-                if (last && !P.direct_store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
-                // paired launch, direct stores: every thread's part of the A tile is performed at GPU scope before
-                // the block counter moves
-                if (out && paired && ph == 0) __threadfence();
+                if (last) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
                 group_barrier(group, GT);
             }
             n_done++;
             if (tig == 0) {
-                if (P.direct_store) {
-                    mbar_arrive(&empty[s]);                  // the stage has been read for the last time
-                    if (paired && ph == 0) atomicAdd(P.done + ((item & (kPhaseB - 1ull)) >> P.blk_tile_bits), 1u);
-                } else {
-                    mbar_arrive(&computed[s]);
-                }
+                mbar_arrive(&computed[s]);
                 QCS_TIMING_ADD(P, 4 + 2 * group, t1 - t0);              // waiting for the load
                 QCS_TIMING_ADD(P, 5 + 2 * group, QCS_TICK(P) - t1);     // the steps
             }
@@ -508,7 +497,7 @@ template <int TB, int STAGES, int GROUPS, int GT, int MODE>
 int launch_mode(qcs_register *reg, const CUtensorMap &tmap0, const CUtensorMap &tmap1, const pipe_params &P, size_t smem,
                 const qft::sweep_target &tg)
 {
-    auto kern = k_qft_sweep_tma<TB, STAGES, GROUPS, GT, MODE>;
+    auto kern = P.n_phases > 1 ? k_qft_sweep_tma<TB, STAGES, GROUPS, GT, MODE, true> : k_qft_sweep_tma<TB, STAGES, GROUPS, GT, MODE, false>;
     QCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     uint64_t grid = (uint64_t) reg->sm_count;
     if (tg.max_ctas > 0 && grid > (uint64_t) tg.max_ctas) grid = (uint64_t) tg.max_ctas;
@@ -544,7 +533,8 @@ int launch_by_shape(qcs_register *reg, int shape_id, const CUtensorMap &tmap0, c
 }
 
 // tensor map + box geometry of one sweep
-int encode_phase(const pipe_shape &sh, const qft::sweep_target &tg, const qft::sweep_plan &plan, phase_params &Q, CUtensorMap &tmap)
+int encode_phase(const pipe_shape &sh, const qft::sweep_target &tg, const qft::sweep_plan &plan, phase_params &Q, CUtensorMap &tmap,
+                 bool allow_split3)
 {
     encode_fn_t encode = get_encode();
     if (!encode) {
@@ -570,22 +560,45 @@ int encode_phase(const pipe_shape &sh, const qft::sweep_target &tg, const qft::s
         Q.lo_gap = plan.d.g_lo - plan.d.a;
         Q.d.sw = 28;                                         // no XOR
     } else {
-        rows = 1u << (sh.tb - 3);
-        dims[0] = 16;                                        // 128 B rows
-        dims[1] = (1ull << tg.n_bits) >> 3;
-        dims[2] = 1;
-        strides[0] = 128;
-        strides[1] = 128ull * dims[1];
-        box[0] = 16;
-        swz = CU_TENSOR_MAP_SWIZZLE_128B;
+        // contiguous tile, 128 B rows, 128-byte hardware swizzle.  Two views of the same 2^tb amplitudes:
+        //   plain   : rows e >> 3                              -> phys(e) = e ^ ((e >> 3) & 7)
+        //   split-3 : {8 amplitudes} x {e >> 4} x {bit 3 of e} -> split3_phys(e): conflict-free for every
+        //             radix-16 step; taken when the sweep consists of radix-16 steps at bits 8, 4, 0 of a 2^12
+        //             tile (the kernel has compile-time addressing for exactly those)
         Q.lo_gap = -1;
-        Q.d.sw = 3;
+        swz = CU_TENSOR_MAP_SWIZZLE_128B;
+        dims[0] = 16;
+        box[0] = 16;
+        bool split = allow_split3 && sh.tb == 12 && plan.d.n_steps >= 1;
+        for (int k = 0; k < plan.d.n_steps && split; k++)
+            split = plan.d.step[k].r == 4 && (plan.d.step[k].s == 8 || plan.d.step[k].s == 4 || plan.d.step[k].s == 0);
+        if (split) {
+            dims[1] = (1ull << tg.n_bits) >> 4;
+            dims[2] = 2;
+            strides[0] = 256;
+            strides[1] = 128;
+            Q.d.sw = kSwizzleSplit3;
+            Q.box_rows = 1 << (sh.tb - 4);
+            Q.n_boxes = 1;
+            Q.box_bytes = 16u << sh.tb;
+            box[1] = (cuuint32_t) Q.box_rows;
+            box[2] = 2;
+        } else {
+            rows = 1u << (sh.tb - 3);
+            dims[1] = (1ull << tg.n_bits) >> 3;
+            dims[2] = 1;
+            strides[0] = 128;
+            strides[1] = 128ull * dims[1];
+            Q.d.sw = 3;
+        }
     }
-    Q.box_rows = rows < 256u ? (int) rows : 256;             // a box dimension is at most 256
-    Q.n_boxes = (int) (rows / (unsigned) Q.box_rows);
-    Q.box_bytes = (uint32_t) (((size_t) 16 << sh.tb) / (size_t) Q.n_boxes);
-    box[1] = (cuuint32_t) Q.box_rows;
-    box[2] = 1;
+    if (Q.lo_gap >= 0 || Q.d.sw == 3) {
+        Q.box_rows = rows < 256u ? (int) rows : 256;         // a box dimension is at most 256
+        Q.n_boxes = (int) (rows / (unsigned) Q.box_rows);
+        Q.box_bytes = (uint32_t) (((size_t) 16 << sh.tb) / (size_t) Q.n_boxes);
+        box[1] = (cuuint32_t) Q.box_rows;
+        box[2] = 1;
+    }
     // 128 B rows: promoting the requests to 256 B would fetch a neighbour's half-line with every row
     // (measured at n = 30: 21.2-21.4 ms for every promotion setting -- not a lever)
     const CUtensorMapL2promotion promo = (strided && plan.d.a <= 3) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
@@ -658,12 +671,10 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
     const int shape_id = reg->opt_pipe_shape >= 0 && reg->opt_pipe_shape < kNumShapes ? reg->opt_pipe_shape : 0;
     pipe_params P = {};
     CUtensorMap tmap;
-    QCS_TRY(encode_phase(sh, tg, plan, P.ph[0], tmap));
+    QCS_TRY(encode_phase(sh, tg, plan, P.ph[0], tmap, reg->opt_split3 != 0));
     P.ph[0].wcol_base = 0;
     P.n_phases = 1;
     P.n_tiles = plan.n_tiles;
-    P.amp = tg.amp;
-    P.direct_store = reg->opt_direct_store && plan.d.n_diag == 0;
     return run_launch(reg, sh, shape_id, tmap, tmap, P, pipe_smem(sh, plan.d.wcol_total, plan.d.n_diag), tg);
 }
 
@@ -716,8 +727,9 @@ int qcs_pipeline_launch_pair(qcs_register *reg, const qft::sweep_target &tg, con
     const int shape_id = reg->opt_pipe_shape >= 0 && reg->opt_pipe_shape < kNumShapes ? reg->opt_pipe_shape : 0;
     pipe_params P = {};
     CUtensorMap tmap0, tmap1;
-    QCS_TRY(encode_phase(sh, tg, a, P.ph[0], tmap0));
-    QCS_TRY(encode_phase(sh, tg, b, P.ph[1], tmap1));
+    const bool split_ok = reg->opt_split3 != 0;
+    QCS_TRY(encode_phase(sh, tg, a, P.ph[0], tmap0, split_ok));
+    QCS_TRY(encode_phase(sh, tg, b, P.ph[1], tmap1, split_ok));
     P.ph[0].wcol_base = 0;
     P.ph[1].wcol_base = a.d.wcol_total;
     P.n_phases = 2;
@@ -735,8 +747,6 @@ int qcs_pipeline_launch_pair(qcs_register *reg, const qft::sweep_target &tg, con
     if (lag > a.n_tiles) lag = a.n_tiles;
     P.lag = lag;
     P.l2_hints = reg->opt_l2_pair_hints;
-    P.amp = tg.amp;
-    P.direct_store = reg->opt_direct_store;
     // queue head + one counter per block, zeroed in stream order
     const size_t need = 8 + 4 * (size_t) n_blocks;
     if (need > reg->d_pair_cap) {

@@ -155,7 +155,9 @@ def test_fused_sweep_count(qcs):
         reg.inverse_QFT()
         reg.synchronize()
         launches, _, by = reg.profile()["tile_sweep"]
-        assert 1 <= launches <= 5 and by == launches * 32.0 * (1 << 26)
+        # algorithmic bytes = sweeps made x 32 B per amplitude; an L2-paired launch makes two sweeps
+        sweeps = by / (32.0 * (1 << 26))
+        assert 1 <= launches <= 5 and sweeps == int(sweeps) and launches <= sweeps <= 2 * launches
 
 
 @pytest.mark.parametrize("L,M,Cn,a,mode", [(3, 4, 15, 7, 0), (5, 5, 21, 2, 0), (6, 5, 21, 4, 0), (3, 4, 15, 6, 0),

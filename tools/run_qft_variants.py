@@ -24,10 +24,9 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     lags = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [444]
-    variants = [("pair off", {q.OPT_L2_PAIR: 0, q.OPT_DIRECT_STORE: 0})]
-    variants += [(f"pair lag {lag}", {q.OPT_L2_PAIR: 1, q.OPT_L2_PAIR_LAG: lag, q.OPT_DIRECT_STORE: 0}) for lag in lags]
-    variants += [("direct store, pair off", {q.OPT_L2_PAIR: 0, q.OPT_DIRECT_STORE: 1})]
-    variants += [(f"direct store, pair lag {lag}", {q.OPT_L2_PAIR: 1, q.OPT_L2_PAIR_LAG: lag, q.OPT_DIRECT_STORE: 1}) for lag in lags]
+    variants = [("pair off", {q.OPT_L2_PAIR: 0, q.OPT_SPLIT3: 1})]
+    variants += [(f"pair lag {lag}", {q.OPT_L2_PAIR: 1, q.OPT_L2_PAIR_LAG: lag}) for lag in lags]
+    variants += [("pair off, plain swizzle", {q.OPT_L2_PAIR: 0, q.OPT_SPLIT3: 0})]
     N = 1 << n
     with q.Register(n, 0) as reg:
         for name, opts in variants:
