@@ -304,6 +304,21 @@ int qcs_fuse_flush(qcs_register *reg)
             ps.plan.d.n_diag = (int) ps.in_sweep.size();
             ps.plan.d.diag = ps.in_sweep.empty() ? nullptr : d_all + at;
             at += ps.in_sweep.size();
+        }
+    }
+    for (size_t k = 0; k < passes.size(); k++) {
+        pass &ps = passes[k];
+        if (ps.type == 0) {
+            // two neighbouring sweeps with nothing in between may share an L2-paired launch
+            if (k + 1 < passes.size() && passes[k + 1].type == 0 && ps.after.empty()) {
+                bool paired = false;
+                QCS_TRY(qcs_launch_sweep_pair(reg, ps.plan, passes[k + 1].plan, &paired));
+                if (paired) {
+                    k++;
+                    QCS_TRY(launch_diag_list(reg, queue, passes[k].after, d_scratch, stage));
+                    continue;
+                }
+            }
             QCS_TRY(qcs_launch_sweep_plan(reg, ps.plan));
         } else if (ps.type == 1) {
             QCS_TRY(qcs_k_hadamard_local(reg, ps.q));

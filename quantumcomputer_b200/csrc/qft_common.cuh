@@ -541,3 +541,5 @@ inline void make_forward(std::vector<sweep_plan> &plans)
 int qcs_plan_hadamard_sweeps(const qcs_register *reg, unsigned lo, unsigned hi, std::vector<qft::sweep_plan> &plans);
 // launch one planned sweep on the register's shard and stream
 int qcs_launch_sweep_plan(qcs_register *reg, const qft::sweep_plan &plan);
+// two consecutive sweeps of the shard as one L2-paired launch if they qualify (*paired), else nothing happens
+int qcs_launch_sweep_pair(qcs_register *reg, const qft::sweep_plan &a, const qft::sweep_plan &b, bool *paired);

@@ -208,6 +208,18 @@ int qcs_plan_hadamard_sweeps(const qcs_register *reg, unsigned lo, unsigned hi, 
     return QCS_NO_ERROR;
 }
 
+// two consecutive sweeps as one L2-paired launch when they qualify (*paired tells), else nothing is launched
+int qcs_launch_sweep_pair(qcs_register *reg, const sweep_plan &a, const sweep_plan &b, bool *paired)
+{
+    const sweep_target tg = {reg->amp, reg->n_local, reg->stream};
+    *paired = reg->opt_pipeline && qcs_pipeline_pair_supported(reg, tg, a, b);
+    if (!*paired) return QCS_NO_ERROR;
+    reg->launch_stream = tg.stream;
+    const int rc = qcs_pipeline_launch_pair(reg, tg, a, b);
+    reg->launch_stream = nullptr;
+    return rc;
+}
+
 int qcs_launch_sweep_plan(qcs_register *reg, const sweep_plan &plan)
 {
     const sweep_target tg = {reg->amp, reg->n_local, reg->stream};

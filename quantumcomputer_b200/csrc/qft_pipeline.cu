@@ -264,7 +264,10 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             }
         }
     }
+    // diagonal gates riding along (Walsh-Hadamard sweeps of the gate stream): phase 0's list, then phase 1's
     for (int i = threadIdx.x; i < P.ph[0].d.n_diag; i += kThreads) sdiag[i] = P.ph[0].d.diag[i];
+    if (PAIRED)
+        for (int i = threadIdx.x; i < P.ph[1].d.n_diag; i += kThreads) sdiag[P.ph[0].d.n_diag + i] = P.ph[1].d.diag[i];
     __syncthreads();
 
     if (warp == 0) {
@@ -414,20 +417,21 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             G.g_lo = Q.d.g_lo;
             G.sw = Q.d.sw;
             const double2 *my_wcol = wcol + Q.wcol_base;
+            const diag_gate *my_diag = sdiag + (ph ? P.ph[0].d.n_diag : 0);
             for (int st = 0; st < Q.d.n_steps; st++) {
                 const sweep_step S = Q.d.step[st];
                 const bool last = st == Q.d.n_steps - 1;
                 const double2 wb = wbase[s * kMaxSteps + st];
                 // strided tiles lie linearly in shared memory, the contiguous one carries the 128-byte swizzle
                 if (Q.lo_gap >= 0) {
-                    if (MODE == kWalsh) dispatch_step<true, false, true>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT, sdiag, Q.d.n_diag, Q.d.index_or);
+                    if (MODE == kWalsh) dispatch_step<true, false, true>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT, my_diag, Q.d.n_diag, Q.d.index_or);
                     else dispatch_step<MODE == kInverse, true, true>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT);
                 } else if (TB == 12 && Q.d.sw == kSwizzleSplit3) {
                     // contiguous tile in the split-3 layout: radix-16 steps at bits 8, 4, 0
-                    if (MODE == kWalsh) dispatch_split3<true, false>(tile, my_wcol + S.col_off, wb, G, S, base, last, Q.d.scale, tig, GT, sdiag, Q.d.n_diag, Q.d.index_or);
+                    if (MODE == kWalsh) dispatch_split3<true, false>(tile, my_wcol + S.col_off, wb, G, S, base, last, Q.d.scale, tig, GT, my_diag, Q.d.n_diag, Q.d.index_or);
                     else dispatch_split3<MODE == kInverse, true>(tile, my_wcol + S.col_off, wb, G, S, base, last, Q.d.scale, tig, GT);
                 } else {
-                    if (MODE == kWalsh) dispatch_step<true, false, false>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT, sdiag, Q.d.n_diag, Q.d.index_or);
+                    if (MODE == kWalsh) dispatch_step<true, false, false>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT, my_diag, Q.d.n_diag, Q.d.index_or);
                     else dispatch_step<MODE == kInverse, true, false>(nullptr, tile, my_wcol + S.col_off, wb, G, S, TB, base, false, false, last, Q.d.scale, tig, GT);
                 }
                 if (last) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
@@ -715,10 +719,11 @@ bool qcs_pipeline_pair_supported(const qcs_register *reg, const qft::sweep_targe
     int inb_pos, inb_bits;
     uint64_t block_bytes;
     if (!pair_geometry(sh, a, b, inb_pos, inb_bits, block_bytes)) return false;
-    if (a.d.n_diag || b.d.n_diag || a.d.slice_bits || b.d.slice_bits || a.d.tile_first || b.d.tile_first) return false;
+    if (a.d.slice_bits || b.d.slice_bits || a.d.tile_first || b.d.tile_first) return false;
+    if (a.d.hadamard_only != b.d.hadamard_only || a.d.inverse != b.d.inverse) return false;    // one kernel mode per launch
     if (inb_bits > 20 || (uint64_t) a.n_tiles < (2ull << inb_bits)) return false;          // at least two blocks
     if (block_bytes > (uint64_t) reg->opt_l2_pair_max_block) return false;                  // a few blocks must fit the L2
-    return pipe_smem(sh, a.d.wcol_total + b.d.wcol_total, 0) <= reg->smem_optin;
+    return pipe_smem(sh, a.d.wcol_total + b.d.wcol_total, a.d.n_diag + b.d.n_diag) <= reg->smem_optin;
 }
 
 int qcs_pipeline_launch_pair(qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &a, const qft::sweep_plan &b)
@@ -760,7 +765,7 @@ int qcs_pipeline_launch_pair(qcs_register *reg, const qft::sweep_target &tg, con
     QCS_CUDA(cudaMemsetAsync(reg->d_pair, 0, need, tg.stream));
     P.ticket = (unsigned long long *) reg->d_pair;
     P.done = (unsigned *) ((unsigned char *) reg->d_pair + 8);
-    return run_launch(reg, sh, shape_id, tmap0, tmap1, P, pipe_smem(sh, a.d.wcol_total + b.d.wcol_total, 0), tg);
+    return run_launch(reg, sh, shape_id, tmap0, tmap1, P, pipe_smem(sh, a.d.wcol_total + b.d.wcol_total, a.d.n_diag + b.d.n_diag), tg);
 }
 
 

@@ -146,3 +146,47 @@ def test_save_and_load_state(qcs, tmp_path):
     with qcs.Register(4, 0) as small:
         with pytest.raises(qcs.QcsError):
             small.load_state(os.path.join(tmp_path, "missing.qcs"))
+
+
+def test_single_caller_handle_on_one_gpu_and_async_upload(qcs, oracle_built):
+    """qcs_register_create_multi with n_gpus = 1 is an ordinary register; qcs_set_state_async from a
+    pinned buffer allocated next to the device (qcs_host_alloc_near) uploads the same state as qcs_set_state."""
+    n = 14
+    o = oracle_built.Restatement(n, 0)
+    o.fill_synthetic(5)
+    o.scale(1.0 / math.sqrt(o.norm2()))
+    state = o.get_state().copy()
+    o.inverse_QFT()
+    want = o.get_state()
+    with qcs.Register(n, 0, n_gpus=1) as reg:
+        assert reg.num_gpus == 1 and reg.local_states == 1 << n
+        pinned = qcs.PinnedBuffer(2 << n, device=0)
+        pinned.array[:] = state.view(np.float64)
+        reg.set_state_async(pinned.array)
+        reg.inverse_QFT()
+        got = reg.get_state()
+        pinned.close()
+        assert rel_l2(got, want) <= 1e-12
+    with pytest.raises(qcs.QcsError):
+        qcs.Register(n, 0, n_gpus=3)                   # not a power of two
+
+
+def test_measurement_with_zero_variate_and_leading_zeros(qcs, oracle_built):
+    """gsl_rng_uniform can return exactly 0.0: measure_state then returns index 0 whatever amp[0] is
+    (qc_shor.c:286-289), also when the parallel scan would skip the all-zero leading chunks."""
+    n = 19
+    amps = np.zeros(1 << n, dtype=np.complex128)
+    amps[(1 << 18) + 5] = 0.6
+    amps[(1 << 18) + 77] = 0.8j
+    o = oracle_built.Restatement(n, 0)
+    o.set_state(amps)
+    with qcs.Register(n, 0) as reg:
+        reg.set_state(amps)
+        for r in (0.0, -0.5):
+            assert reg.sample_states([r])[0] == 0
+        got = [int(x) for x in reg.sample_states([0.0, 0.2, 0.36, 0.37, 0.999])]
+        ref = []
+        for r in (0.0, 0.2, 0.36, 0.37, 0.999):
+            o.set_state(amps)
+            ref.append(int(o.measure_state(r)))
+        assert got == ref and got[0] == 0
