@@ -71,7 +71,7 @@ int qcs_profile_resolve(qcs_register *reg)
 // ---------------------------------------------------------------------------
 // misc
 // ---------------------------------------------------------------------------
-extern "C" const char *qcs_version(void) { return "qcs 0.1.0 (sm_100a)"; }
+extern "C" const char *qcs_version(void) { return "qcs 0.2.0 (sm_100a)"; }
 
 extern "C" const char *qcs_error_string(int code)
 {
@@ -176,7 +176,7 @@ extern "C" int qcs_host_free(void *ptr)
     do {                                                            \
         if (!(reg)) return QCS_BAD_ARGUMENTS;                       \
         QCS_CUDA(cudaSetDevice((reg)->device));                     \
-        if (!(reg)->queue.empty()) QCS_TRY(qcs_fuse_flush(reg));    \
+        if (!(reg)->queue.empty() || (reg)->dense_pending) QCS_TRY(qcs_fuse_flush(reg));    \
     } while (0)
 #define QCS_ENTER_GATE(reg)                         \
     do {                                            \
@@ -247,6 +247,8 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->opt_l2_pair_lag = 3 * 148;
     reg->opt_l2_pair_max_block = 16ll << 20;     // measured: 32 MiB blocks (n = 30) no longer stay in the L2 (profiles/README.md)
     reg->fusing = 0;
+    reg->dense_pending = 0;
+    reg->dense_gates = 0;
     reg->d_diag = nullptr;
     reg->d_diag_cap = 0;
     reg->launches_total = 0;
@@ -474,6 +476,7 @@ extern "C" int qcs_hadamard_gate(qcs_register *reg, unsigned qubit_num)
     QCS_ENTER_GATE(reg);
     if (reg->fusing && reg->opt_fusion) {
         if (qubit_num >= reg->n) return QCS_BAD_ARGUMENTS;
+        if (reg->dense_pending) QCS_TRY(qcs_fuse_flush(reg));         // program order: the dense block first
         reg->queue.push_back({0, qubit_num, qubit_num, 0.0, 0.0});
         return QCS_NO_ERROR;
     }
@@ -502,6 +505,7 @@ extern "C" int qcs_c_phase_shift_gate(qcs_register *reg, unsigned c_qubit_num, u
     // gsl_complex_polar(1.0, theta), qc_shor.c:526: host libm like the reference
     if (reg->fusing && reg->opt_fusion) {
         if (c_qubit_num >= reg->n || qubit_num >= reg->n) return QCS_BAD_ARGUMENTS;
+        if (reg->dense_pending) QCS_TRY(qcs_fuse_flush(reg));
         reg->queue.push_back({1, c_qubit_num, qubit_num, 1.0 * cos(theta), 1.0 * sin(theta)});
         return QCS_NO_ERROR;
     }

@@ -272,8 +272,59 @@ static int schedule_stream(const qcs_register *reg, const std::vector<qcs_pendin
     return QCS_NO_ERROR;
 }
 
+// A run of general (controlled) single-qubit gates on qubits 0..3 inside the window -- the generalisation
+// of HADAMARD_BASE_MATRIX / C_PHASE_SHIFT_BASE_MATRIX (qc_shor.c:210-225) to arbitrary 2x2 matrices -- is
+// multiplied up on the host into one 16 x 16 unitary and applied as ONE dense block on the FP64 tensor cores
+// (dense_block.cu) when the run ends: the "k low qubits as one 2^k x 2^k dense contraction" of north_star.
+bool qcs_fuse_record_dense(qcs_register *reg, unsigned q, int c, const double *u, int *rc)
+{
+    *rc = QCS_NO_ERROR;
+    if (!reg->fusing || !reg->opt_fusion || !u || q >= 4 || c >= 4 || c == (int) q || reg->n_local < 7) return false;
+    // program order: gates recorded before this run are launched first
+    if (!reg->queue.empty()) {
+        *rc = qcs_fuse_flush(reg);
+        if (*rc != QCS_NO_ERROR) return true;
+    }
+    if (!reg->dense_pending) {
+        for (int i = 0; i < 512; i++) reg->dense_acc[i] = 0.0;
+        for (int i = 0; i < 16; i++) reg->dense_acc[2 * (i * 16 + i)] = 1.0;
+        reg->dense_pending = 1;
+        reg->dense_gates = 0;
+    }
+    // acc <- G acc, G = the gate embedded on index bits 0..3: row i mixes rows i with bit q cleared / set
+    double next[512];
+    for (int i = 0; i < 16; i++) {
+        const bool on = c < 0 || ((i >> c) & 1);
+        const int i0 = i & ~(1 << q), i1 = i | (1 << q), b = (i >> q) & 1;
+        for (int j = 0; j < 16; j++) {
+            double re, im;
+            if (!on) {
+                re = reg->dense_acc[2 * (i * 16 + j)];
+                im = reg->dense_acc[2 * (i * 16 + j) + 1];
+            } else {
+                const double a_re = u[2 * (2 * b)], a_im = u[2 * (2 * b) + 1];            // U[b][0]
+                const double b_re = u[2 * (2 * b + 1)], b_im = u[2 * (2 * b + 1) + 1];    // U[b][1]
+                const double x_re = reg->dense_acc[2 * (i0 * 16 + j)], x_im = reg->dense_acc[2 * (i0 * 16 + j) + 1];
+                const double y_re = reg->dense_acc[2 * (i1 * 16 + j)], y_im = reg->dense_acc[2 * (i1 * 16 + j) + 1];
+                re = a_re * x_re - a_im * x_im + b_re * y_re - b_im * y_im;
+                im = a_re * x_im + a_im * x_re + b_re * y_im + b_im * y_re;
+            }
+            next[2 * (i * 16 + j)] = re;
+            next[2 * (i * 16 + j) + 1] = im;
+        }
+    }
+    for (int i = 0; i < 512; i++) reg->dense_acc[i] = next[i];
+    reg->dense_gates++;
+    return true;
+}
+
 int qcs_fuse_flush(qcs_register *reg)
 {
+    if (reg->dense_pending) {
+        // never both pending: recording into one launches the other first
+        reg->dense_pending = 0;
+        return qcs_k_dense_block(reg, 4, reg->dense_acc);
+    }
     if (reg->queue.empty()) return QCS_NO_ERROR;
     std::vector<qcs_pending_gate> queue;
     queue.swap(reg->queue);             // the per-gate calls below must not see a pending queue
@@ -416,5 +467,5 @@ extern "C" int qcs_fuse_end(qcs_register *reg)
 extern "C" unsigned long long qcs_fuse_pending(const qcs_register *reg)
 {
     if (reg && reg->group) return qcs_fuse_pending(qcs_group_member(reg, 0));
-    return reg ? (unsigned long long) reg->queue.size() : 0ull;
+    return reg ? (unsigned long long) reg->queue.size() + (reg->dense_pending ? reg->dense_gates : 0u) : 0ull;
 }

@@ -89,6 +89,12 @@ extern "C" int qcs_apply_dense_block(qcs_register *reg, unsigned k, const double
     if (!reg || !u_interleaved) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaSetDevice(reg->device));
     QCS_TRY(qcs_fuse_flush(reg));
+    return qcs_k_dense_block(reg, k, u_interleaved);
+}
+
+// the launch itself (no flush): also what the gate stream emits for a run of general gates on the low qubits
+int qcs_k_dense_block(qcs_register *reg, unsigned k, const double *u_interleaved)
+{
     if ((k != 3 && k != 4) || k + 3 > reg->n_local) return QCS_BAD_ARGUMENTS;
     const int R = 1 << k, K2 = 2 * R;
     const int MT = K2 / 8, KS = K2 / 4, PIECE = K2 / 4, OUT = K2 / 8;

@@ -123,6 +123,8 @@ extern "C" int qcs_apply_gate(qcs_register *reg, unsigned qubit_num, const doubl
     QCS_GROUP_FORWARD(reg, qcs_apply_gate(m, qubit_num, u_interleaved));
     if (!reg) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaSetDevice(reg->device));
+    int rc = QCS_NO_ERROR;
+    if (qcs_fuse_record_dense(reg, qubit_num, -1, u_interleaved, &rc)) return rc;
     QCS_TRY(qcs_fuse_flush(reg));
     return qcs_k_gate_1q(reg, qubit_num, -1, u_interleaved);
 }
@@ -133,6 +135,8 @@ extern "C" int qcs_apply_controlled_gate(qcs_register *reg, unsigned c_qubit_num
     QCS_GROUP_FORWARD(reg, qcs_apply_controlled_gate(m, c_qubit_num, qubit_num, u_interleaved));
     if (!reg) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaSetDevice(reg->device));
+    int rc = QCS_NO_ERROR;
+    if (qcs_fuse_record_dense(reg, qubit_num, (int) c_qubit_num, u_interleaved, &rc)) return rc;
     QCS_TRY(qcs_fuse_flush(reg));
     return qcs_k_gate_1q(reg, qubit_num, (int) c_qubit_num, u_interleaved);
 }

@@ -73,6 +73,11 @@ struct qcs_register {
     // deferred gate stream (qcs_fuse_begin .. qcs_fuse_end)
     int fusing;
     std::vector<qcs_pending_gate> queue;
+    // a run of general (controlled) single-qubit gates on qubits 0..3 recorded in the window is kept as ONE
+    // 16 x 16 matrix (row-major, interleaved) and leaves as one DMMA dense block (dense_block.cu)
+    int dense_pending;
+    unsigned dense_gates;         // gates folded into it
+    double dense_acc[512];
     void *d_diag;                 // device array of qft::diag_gate for the sweeps in flight
     size_t d_diag_cap;            // in gates
 
@@ -190,9 +195,15 @@ int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, 
 // ---- general gates: gates_general.cu ------------------------------------------
 int qcs_k_gate_1q(qcs_register *reg, unsigned q, int c /* < 0: no control */, const double *u_interleaved);
 
+// ---- dense block on the low qubits: dense_block.cu
+int qcs_k_dense_block(qcs_register *reg, unsigned k, const double *u_interleaved);
+
 // ---- deferred gate stream: circuit.cu ------------------------------------------
 // schedule and launch every recorded gate (no-op when the queue is empty)
 int qcs_fuse_flush(qcs_register *reg);
+// record u (2x2, row-major interleaved) on qubit q < 4, control c < 4 or < 0, into the pending dense block;
+// false: not recordable here (not fusing, qubits too high, register too small): apply it the ordinary way
+bool qcs_fuse_record_dense(qcs_register *reg, unsigned q, int c, const double *u, int *rc);
 
 // ---- multi-GPU: dist.cu ---------------------------------------------------
 int qcs_dist_init(qcs_register *reg, const void *comm_id);

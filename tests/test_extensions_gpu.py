@@ -190,3 +190,50 @@ def test_measurement_with_zero_variate_and_leading_zeros(qcs, oracle_built):
             o.set_state(amps)
             ref.append(int(o.measure_state(r)))
         assert got == ref and got[0] == 0
+
+
+def test_run_of_general_gates_on_low_qubits_becomes_one_dense_block(qcs):
+    """Inside a fuse window a run of arbitrary (controlled) single-qubit gates on qubits 0..3 is multiplied
+    up on the host and leaves as ONE DMMA dense block; the result equals the gates applied one by one."""
+    n = 16
+    rng = np.random.default_rng(31)
+
+    def unitary():
+        a = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+        qm, _ = np.linalg.qr(a)
+        return qm
+
+    gates = []
+    for _ in range(40):
+        t = int(rng.integers(4))
+        if rng.random() < 0.5:
+            gates.append((t, -1, unitary()))
+        else:
+            c = int(rng.choice([x for x in range(4) if x != t]))
+            gates.append((t, c, unitary()))
+    with qcs.Register(n, 0) as one, qcs.Register(n, 0) as fused:
+        for reg in (one, fused):
+            reg.fill_synthetic(3)
+            reg.scale(1.0 / math.sqrt(reg.norm2()))
+        for t, c, U in gates:
+            one.apply_gate(t, U) if c < 0 else one.apply_controlled_gate(c, t, U)
+        before = fused.launch_count
+        with fused.fused():
+            for t, c, U in gates:
+                fused.apply_gate(t, U) if c < 0 else fused.apply_controlled_gate(c, t, U)
+            assert fused.fuse_pending == len(gates) and fused.launch_count == before     # nothing launched yet
+            fused.hadamard_gate(9)                     # ends the run: the dense block goes first
+            assert fused.launch_count == before + 1 and fused.fuse_pending == 1
+            fused.apply_gate(2, gates[0][2])           # a new run after the Hadamard
+        one.hadamard_gate(9)
+        one.apply_gate(2, gates[0][2])
+        assert fused.launch_count == before + 3        # dense block, Hadamard, dense block
+        assert rel_l2(fused.get_state(), one.get_state()) <= 1e-12
+        # gates on higher qubits are not recorded: they run at once, after the pending block
+        with fused.fused():
+            fused.apply_gate(1, gates[1][2])
+            fused.apply_gate(7, gates[2][2])
+            assert fused.fuse_pending == 0
+        one.apply_gate(1, gates[1][2])
+        one.apply_gate(7, gates[2][2])
+        assert rel_l2(fused.get_state(), one.get_state()) <= 1e-12
