@@ -40,7 +40,7 @@ def profiled_traffic(n):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the tile-sweep kernel from the
     committed `ncu --set full` capture of the same workload (profiles/, summarised by
     tools/ncu_summary.py), or None.  Not measured in this run: the line says so."""
-    path = os.path.join(ROOT, "profiles", "r02_ncu_qft_sweeps_n30.csv")
+    path = os.path.join(ROOT, "profiles", "r02_ncu_qft_sweeps_final_n30.csv")
     if n != 30 or not os.path.exists(path):
         return None, None
     try:

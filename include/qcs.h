@@ -251,7 +251,9 @@ int qcs_set_state_async(qcs_register *reg, unsigned long long first, unsigned lo
 /* Arbitrary single-qubit gate: the 2x2 complex matrix u (row-major, interleaved re/im, 8
  * doubles) on qubit_num -- what HADAMARD_BASE_MATRIX (Q:210-213) is one instance of -- and its
  * controlled form (u applied where bit c_qubit_num is 1), the generalisation of
- * C_PHASE_SHIFT_BASE_MATRIX (Q:220-225).  Same pair-stride pass as qcs_hadamard_gate. */
+ * C_PHASE_SHIFT_BASE_MATRIX (Q:220-225).  Same pair-stride pass as qcs_hadamard_gate.  Between
+ * qcs_fuse_begin and qcs_fuse_end a run of such gates whose qubits are all below 4 is multiplied up on
+ * the host and applied as ONE 16 x 16 dense block on the FP64 tensor cores when the run ends. */
 int qcs_apply_gate(qcs_register *reg, unsigned qubit_num, const double *u_interleaved);
 int qcs_apply_controlled_gate(qcs_register *reg, unsigned c_qubit_num, unsigned qubit_num,
                               const double *u_interleaved);

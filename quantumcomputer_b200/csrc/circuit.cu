@@ -61,12 +61,12 @@ k_diag_multi(double2 *__restrict__ amp, uint64_t n_pairs, const diag_gate *__res
 struct pass {
     int type;                   // 0: tile sweep, 1: single local Hadamard kernel, 2: global Hadamard(s),
                                 // 3: run of H qubits reaching the global ones, as sharded sweeps on peer memory
-    unsigned run_lo, run_hi;    // type 3
-    int group;
-    uint64_t hmask;             // qubits this pass applies H to
-    sweep_plan plan;            // type 0
-    unsigned q;                 // type 1
-    bool top_stages;            // type 2: all global qubits at once through the qubit-swap pipeline
+    unsigned run_lo = 0, run_hi = 0;    // type 3
+    int group = 0;
+    uint64_t hmask = 0;         // qubits this pass applies H to
+    sweep_plan plan = {};       // type 0
+    unsigned q = 0;             // type 1
+    bool top_stages = false;    // type 2: all global qubits at once through the qubit-swap pipeline
     std::vector<diag_gate> in_sweep;    // applied in the last step of the sweep (type 0)
     std::vector<int> in_sweep_idx;      // ... and their positions in the recorded stream
     std::vector<int> after;             // recorded gates applied by standalone kernels after the pass

@@ -482,9 +482,9 @@ static int measure_scan_sequential(qcs_register *reg, double cum_in, double r, u
 
 // scratch of the parallel scan (lazily allocated, sized for the whole shard)
 struct scan_buffers {
-    pair64 *maps, *super_maps;
-    double *csum;
-    int *code, *super_code;
+    pair64 *maps = nullptr, *super_maps = nullptr;
+    double *csum = nullptr;
+    int *code = nullptr, *super_code = nullptr;
 };
 
 static int scan_scratch(qcs_register *reg, scan_buffers &b)
