@@ -177,12 +177,21 @@ extern "C" int qcs_host_free(void *ptr)
         if (!(reg)) return QCS_BAD_ARGUMENTS;                       \
         QCS_CUDA(cudaSetDevice((reg)->device));                     \
         if (!(reg)->queue.empty() || (reg)->dense_pending) QCS_TRY(qcs_fuse_flush(reg));    \
+        if ((reg)->lazy_reset) QCS_TRY(qcs_materialise_reset(reg)); \
     } while (0)
 #define QCS_ENTER_GATE(reg)                         \
     do {                                            \
         if (!(reg)) return QCS_BAD_ARGUMENTS;       \
         QCS_CUDA(cudaSetDevice((reg)->device));     \
+        if ((reg)->lazy_reset && !((reg)->fusing && (reg)->opt_fusion)) QCS_TRY(qcs_materialise_reset(reg)); \
     } while (0)
+
+int qcs_materialise_reset(qcs_register *reg)
+{
+    if (!reg->lazy_reset) return QCS_NO_ERROR;
+    reg->lazy_reset = 0;
+    return qcs_k_reset(reg);
+}
 
 // ---------------------------------------------------------------------------
 // register life-cycle
@@ -247,6 +256,7 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->opt_l2_pair_lag = 3 * 148;
     reg->opt_l2_pair_max_block = 16ll << 20;     // measured: 32 MiB blocks (n = 30) no longer stay in the L2 (profiles/README.md)
     reg->fusing = 0;
+    reg->lazy_reset = 0;
     reg->dense_pending = 0;
     reg->dense_gates = 0;
     reg->d_diag = nullptr;
@@ -458,7 +468,17 @@ extern "C" int qcs_synchronize(qcs_register *reg)
 extern "C" int qcs_reset_register(qcs_register *reg)
 {
     QCS_GROUP_FORWARD(reg, qcs_reset_register(m));
-    QCS_ENTER(reg);
+    if (!reg) return QCS_BAD_ARGUMENTS;
+    QCS_CUDA(cudaSetDevice(reg->device));
+    // whatever was recorded or pending is overwritten by the reset: drop it
+    reg->queue.clear();
+    reg->dense_pending = 0;
+    if (reg->opt_fusion) {
+        // fused mode: written when first needed -- or never, when quantum_computation follows (qc_shor.c:922-923)
+        reg->lazy_reset = 1;
+        return QCS_NO_ERROR;
+    }
+    reg->lazy_reset = 0;
     return qcs_k_reset(reg);
 }
 
@@ -621,7 +641,14 @@ extern "C" int qcs_QFT_range(qcs_register *reg, unsigned lo, unsigned hi)
 extern "C" int qcs_quantum_computation(qcs_register *reg, unsigned C, unsigned a, int pow_mode)
 {
     QCS_GROUP_FORWARD(reg, qcs_quantum_computation(m, C, a, pow_mode));
-    QCS_ENTER(reg);
+    if (!reg) return QCS_BAD_ARGUMENTS;
+    QCS_CUDA(cudaSetDevice(reg->device));
+    // find_period's sequence reset_register -> quantum_computation (qc_shor.c:922-923): the state after the
+    // Hadamards and the controlled multiplications of |0...01> is known in closed form -- 2^(-L/2) at
+    // (x, a^x mod C built gate by gate exactly as c_amodc_gate would) -- and is written in ONE pass instead of
+    // a reset pass, the Walsh-Hadamard sweeps and the modular-exponentiation sweep
+    const bool from_reset = reg->lazy_reset && reg->queue.empty() && !reg->dense_pending && reg->opt_fusion && reg->L_size > 0;
+    if (!from_reset) QCS_ENTER(reg);
     if (C == 0 || (pow_mode != QCS_POW_VERBATIM && pow_mode != QCS_POW_MODULAR)) return QCS_BAD_ARGUMENTS;
     const unsigned first = reg->n - (unsigned) reg->L_size;          // qc_shor.c:720
     // atox per gate, qc_shor.c:728-731 (x doubles as an unsigned int)
@@ -635,6 +662,15 @@ extern "C" int qcs_quantum_computation(qcs_register *reg, unsigned C, unsigned a
     if (reg->opt_fusion && reg->L_size > 0) {
         std::vector<unsigned> A((size_t) reg->L_size);
         for (int k = 0; k < reg->L_size; k++) A[(size_t) k] = (unsigned) (atox[(size_t) k] % C);
+        if (from_reset) {
+            bool done = false;
+            QCS_TRY(qcs_shor_state_from_reset(reg, C, A.data(), (unsigned) reg->L_size, &done));
+            if (done) {
+                reg->lazy_reset = 0;
+                return qft_any(reg, (unsigned) reg->M_size, reg->n, true);
+            }
+            QCS_TRY(qcs_materialise_reset(reg));
+        }
         int rc = qcs_fused_modexp(reg, C, A.data(), (unsigned) reg->L_size);
         if (rc != QCS_NO_ERROR) return rc;
         return qft_any(reg, (unsigned) reg->M_size, reg->n, true);

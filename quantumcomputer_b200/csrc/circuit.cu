@@ -320,6 +320,7 @@ bool qcs_fuse_record_dense(qcs_register *reg, unsigned q, int c, const double *u
 
 int qcs_fuse_flush(qcs_register *reg)
 {
+    if (reg->lazy_reset) QCS_TRY(qcs_materialise_reset(reg));        // a deferred reset_register comes first
     if (reg->dense_pending) {
         // never both pending: recording into one launches the other first
         reg->dense_pending = 0;

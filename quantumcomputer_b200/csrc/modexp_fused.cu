@@ -119,6 +119,47 @@ k_modexp_sweep(double2 *__restrict__ amp, uint64_t n_chunks, const modexp_params
     }
 }
 
+// quantum_computation's first two loops (qc_shor.c:720-731) applied to the reset state |0...01>, in closed
+// form.  H on every qubit of the L register turns |x = 0, f = 1> into 2^(-L/2) sum_x |x, 1>; gate k then moves,
+// in every block x whose bit k is set, the block's single non-zero amplitude from f to (A_k f) % C when
+// f < C (32-bit unsigned product, row index masked to the M register: qc_shor.c:619-652) and leaves it
+// otherwise.  A single source per block never collides, so this holds for non-bijective multipliers and for
+// A_k = 0 (INT_POW overflow) as well.  One write pass; the value is the Walsh-Hadamard sweep's own scale.
+struct closed_params {
+    unsigned M, L, C, n_local, rank;
+    unsigned A[kMaxGates];
+    double value;
+};
+
+__global__ void __launch_bounds__(256)
+k_shor_state_from_reset(double2 *__restrict__ amp, uint64_t n_windows, int window_bits, const closed_params P)
+{
+    // a WINDOW = 2^window_bits <= 2^M consecutive amplitudes of one block (one x, one f).  Windows of >= 32
+    // amplitudes are written by a whole warp, lane t taking elements t, t + 32, ... (coalesced 512-byte
+    // stores; f is computed by every lane); smaller windows (M < 5) by one thread each.
+    const unsigned maskM = (1u << P.M) - 1u;
+    const bool by_warp = window_bits >= 5;
+    const uint64_t unit = by_warp ? ((uint64_t) blockIdx.x * 256 + threadIdx.x) >> 5 : (uint64_t) blockIdx.x * 256 + threadIdx.x;
+    const uint64_t stride = by_warp ? ((uint64_t) gridDim.x * 256) >> 5 : (uint64_t) gridDim.x * 256;
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint64_t w = unit; w < n_windows; w += stride) {
+        const uint64_t first = w << window_bits;                  // shard-local index of the window
+        uint64_t x = first >> P.M;
+        if (P.n_local < P.M + P.L) x |= (uint64_t) P.rank << (P.n_local - P.M);   // global qubits: the rank's bits
+        unsigned f = 1u;
+        for (unsigned k = 0; k < P.L; k++)
+            if (((x >> k) & 1ull) && f < P.C) f = ((P.A[k] * f) % P.C) & maskM;
+        const unsigned e0 = (unsigned) first & maskM;
+        if (by_warp) {
+            for (unsigned e = lane; e < (1u << window_bits); e += 32u)
+                amp[first + e] = make_double2(e0 + e == f ? P.value : 0.0, 0.0);
+        } else {
+            for (unsigned e = 0; e < (1u << window_bits); e++)
+                amp[first + e] = make_double2(e0 + e == f ? P.value : 0.0, 0.0);
+        }
+    }
+}
+
 unsigned h_gcd(unsigned a, unsigned b)
 {
     while (b) { const unsigned t = a % b; a = b; b = t; }
@@ -210,4 +251,37 @@ int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, 
     qcs_launch_begin(reg, QCS_K_MODEXP_SWEEP, 32.0 * (double) reg->N_local * (frac < 1.0 ? frac : 1.0));
     k_modexp_sweep<<<(unsigned) grid, threads, smem, reg->stream>>>(reg->amp, n_chunks, P);
     return qcs_launch_end(reg, QCS_K_MODEXP_SWEEP, "k_modexp_sweep");
+}
+
+
+int qcs_shor_state_from_reset(qcs_register *reg, unsigned C, const unsigned *A_per_gate, unsigned n_gates, bool *done)
+{
+    *done = false;
+    const unsigned M = (unsigned) reg->M_size, L = n_gates;
+    // M >= 1 (index 1 must belong to the M register, else the Hadamards see |x = 1>), controls = the whole L
+    // register, products below 2^32 as in c_amodc_gate, the M register inside the shard
+    if (M < 1 || M > 30 || L != (unsigned) reg->L_size || L > (unsigned) kMaxGates || C == 0 || C > 65536u || M > reg->n_local ||
+        reg->n != M + L)
+        return QCS_NO_ERROR;
+    closed_params P;
+    P.M = M;
+    P.L = L;
+    P.C = C;
+    P.n_local = reg->n_local;
+    P.rank = (unsigned) reg->rank;
+    for (unsigned k = 0; k < L; k++) P.A[k] = A_per_gate[k] % C;
+    // the scale the fused Walsh-Hadamard sweeps apply (qft_common.cuh): an exact power of two for even L
+    P.value = L % 2 == 0 ? ldexp(1.0, -(int) L / 2) : ldexp(0.70710678118654752440, -((int) L - 1) / 2);
+    const int window_bits = M < 8 ? (int) M : 8;              // 256 amplitudes = 4 KiB per warp iteration
+    const uint64_t n_windows = reg->N_local >> window_bits;
+    const uint64_t units_per_cta = window_bits >= 5 ? 8 : 256;
+    uint64_t grid = (n_windows + units_per_cta - 1) / units_per_cta;
+    const uint64_t cap = (uint64_t) reg->sm_count * 16;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    qcs_launch_begin(reg, QCS_K_FILL, 16.0 * (double) reg->N_local);
+    k_shor_state_from_reset<<<(unsigned) grid, 256, 0, reg->stream>>>(reg->amp, n_windows, window_bits, P);
+    QCS_TRY(qcs_launch_end(reg, QCS_K_FILL, "k_shor_state_from_reset"));
+    *done = true;
+    return QCS_NO_ERROR;
 }

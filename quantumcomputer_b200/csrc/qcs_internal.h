@@ -70,6 +70,11 @@ struct qcs_register {
     int opt_l2_pair_lag;          // tiles the second sweep of a pair trails the first by, beyond one block
     long long opt_l2_pair_max_block;   // largest block (bytes) a paired launch may use
 
+    // qcs_reset_register is deferred (fused mode): the all-zero-but-one state is only written when something
+    // needs it, so that quantum_computation from the reset state (qc_shor.c:922-923, every find_period) can write
+    // the state after the Hadamards and the modular exponentiation in closed form instead (modexp_fused.cu)
+    int lazy_reset;
+
     // deferred gate stream (qcs_fuse_begin .. qcs_fuse_end)
     int fusing;
     std::vector<qcs_pending_gate> queue;
@@ -150,6 +155,8 @@ __host__ __device__ __forceinline__ uint64_t qcs_insert_zero_bit(uint64_t x, uns
 
 // ---- per-gate (reference-order) kernels: gates_exact.cu -------------------
 int qcs_k_reset(qcs_register *reg);
+// write a deferred reset_register now (no-op when none is pending)
+int qcs_materialise_reset(qcs_register *reg);
 int qcs_k_collapse(qcs_register *reg, uint64_t local_index, bool owner);
 int qcs_k_fill_synthetic(qcs_register *reg, uint64_t seed);
 int qcs_k_scale(qcs_register *reg, double s);
@@ -191,6 +198,9 @@ int qcs_fused_top_sweep(qcs_register *reg, double2 *buf, unsigned c, unsigned p,
                         unsigned long long y_const, bool inverse, bool hadamard_only, cudaStream_t stream);
 // H on the L register, then all L controlled a^(2^k) mod C gates in one block-local sweep
 int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, unsigned n_gates);
+// the same two loops applied to the reset state |0...01> in closed form: one write pass.  *done = false: the
+// shape is not covered (caller writes the reset state and takes the general path)
+int qcs_shor_state_from_reset(qcs_register *reg, unsigned C, const unsigned *A_per_gate, unsigned n_gates, bool *done);
 
 // ---- general gates: gates_general.cu ------------------------------------------
 int qcs_k_gate_1q(qcs_register *reg, unsigned q, int c /* < 0: no control */, const double *u_interleaved);

@@ -267,3 +267,33 @@ def test_full_size_n30_properties(qcs):
         reg.inverse_QFT()
         mid2 = np.array([reg.get_state(i, 1)[0] for i in probes])
         assert np.max(np.abs(mid2 - 1j * mid)) <= 1e-12 * np.max(np.abs(mid)) * 10
+
+
+@pytest.mark.parametrize("L,M,Cn,a,mode", [(3, 4, 15, 7, 0), (5, 5, 21, 2, 0), (6, 5, 21, 4, 0), (3, 4, 15, 6, 0), (7, 4, 15, 7, 0),
+                                           (9, 5, 21, 2, 1), (8, 7, 77, 3, 1), (6, 11, 2047, 5, 1), (13, 6, 35, 4, 1),
+                                           (7, 4, 12, 10, 1), (5, 12, 4001, 7, 1), (6, 4, 21, 2, 1), (9, 1, 2, 3, 1), (16, 8, 221, 6, 1)])
+def test_quantum_computation_from_reset_closed_form(qcs, L, M, Cn, a, mode):
+    """reset_register + quantum_computation in fused mode writes the state after the Hadamards and the
+    controlled multiplications in closed form (one pass); it must equal the gate-by-gate kernels -- non-bijective
+    multipliers, A = 0 from the INT_POW overflow (L = 7, a = 7 verbatim), C > 2^M (row index masked), odd L."""
+    with qcs.Register(L, M) as fused, qcs.Register(L, M) as exact:
+        exact.set_option(qcs.OPT_FUSION, 0)
+        for reg in (fused, exact):
+            reg.reset_register()
+        before = fused.launch_count
+        fused.quantum_computation(Cn, a, mode)
+        launches = fused.launch_count - before
+        exact.quantum_computation(Cn, a, mode)
+        want, got = exact.get_state(), fused.get_state()
+        assert rel_l2(got, want) <= TOL
+        assert launches <= 1 + 4, launches            # one closed-form pass + the inverse-QFT sweeps
+        # the deferred reset is observable as a reset when nothing consumes it
+        fused.reset_register()
+        assert fused.nonzero_states()[0] == [1]
+        # ... and a second computation from a NON-reset state takes the general path
+        fused.hadamard_gate(M)
+        exact.reset_register()
+        exact.hadamard_gate(M)
+        fused.quantum_computation(Cn, a, mode)
+        exact.quantum_computation(Cn, a, mode)
+        assert rel_l2(fused.get_state(), exact.get_state()) <= TOL
