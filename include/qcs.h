@@ -185,7 +185,10 @@ int qcs_synchronize(qcs_register *reg);
 
 /* ---- gate path ---------------------------------------------------------- */
 
-/* void reset_register(Register), Q:318-324: state <- |0...01> (index 1). */
+/* void reset_register(Register), Q:318-324: state <- |0...01> (index 1).  With QCS_OPT_FUSION = 1 the
+ * write is deferred until something needs the state; qcs_quantum_computation right after it (the
+ * sequence of find_period, Q:922-923) never needs it: it writes the state after the Hadamards and the
+ * controlled multiplications in closed form.  Not observable through the ABI. */
 int qcs_reset_register(qcs_register *reg);
 
 /* void hadamard_gate(unsigned qubit_num, Register*, matrix*), Q:442-484. */
