@@ -186,11 +186,14 @@ extern "C" int qcs_host_free(void *ptr)
         if ((reg)->lazy_reset && !((reg)->fusing && (reg)->opt_fusion)) QCS_TRY(qcs_materialise_reset(reg)); \
     } while (0)
 
+// write the pending basis state: |0...01> of a deferred reset_register (qc_shor.c:318-324) or the collapsed
+// state of a measure_state (qc_shor.c:302-303)
 int qcs_materialise_reset(qcs_register *reg)
 {
     if (!reg->lazy_reset) return QCS_NO_ERROR;
     reg->lazy_reset = 0;
-    return qcs_k_reset(reg);
+    const uint64_t owner = reg->lazy_index >> reg->n_local;
+    return qcs_k_collapse(reg, reg->lazy_index & (reg->N_local - 1), owner == (uint64_t) reg->rank);
 }
 
 // ---------------------------------------------------------------------------
@@ -257,6 +260,7 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->opt_l2_pair_max_block = 16ll << 20;     // measured: 32 MiB blocks (n = 30) no longer stay in the L2 (profiles/README.md)
     reg->fusing = 0;
     reg->lazy_reset = 0;
+    reg->lazy_index = 1;
     reg->dense_pending = 0;
     reg->dense_gates = 0;
     reg->d_diag = nullptr;
@@ -476,6 +480,7 @@ extern "C" int qcs_reset_register(qcs_register *reg)
     if (reg->opt_fusion) {
         // fused mode: written when first needed -- or never, when quantum_computation follows (qc_shor.c:922-923)
         reg->lazy_reset = 1;
+        reg->lazy_index = 1;
         return QCS_NO_ERROR;
     }
     reg->lazy_reset = 0;
@@ -647,7 +652,7 @@ extern "C" int qcs_quantum_computation(qcs_register *reg, unsigned C, unsigned a
     // Hadamards and the controlled multiplications of |0...01> is known in closed form -- 2^(-L/2) at
     // (x, a^x mod C built gate by gate exactly as c_amodc_gate would) -- and is written in ONE pass instead of
     // a reset pass, the Walsh-Hadamard sweeps and the modular-exponentiation sweep
-    const bool from_reset = reg->lazy_reset && reg->queue.empty() && !reg->dense_pending && reg->opt_fusion && reg->L_size > 0;
+    const bool from_reset = reg->lazy_reset && reg->lazy_index == 1 && reg->queue.empty() && !reg->dense_pending && reg->opt_fusion && reg->L_size > 0;
     if (!from_reset) QCS_ENTER(reg);
     if (C == 0 || (pow_mode != QCS_POW_VERBATIM && pow_mode != QCS_POW_MODULAR)) return QCS_BAD_ARGUMENTS;
     const unsigned first = reg->n - (unsigned) reg->L_size;          // qc_shor.c:720
@@ -777,9 +782,15 @@ extern "C" int qcs_measure_state(qcs_register *reg, double r, unsigned long long
     if (!state_num) return QCS_BAD_ARGUMENTS;
     uint64_t global_index = 0;
     QCS_TRY(locate_state(reg, r, &global_index));
-    // collapse, qc_shor.c:302-303
-    const uint64_t owner = global_index >> reg->n_local;
-    QCS_TRY(qcs_k_collapse(reg, global_index & (reg->N_local - 1), owner == (uint64_t) reg->rank));
+    // collapse, qc_shor.c:302-303.  Fused mode: deferred like reset_register -- in find_period the next call
+    // is the next trial's reset_register, which overwrites it unseen
+    if (reg->opt_fusion) {
+        reg->lazy_reset = 1;
+        reg->lazy_index = global_index;
+    } else {
+        const uint64_t owner = global_index >> reg->n_local;
+        QCS_TRY(qcs_k_collapse(reg, global_index & (reg->N_local - 1), owner == (uint64_t) reg->rank));
+    }
     QCS_CUDA(cudaStreamSynchronize(reg->stream));
     *state_num = global_index;
     return QCS_NO_ERROR;
@@ -847,6 +858,12 @@ extern "C" int qcs_set_state(qcs_register *reg, unsigned long long first, unsign
             return qcs_set_state(m, a - lo, b - a, interleaved_in + 2 * (a - first));
         });
     }
+    // the whole shard is overwritten: whatever is pending (a deferred reset / collapse, recorded gates) is dead
+    if (reg && !reg->group && first == 0 && count == reg->N_local && interleaved_in) {
+        reg->lazy_reset = 0;
+        reg->queue.clear();
+        reg->dense_pending = 0;
+    }
     QCS_ENTER(reg);
     if (first > reg->N_local || count > reg->N_local - first || (!interleaved_in && count)) return QCS_BAD_ARGUMENTS;
     QCS_CUDA(cudaMemcpyAsync(reg->amp + first, interleaved_in, count * sizeof(double2),
@@ -869,6 +886,12 @@ extern "C" int qcs_set_state_async(qcs_register *reg, unsigned long long first, 
             if (a >= b) return QCS_NO_ERROR;
             return qcs_set_state_async(m, a - lo, b - a, interleaved_in + 2 * (a - first));
         });
+    }
+    // the whole shard is overwritten: whatever is pending (a deferred reset / collapse, recorded gates) is dead
+    if (reg && !reg->group && first == 0 && count == reg->N_local && interleaved_in) {
+        reg->lazy_reset = 0;
+        reg->queue.clear();
+        reg->dense_pending = 0;
     }
     QCS_ENTER(reg);
     if (first > reg->N_local || count > reg->N_local - first || (!interleaved_in && count)) return QCS_BAD_ARGUMENTS;
@@ -936,6 +959,12 @@ extern "C" int qcs_nonzero_states(qcs_register *reg, unsigned long long capacity
 extern "C" int qcs_fill_synthetic(qcs_register *reg, unsigned long long seed)
 {
     QCS_GROUP_FORWARD(reg, qcs_fill_synthetic(m, seed));
+    // the whole shard is overwritten: whatever is pending (a deferred reset / collapse, recorded gates) is dead
+    if (reg && !reg->group && true) {
+        reg->lazy_reset = 0;
+        reg->queue.clear();
+        reg->dense_pending = 0;
+    }
     QCS_ENTER(reg);
     return qcs_k_fill_synthetic(reg, seed);
 }

@@ -74,6 +74,7 @@ struct qcs_register {
     // needs it, so that quantum_computation from the reset state (qc_shor.c:922-923, every find_period) can write
     // the state after the Hadamards and the modular exponentiation in closed form instead (modexp_fused.cu)
     int lazy_reset;
+    uint64_t lazy_index;          // the pending basis state (1 after reset_register; the measured index after measure_state)
 
     // deferred gate stream (qcs_fuse_begin .. qcs_fuse_end)
     int fusing;
