@@ -76,8 +76,8 @@ enum {
     /* 1 (default): fused sweeps use the TMA + mbarrier pipelined kernel where it
      * applies (tile = 2^12 amplitudes by default); 0: the direct global<->register kernel. */
     QCS_OPT_PIPELINE = 5,
-    /* how many tiles ahead of its TMA load the pipelined sweep prefetches into L2
-     * (0 = off, the default: measured slower on B200, see profiles/README.md) */
+    /* accepted and ignored: the L2 prefetch ahead of the TMA ring was measured slower on B200 in both
+     * rounds (profiles/README.md) and its code is gone */
     QCS_OPT_PREFETCH_TILES = 6,
     /* which instantiated shape of the pipelined sweep runs (tile size, ring depth, consumer
      * groups; csrc/qft_pipeline.cu kShapes).  Tuning knob; -1 = library default. */

@@ -54,7 +54,7 @@ struct qcs_register {
     int opt_fusion;
     int opt_profile;
     int opt_tile_bits;
-    int opt_prefetch_tiles;       // L2 prefetch distance of the pipelined sweep (tiles)
+    int opt_prefetch_tiles;       // accepted, ignored (the L2 prefetch was measured slower and removed)
     int opt_pipeline;             // 1: TMA/mbarrier pipelined sweep kernel where it applies
     int opt_pipe_shape;           // which instantiated pipeline shape (qft_pipeline.cu kShapes)
     int opt_overlap_slices;       // sharded QFT: the global sweep runs in this many slices, the local strided
