@@ -35,3 +35,21 @@ def test_gpu_arm_fails_loudly_without_a_gpu(qcs):
     assert out.returncode != 0
     assert "no usable CUDA device" in out.stderr and "no CPU path" in out.stderr
     assert not out.stdout.strip(), "no bench line may be printed without a GPU"
+
+
+def test_bench_helpers_on_cpu(oracle_built):
+    """The pieces of bench.py that run on the host: the closed-form index helper, the size of the reference
+    sample, and the matrix-free CPU baseline (one thread and, when OpenMP is available, all cores)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.bitrev(0b0011, 4) == 0b1100 and bench.bitrev(1, 30) == 1 << 29
+    assert bench.qft_gate_count(30) == 465
+    assert bench.reference_n_for(25) == bench.REF_N                       # the driver's 20 + 5 runs keep n = 12
+    assert bench.reference_n_for(500) < bench.REF_N
+    one = bench.port_gate_rate(12, False, 0.3)
+    assert one["kind"] == "port" and one["cores"] == 1 and one["value"] > 0 and one["qubits"] == 12
+    if oracle_built.have_restatement_omp():
+        many = bench.port_gate_rate(12, True, 0.3)
+        assert many["cores"] >= 1 and many["value"] > 0
+    traffic, src = bench.profiled_traffic(30)
+    assert traffic is None or (3.3e10 < traffic < 3.6e10 and src.startswith("profiles/"))
