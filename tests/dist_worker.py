@@ -158,7 +158,21 @@ def main():
             both(lambda r: r.reset_register())
             both(lambda r: r.quantum_computation(21, 2, q.POW_MODULAR))
             got = gather_state(sh, rank, world)
-            check(f"n={n} M={M} fused quantum_computation", got, single.get_state() if rank == 0 else None)
+            check(f"n={n} M={M} fused quantum_computation (closed form from reset)", got, single.get_state() if rank == 0 else None)
+            # ... and from a state that is not the reset state: sharded Walsh-Hadamard sweeps + modexp sweep + inverse QFT
+            both(lambda r: r.quantum_computation(21, 4, q.POW_MODULAR))
+            got = gather_state(sh, rank, world)
+            check(f"n={n} M={M} fused quantum_computation (general path)", got, single.get_state() if rank == 0 else None)
+            # a measurement, then the next trial's reset + computation (deferred collapse and reset on every shard)
+            a = sh.measure_state(0.4242)
+            if rank == 0:
+                b = single.measure_state(0.4242)
+                if a != b:
+                    failures.append("measure after quantum_computation")
+            both(lambda r: r.reset_register())
+            both(lambda r: r.quantum_computation(21, 5, q.POW_MODULAR))
+            got = gather_state(sh, rank, world)
+            check(f"n={n} M={M} second trial after measure_state", got, single.get_state() if rank == 0 else None)
         sh.close()
         if single is not None:
             single.close()
