@@ -9,6 +9,7 @@
 #include "qcs_internal.h"
 
 #include <dlfcn.h>
+#include <mutex>
 #include <nccl.h>     // types only; every entry point is looked up at run time
 #include <string.h>
 
@@ -30,7 +31,17 @@ struct nccl_api {
 
 nccl_api g_nccl;
 
+int load_nccl_once();
 int load_nccl()
+{
+    // threads of one process may create shards at the same time (group.cu)
+    static std::once_flag once;
+    static int rc = QCS_UNKNOWN_ERROR;
+    std::call_once(once, [] { rc = load_nccl_once(); });
+    return rc;
+}
+
+int load_nccl_once()
 {
     if (g_nccl.handle) return QCS_NO_ERROR;
     void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);

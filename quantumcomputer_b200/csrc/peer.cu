@@ -23,6 +23,7 @@
 
 #include <cuda.h>
 #include <errno.h>
+#include <mutex>
 #include <poll.h>
 #include <pthread.h>
 #include <stdlib.h>
@@ -59,7 +60,17 @@ struct driver_api {
 
 driver_api g_drv;
 
+// the worker threads of a single-caller register (group.cu) arrive here at the same time: resolve once
+bool load_driver_once();
 bool load_driver()
+{
+    static std::once_flag once;
+    static bool ok = false;
+    std::call_once(once, [] { ok = load_driver_once(); });
+    return ok;
+}
+
+bool load_driver_once()
 {
     if (g_drv.ok) return true;
     struct { const char *name; void **slot; } syms[] = {
