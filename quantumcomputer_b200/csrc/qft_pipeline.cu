@@ -401,6 +401,8 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             const uint32_t round = (uint32_t) (k / STAGES);
             double2 *tile = stage_buf + (size_t) s * (1u << TB);
             const long long t0 = QCS_TICK(P);
+            // every thread waits on the barrier itself: electing one lane per warp to poll (the others at
+            // __syncwarp) was measured 10 % slower (24.05 against 21.81 ms at n = 30)
             mbar_wait(&full[s], round & 1u);
             const long long t1 = QCS_TICK(P);
             const uint64_t item = s_item[s];
