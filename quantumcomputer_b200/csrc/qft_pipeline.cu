@@ -323,7 +323,7 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
                 mbar_expect_tx(&full[s], kTileBytes);
                 unsigned char *dst = (unsigned char *) (stage_buf + (size_t) s * (1u << TB));
                 const CUtensorMap *map = ph ? &tmap1 : &tmap0;
-                if (paired && P.l2_hints) {
+                if (P.l2_hints) {
                     // A's input and B's input (A's output, read for the last time) may leave the L2 first
                     for (int b = 0; b < Q.n_boxes; b++)
                         tma_load_3d_hint(dst + (size_t) b * Q.box_bytes, map, &full[s], c0, c1 + b * Q.box_rows, c2, pol_stream);
@@ -366,9 +366,9 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
                 tile_coords<TB>(Q, paired ? pair_tile(P, Q, idx) : tile_number(Q.d, idx), c0, c1, c2);
                 const unsigned char *src = (const unsigned char *) (stage_buf + (size_t) s * (1u << TB));
                 const CUtensorMap *map = ph ? &tmap1 : &tmap0;
-                if (paired && P.l2_hints) {
-                    // A's output stays in the L2 until B has read it; B's output is final
-                    const uint64_t pol = ph == 0 ? pol_keep : pol_stream;
+                if (P.l2_hints) {
+                    // A's output stays in the L2 until B has read it; B's output (and a single sweep's) is final
+                    const uint64_t pol = (PAIRED && ph == 0) ? pol_keep : pol_stream;
                     for (int b = 0; b < Q.n_boxes; b++)
                         tma_store_3d_hint(map, src + (size_t) b * Q.box_bytes, c0, c1 + b * Q.box_rows, c2, pol);
                 } else {
@@ -681,6 +681,7 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
     P.ph[0].wcol_base = 0;
     P.n_phases = 1;
     P.n_tiles = plan.n_tiles;
+    P.l2_hints = 0;              // evict_first on a single sweep's traffic was measured: no effect (21.6 ms either way)
     return run_launch(reg, sh, shape_id, tmap, tmap, P, pipe_smem(sh, plan.d.wcol_total, plan.d.n_diag), tg);
 }
 
