@@ -12,6 +12,9 @@
 //    sequential additions and the `>=` test.
 #include "qcs_internal.h"
 
+#include <stdlib.h>
+#include <vector>
+
 namespace {
 
 constexpr int kRedThreads = 256;
@@ -141,11 +144,17 @@ k_measure_scan(const double2 *__restrict__ amp, uint64_t limit, double cum_in, d
 //  pass 2  prefix of those sums; a chunk is CLEAN(e) when rigorous error
 //          bounds (relative margin delta >= 4 N 2^-53) prove that the exact
 //          sequential sum stays inside binade e throughout the chunk AND stays
-//          below r; ZERO when all its p are 0; otherwise SEQ
+//          below r; ZERO when all its p are 0 -- or all below half an ulp of
+//          the smallest possible running sum, so that none of them moves it
+//          (pass 1 also keeps each chunk's largest p); otherwise SEQ
 //  pass 3  (de, do) of every CLEAN chunk, then of every uniform super-chunk
 //  pass 4  one CTA walks the summaries in index order carrying the exact s;
-//          SEQ chunks (binade crossings, the neighbourhood of r) are added
-//          element by element with the `>=` test of qc_shor.c:289
+//          a SEQ chunk (binade crossing, the neighbourhood of r) is refined on
+//          the spot into 128 sub-chunks of 32 elements, classified the same
+//          way from the exact s at its start; only the SEQ sub-chunks are
+//          added element by element with the `>=` test of qc_shor.c:289
+//          (a Shor state after the inverse QFT has ~200 SEQ chunks: 4096
+//          dependent additions each made the walk 22-37 ms at n = 30)
 //
 // The result is the index the reference's loop (qc_shor.c:283-292) returns.
 // ---------------------------------------------------------------------------
@@ -155,6 +164,7 @@ constexpr int kSuperBits = 8;
 constexpr int kSuper = 1 << kSuperBits;
 constexpr int kWalkBlock = 512;                  // summaries staged per round of the walk (>= kSuper)
 constexpr int kCodeSeq = -1, kCodeZero = -2;     // otherwise: binade exponent + 2000
+constexpr double kSubDelta = 0x1p-36;            // relative bound on a running sum over <= 4096 additions, with margin
 
 struct pair64 { long long de, od; };
 
@@ -166,50 +176,64 @@ __device__ __forceinline__ pair64 compose(pair64 f1, pair64 f2)
     return r;
 }
 
-// the map of one addend p inside binade e
-__device__ __forceinline__ pair64 element_map(double p, int e)
+// Every addend of the (sub-)chunk is below half an ulp of ANY running sum >= 2^e_lo: RN(s + p) = s all the
+// way through, whichever binade s is in -- the chunk is skipped like a ZERO one.  This is what keeps the
+// plateaus of a symmetric state cheap: a Shor state after the inverse QFT parks the running sum within
+// rounding of 1/4 and 1/2 for a hundred chunks of 1e-30 addends, where no bound can name the binade.
+__device__ __forceinline__ bool absorbed(double biggest, int e_lo)
 {
-    const unsigned long long bits = (unsigned long long) __double_as_longlong(p);
-    const int ef = (int) ((bits >> 52) & 0x7ff);
-    unsigned long long m = bits & 0xfffffffffffffull;
-    int ep;
-    if (ef == 0) ep = -1022; else { m |= 1ull << 52; ep = ef - 1023; }
+    return biggest < ldexp(1.0, e_lo - 53);      // 0 when e_lo - 53 < -1074: never true then
+}
+
+// 2^(52 - e): p * scale = p / ulp of binade e (exact: a power of two; -960 < e keeps it finite)
+__device__ __forceinline__ double binade_scale(int e)
+{
+    return __longlong_as_double((long long) (1023 + 52 - e) << 52);
+}
+
+// the map of one addend p inside the binade whose scale is given.  x = p / ulp < 2^53 exactly;
+// RN(a + x) - a = RNint(x) unless x is an exact tie k + 1/2, where the parity of a decides: an even a
+// rounds like x itself (half to even), an odd a takes the other neighbour.  Branch-free: this runs once
+// per amplitude of the scanned range.
+__device__ __forceinline__ pair64 element_map(double p, double scale)
+{
+    const double x = p * scale;
     pair64 r;
-    const int shift = e - ep;                    // p / ulp = m * 2^-shift
-    if (m == 0 || shift >= 55) { r.de = r.od = 0; return r; }
-    if (shift <= 0) {                            // cannot happen in a CLEAN chunk; keep it exact anyway
-        const long long k = (long long) (m << (-shift > 10 ? 10 : -shift));
-        r.de = r.od = k;
-        return r;
-    }
-    const unsigned long long k = shift >= 64 ? 0ull : (m >> shift);
-    const unsigned long long rem = m & ((1ull << shift) - 1ull);
-    const unsigned long long half = 1ull << (shift - 1);
-    if (rem < half) { r.de = r.od = (long long) k; }
-    else if (rem > half) { r.de = r.od = (long long) k + 1; }
-    else { r.de = (long long) (k + (k & 1ull)); r.od = (long long) (k + 1ull - (k & 1ull)); }
+    r.de = __double2ll_rn(x);
+    const double t = x - (double) r.de;              // exact
+    r.od = r.de + (t == 0.5 ? 1 : 0) - (t == -0.5 ? 1 : 0);
     return r;
 }
 
 __global__ void __launch_bounds__(256)
-k_chunk_sums(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks, double *__restrict__ csum)
+k_chunk_sums(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks, double *__restrict__ csum,
+             double *__restrict__ cmax)
 {
-    __shared__ double warp_part[8];
+    __shared__ double warp_part[8], warp_big[8];
     for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const uint64_t base = c << kChunkBits;
-        double s = 0.0;
+        double s = 0.0, big = 0.0;
 #pragma unroll 4
         for (int u = 0; u < kChunk / 256; u++) {
             const uint64_t i = base + (uint64_t) u * 256 + threadIdx.x;
-            if (i < limit) s += abs2_ref(amp[i]);
+            if (i < limit) {
+                const double p = abs2_ref(amp[i]);
+                s += p;
+                big = fmax(big, p);
+            }
         }
         s = warp_sum(s);
-        if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = s;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) big = fmax(big, __shfl_xor_sync(0xffffffffu, big, o));
+        if ((threadIdx.x & 31) == 0) { warp_part[threadIdx.x >> 5] = s; warp_big[threadIdx.x >> 5] = big; }
         __syncthreads();
         if (threadIdx.x < 32) {
             double v = threadIdx.x < 8 ? warp_part[threadIdx.x] : 0.0;
+            double m = threadIdx.x < 8 ? warp_big[threadIdx.x] : 0.0;
             v = warp_sum(v);
-            if (threadIdx.x == 0) csum[c] = v;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (threadIdx.x == 0) { csum[c] = v; cmax[c] = m; }
         }
         __syncthreads();
     }
@@ -217,8 +241,8 @@ k_chunk_sums(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
 
 // single CTA: exclusive prefix over chunk sums + classification
 __global__ void __launch_bounds__(1024)
-k_classify(const double *__restrict__ csum, uint64_t n_chunks, double cum_in, double r, double delta,
-           int *__restrict__ code, int *__restrict__ super_code)
+k_classify(const double *__restrict__ csum, const double *__restrict__ cmax, uint64_t n_chunks, double cum_in,
+           double r, double delta, int *__restrict__ code, int *__restrict__ super_code)
 {
     __shared__ double warp_tot[32];
     __shared__ double carry_s;
@@ -243,11 +267,12 @@ k_classify(const double *__restrict__ csum, uint64_t n_chunks, double cum_in, do
             int cd = kCodeSeq;
             const double lo = P * (1.0 - delta), hi = (P + v) * (1.0 + delta);
             if (v == 0.0) cd = kCodeZero;
-            else if (hi < r && lo > 0.0) {
+            else if (lo > 0.0) {
                 int e;
                 frexp(lo, &e);                       // lo = f * 2^e, f in [0.5, 1)  ->  binade e-1
                 e -= 1;
-                if (hi < ldexp(1.0, e + 1) && e > -1000) cd = e + 2000;
+                if (absorbed(cmax[c], e)) cd = kCodeZero;
+                else if (hi < r && hi < ldexp(1.0, e + 1) && e > -960) cd = e + 2000;
             }
             code[c] = cd;
         }
@@ -284,7 +309,7 @@ k_chunk_maps(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
     for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const int cd = code[c];
         if (cd < 0) continue;
-        const int e = cd - 2000;
+        const double scale = binade_scale(cd - 2000);
         const uint64_t base = c << kChunkBits;
         for (int u = 0; u < kChunk / 128; u++) {
             const int i = u * 128 + threadIdx.x;
@@ -292,7 +317,7 @@ k_chunk_maps(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
         }
         __syncthreads();
         pair64 f = {0, 0};
-        for (int k = 0; k < 32; k++) f = compose(f, element_map(p[threadIdx.x * 33 + k], e));
+        for (int k = 0; k < 32; k++) f = compose(f, element_map(p[threadIdx.x * 33 + k], scale));
         // ordered reduction: lane 0 ends with the composition of lanes 0..31 in order
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -327,17 +352,21 @@ struct walk_result {
     unsigned long long index;
     int found;
     int bad;           // an invariant failed: caller falls back to the plain sequential scan
+    unsigned seq_chunks;        // chunks refined into sub-chunks              (QCS_MEASURE_DEBUG prints both)
+    unsigned mixed_supers;      // super-chunks walked chunk by chunk
 };
 
-// apply a (de, do) map valid in binade e to the exact running sum
+// apply a (de, do) map valid in binade e to the exact running sum.  Integer arithmetic on the bit
+// pattern (s >= 0 is normal with exponent field e + 1023, a = 2^52 + mantissa): the serial walk applies
+// thousands of these back to back, and two ldexp calls each were most of its time.
 __device__ __forceinline__ bool apply_map(double &s, pair64 f, int e)
 {
-    const double a_d = ldexp(s, 52 - e);
-    if (!(a_d >= 4503599627370496.0 && a_d < 9007199254740992.0)) return false;
-    const long long a = (long long) a_d;
+    const unsigned long long bits = (unsigned long long) __double_as_longlong(s);
+    if ((long long) (bits >> 52) != (long long) e + 1023) return false;
+    const long long a = (long long) ((bits & 0xfffffffffffffull) | (1ull << 52));
     const long long a2 = a + ((a & 1) ? f.od : f.de);
-    if (a2 >= 9007199254740992ll) return false;
-    s = ldexp((double) a2, e - 52);
+    if (a2 < (1ll << 52) || a2 >= (1ll << 53)) return false;
+    s = __longlong_as_double((long long) (((unsigned long long) (e + 1023) << 52) | ((unsigned long long) a2 & 0xfffffffffffffull)));
     return true;
 }
 
@@ -354,11 +383,19 @@ k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
     __shared__ double p[kChunk];
     __shared__ int s_code[kWalkBlock];
     __shared__ pair64 s_map[kWalkBlock];
+    __shared__ int sub_code[kChunk / 32];
+    __shared__ pair64 sub_map[kChunk / 32];
+    __shared__ double warp_tot[32];
+    __shared__ int warp_code[32];
+    __shared__ pair64 warp_map[32];
+    __shared__ double s_run;           // exact running sum at the start of the chunk being refined
     __shared__ long long req;          // index requested by thread 0 (-1: none)
     __shared__ int s_found, s_bad;
+    const int lane = threadIdx.x & 31;
     const uint64_t n_super = (n_chunks + kSuper - 1) >> kSuperBits;
     double s = cum_in;
     uint64_t hit = 0;
+    unsigned n_seq = 0, n_mixed = 0;
     if (threadIdx.x == 0) { s_found = 0; s_bad = 0; req = -1; }
     __syncthreads();
 
@@ -388,6 +425,7 @@ k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
             if (s_bad) break;
             if (req < 0) { sc_next = sb_end; break; }
             const uint64_t sc = (uint64_t) req;
+            n_mixed++;
             // walk the chunks of the non-uniform super-chunk sc
             const uint64_t c_begin = sc << kSuperBits;
             const uint64_t c_end = c_begin + kSuper < n_chunks ? c_begin + kSuper : n_chunks;
@@ -413,17 +451,114 @@ k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
                 if (s_bad || req < 0) break;
                 const uint64_t c = (uint64_t) req;
                 const uint64_t base = c << kChunkBits;
+                n_seq++;
+                // Refine the chunk: 128 sub-chunks of 32 elements, 8 threads each.  The same three
+                // classes one level down, now measured from the EXACT running sum at the chunk's start, so
+                // the bound only has to cover <= 4096 additions (2 * gamma_4096 < 2^-39 < kSubDelta).
+                // Thread 0 then adds element by element only inside the sub-chunks that cross a binade
+                // boundary or reach r -- a handful of 32-element runs instead of 4096 dependent additions.
+                if (threadIdx.x == 0) s_run = s;
+                double q[4];
 #pragma unroll
-                for (int u = 0; u < kChunk / 1024; u++) {
-                    const uint64_t i = base + (uint64_t) u * 1024 + threadIdx.x;
-                    p[u * 1024 + threadIdx.x] = i < limit ? abs2_ref(amp[i]) : 0.0;
+                for (int k = 0; k < 4; k++) {
+                    const uint64_t i = base + 4u * threadIdx.x + k;
+                    q[k] = i < limit ? abs2_ref(amp[i]) : 0.0;
+                    p[4 * threadIdx.x + k] = q[k];
+                }
+                const double mine = (q[0] + q[1]) + (q[2] + q[3]);
+                double x = mine;                                        // inclusive scan over the CTA
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double y = __shfl_up_sync(0xffffffffu, x, o);
+                    if (lane >= o) x += y;
+                }
+                double excl = __shfl_up_sync(0xffffffffu, x, 1);
+                if (lane == 0) excl = 0.0;
+                if (lane == 31) warp_tot[threadIdx.x >> 5] = x;
+                __syncthreads();
+                double before = 0.0;
+                for (int w = 0; w < (int) (threadIdx.x >> 5); w++) before += warp_tot[w];
+                const int g0 = lane & ~7;
+                const double p_start = s_run + (before + __shfl_sync(0xffffffffu, excl, g0));
+                const double p_end = s_run + (before + __shfl_sync(0xffffffffu, x, g0 | 7));
+                double gsum = mine;                                     // exactly 0 iff all 32 addends are 0
+                gsum += __shfl_xor_sync(0xffffffffu, gsum, 1);
+                gsum += __shfl_xor_sync(0xffffffffu, gsum, 2);
+                gsum += __shfl_xor_sync(0xffffffffu, gsum, 4);
+                double gmax = fmax(fmax(q[0], q[1]), fmax(q[2], q[3]));
+                gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 1));
+                gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 2));
+                gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 4));
+                int cd = kCodeSeq;
+                if (gsum == 0.0) cd = kCodeZero;
+                else {
+                    const double lo = p_start * (1.0 - kSubDelta), hi = p_end * (1.0 + kSubDelta);
+                    if (lo > 0.0) {
+                        int e;
+                        frexp(lo, &e);
+                        e -= 1;
+                        if (absorbed(gmax, e)) cd = kCodeZero;
+                        else if (hi < r && hi < ldexp(1.0, e + 1) && e > -960) cd = e + 2000;
+                    }
+                }
+                pair64 f = {0, 0};
+                if (cd >= 0) {
+                    const double scale = binade_scale(cd - 2000);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) f = compose(f, element_map(q[k], scale));
+                }
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {                       // ordered: lane g0 ends with lanes g0..g0+7
+                    pair64 g;
+                    g.de = __shfl_down_sync(0xffffffffu, f.de, o);
+                    g.od = __shfl_down_sync(0xffffffffu, f.od, o);
+                    if (((lane & 7) & (2 * o - 1)) == 0) f = compose(f, g);
+                }
+                if ((lane & 7) == 0) { sub_code[threadIdx.x >> 3] = cd; sub_map[threadIdx.x >> 3] = f; }
+                // one level up: the warp's 4 sub-chunks collapse into one map when none is SEQ and the
+                // CLEAN ones agree on the binade (a ZERO sub-chunk carries the identity map {0, 0})
+                const int lo_cd = __reduce_min_sync(0xffffffffu, cd >= 0 ? cd : 0x7fffffff);
+                const int hi_cd = __reduce_max_sync(0xffffffffu, cd >= 0 ? cd : -1);
+                const bool any_seq = __any_sync(0xffffffffu, cd == kCodeSeq);
+#pragma unroll
+                for (int o = 8; o < 32; o <<= 1) {
+                    pair64 g;
+                    g.de = __shfl_down_sync(0xffffffffu, f.de, o);
+                    g.od = __shfl_down_sync(0xffffffffu, f.od, o);
+                    if ((lane & (2 * o - 1)) == 0) f = compose(f, g);
+                }
+                if (lane == 0) {
+                    const int w = threadIdx.x >> 5;
+                    warp_code[w] = any_seq || (hi_cd >= 0 && lo_cd != hi_cd) ? kCodeSeq : (hi_cd >= 0 ? hi_cd : kCodeZero);
+                    warp_map[w] = f;
                 }
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     const uint64_t len = limit - base < (uint64_t) kChunk ? limit - base : (uint64_t) kChunk;
-                    for (uint64_t j = 0; j < len; j++) {
-                        s = __dadd_rn(s, p[j]);                 // qc_shor.c:286
-                        if (!RECORD && s >= r) { hit = base + j; s_found = 1; break; }   // qc_shor.c:289
+                    for (int w = 0; w < 32 && !s_found && !s_bad; w++) {
+                        const int wd = warp_code[w];
+                        if (wd == kCodeZero) continue;
+                        if (wd >= 0) {
+                            if (!apply_map(s, warp_map[w], wd - 2000)) s_bad = 1;
+                            continue;
+                        }
+                        for (int j = 4 * w; j < 4 * w + 4 && !s_found && !s_bad; j++) {
+                            const int sd = sub_code[j];
+                            if (sd == kCodeZero) continue;
+                            if (sd >= 0) {
+                                if (!apply_map(s, sub_map[j], sd - 2000)) s_bad = 1;
+                                continue;
+                            }
+                            double v[32];                                // fetched ahead of the dependent chain
+#pragma unroll
+                            for (int k = 0; k < 32; k++) v[k] = p[32 * j + k];
+#pragma unroll
+                            for (int k = 0; k < 32; k++) {
+                                if ((uint64_t) (32 * j + k) >= len) break;
+                                s = __dadd_rn(s, v[k]);                 // qc_shor.c:286
+                                if (!RECORD && s >= r) { hit = base + 32 * j + k; s_found = 1; break; }   // qc_shor.c:289
+                            }
+                        }
                     }
                 }
                 __syncthreads();
@@ -439,6 +574,8 @@ k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
         out->index = hit;
         out->found = s_found;
         out->bad = s_bad;
+        out->seq_chunks = n_seq;
+        out->mixed_supers = n_mixed;
     }
 }
 
@@ -483,7 +620,7 @@ static int measure_scan_sequential(qcs_register *reg, double cum_in, double r, u
 // scratch of the parallel scan (lazily allocated, sized for the whole shard)
 struct scan_buffers {
     pair64 *maps = nullptr, *super_maps = nullptr;
-    double *csum = nullptr;
+    double *csum = nullptr, *cmax = nullptr;
     int *code = nullptr, *super_code = nullptr;
 };
 
@@ -492,7 +629,7 @@ static int scan_scratch(qcs_register *reg, scan_buffers &b)
     const uint64_t cap_chunks = (reg->N_local + kChunk - 1) >> kChunkBits;
     const uint64_t cap_super = (cap_chunks + kSuper - 1) >> kSuperBits;
     if (!reg->d_meas) {
-        const size_t bytes = cap_chunks * (sizeof(double) + sizeof(int) + sizeof(pair64)) +
+        const size_t bytes = cap_chunks * (2 * sizeof(double) + sizeof(int) + sizeof(pair64)) +
                              cap_super * (sizeof(int) + sizeof(pair64)) + 64;
         QCS_CUDA(cudaMalloc(&reg->d_meas, bytes));
     }
@@ -500,6 +637,7 @@ static int scan_scratch(qcs_register *reg, scan_buffers &b)
     b.maps = (pair64 *) at;            at += cap_chunks * sizeof(pair64);
     b.super_maps = (pair64 *) at;      at += cap_super * sizeof(pair64);
     b.csum = (double *) at;            at += cap_chunks * sizeof(double);
+    b.cmax = (double *) at;            at += cap_chunks * sizeof(double);
     b.code = (int *) at;               at += cap_chunks * sizeof(int);
     b.super_code = (int *) at;
     return QCS_NO_ERROR;
@@ -520,7 +658,7 @@ static int scan_sums(qcs_register *reg, uint64_t first, uint64_t limit)
     QCS_TRY(scan_scratch(reg, b));
     const uint64_t n_chunks = (limit + kChunk - 1) >> kChunkBits;
     qcs_launch_begin(reg, QCS_K_REDUCE, 16.0 * (double) limit);
-    k_chunk_sums<<<scan_grid(reg, n_chunks), 256, 0, reg->stream>>>(reg->amp + first, limit, n_chunks, b.csum);
+    k_chunk_sums<<<scan_grid(reg, n_chunks), 256, 0, reg->stream>>>(reg->amp + first, limit, n_chunks, b.csum, b.cmax);
     return qcs_launch_end(reg, QCS_K_REDUCE, "k_chunk_sums");
 }
 
@@ -538,7 +676,7 @@ static int scan_maps(qcs_register *reg, uint64_t first, double approx_cum_in, do
     // so the margin also covers an approximate running sum handed over from the shards before)
     const double delta = ldexp(1.0, (int) reg->n + 3 - 53);
     qcs_launch_begin(reg, QCS_K_REDUCE, 12.0 * (double) n_chunks);
-    k_classify<<<1, 1024, 0, reg->stream>>>(b.csum, n_chunks, approx_cum_in, r, delta, b.code, b.super_code);
+    k_classify<<<1, 1024, 0, reg->stream>>>(b.csum, b.cmax, n_chunks, approx_cum_in, r, delta, b.code, b.super_code);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_classify"));
     qcs_launch_begin(reg, QCS_K_REDUCE, 16.0 * (double) limit * (r < 1.0 ? (r > 0.0 ? r : 0.0) : 1.0));
     k_chunk_maps<<<scan_grid(reg, n_chunks), 128, 0, reg->stream>>>(amp, limit, n_chunks, b.code, b.maps);
@@ -571,6 +709,26 @@ static int scan_walk(qcs_register *reg, uint64_t first, double cum_in, double r,
     QCS_CUDA(cudaMemcpyAsync(reg->h_small, d_res, sizeof(walk_result), cudaMemcpyDeviceToHost, reg->stream));
     QCS_CUDA(cudaStreamSynchronize(reg->stream));
     const walk_result *h = (const walk_result *) reg->h_small;
+    static const bool debug = getenv("QCS_MEASURE_DEBUG") != nullptr;
+    if (debug)
+        fprintf(stderr, "qcs measure walk: %llu chunks, %llu super-chunks: %u chunks refined, %u super-chunks chunk by chunk\n",
+                (unsigned long long) n_chunks, (unsigned long long) n_super, h->seq_chunks, h->mixed_supers);
+    if (debug && getenv("QCS_MEASURE_DEBUG")[0] == '2') {      // which chunks, and why
+        std::vector<int> code(n_chunks);
+        std::vector<double> csum(n_chunks), cmax(n_chunks);
+        cudaMemcpy(code.data(), b.code, n_chunks * sizeof(int), cudaMemcpyDeviceToHost);
+        cudaMemcpy(csum.data(), b.csum, n_chunks * sizeof(double), cudaMemcpyDeviceToHost);
+        cudaMemcpy(cmax.data(), b.cmax, n_chunks * sizeof(double), cudaMemcpyDeviceToHost);
+        double run = cum_in;
+        int shown = 0;
+        for (uint64_t c = 0; c < n_chunks && run < r && shown < 60; c++) {
+            if (code[c] == -1) {
+                fprintf(stderr, "  chunk %llu: prefix %.17g sum %.6g max %.6g\n", (unsigned long long) c, run, csum[c], cmax[c]);
+                shown++;
+            }
+            run += csum[c];
+        }
+    }
     *bad = h->bad;
     *found = h->found;
     *index = first + h->index;

@@ -161,7 +161,7 @@ def test_hh_identity_and_norm_at_scale(qcs):
 
 
 @pytest.mark.parametrize("n,kind", [(18, "random"), (20, "random"), (22, "random"), (21, "sparse"),
-                                    (20, "ties"), (19, "spiky")])
+                                    (20, "ties"), (19, "spiky"), (21, "plateau")])
 def test_parallel_measurement_reproduces_sequential_rounding(qcs, oracle_built, n, kind):
     """The parallel scan (csrc/measure.cu) must return the index of the reference's
     sequential loop (qc_shor.c:283-292) -- checked against the oracle and against the
@@ -180,9 +180,15 @@ def test_parallel_measurement_reproduces_sequential_rounding(qcs, oracle_built, 
         v = np.zeros(N, dtype=np.complex128)
         v[:: N // 4096] = 1.0
         v[1:: N // 2048] = 0.5
+    elif kind == "plateau":
+        # four peaks of probability exactly 1/4 over addends around and far below half an ulp of the
+        # running sum: the sum sits on the binade boundaries 1/4 and 1/2 for hundreds of chunks
+        v = rng.choice([1e-15, 3e-9, 5.2e-9, 7.4e-9, 1.05e-8], size=N, p=[0.9, 0.04, 0.03, 0.02, 0.01]).astype(np.complex128)
+        v[N // 8::N // 4] = 0.5
     else:
         v = (rng.normal(size=N) + 1j * rng.normal(size=N)) * np.exp(rng.normal(size=N) * 6)
-    v /= np.linalg.norm(v)
+    if kind != "plateau":
+        v /= np.linalg.norm(v)
     o = oracle_built.Restatement(n, 0)
     p = np.abs(v.real) ** 2 + np.abs(v.imag) ** 2
     prefix = np.cumsum(p)
@@ -217,3 +223,30 @@ def test_parallel_measurement_after_qft_at_scale(qcs):
             reg.set_option(qcs.OPT_MEASURE_SEQUENTIAL, 1)
             b = reg.measure_state(r)
             assert a == b, r
+
+
+def test_parallel_measurement_on_shor_state(qcs, oracle_built):
+    """The state find_period actually measures (peaks of very different height over exact zeros): many
+    chunks cross a binade boundary and take the refined (sub-chunk) path of the walk.  Same index as the
+    oracle's loop and as the single-CTA sequential scan, for variates across the whole range."""
+    L, M, C, a = 13, 9, 511, 5
+    n = L + M
+    rng = np.random.default_rng(5)
+    with qcs.Register(L, M) as reg, qcs.Register(L, M) as seq:
+        seq.set_option(qcs.OPT_MEASURE_SEQUENTIAL, 1)
+        reg.reset_register()
+        reg.quantum_computation(C, a, qcs.POW_VERBATIM)
+        v = reg.get_state().copy()
+        p = np.abs(v.real) ** 2 + np.abs(v.imag) ** 2
+        prefix = np.cumsum(p)
+        rs = [1e-9, 0.01, 0.125, 0.25, 0.5, 0.9, 0.999999] + [float(rng.uniform()) for _ in range(8)]
+        for k in rng.integers(1, (1 << n) - 1, size=3):
+            rs += [float(prefix[k]), float(np.nextafter(prefix[k], 2))]
+        o = oracle_built.Restatement(L, M)
+        for r in rs:
+            o.set_state(v)
+            reg.set_state(v)
+            seq.set_state(v)
+            want = o.measure_state(r)
+            assert seq.measure_state(r) == want, r
+            assert reg.measure_state(r) == want, r
