@@ -569,6 +569,16 @@ def shor_block(q, ranks, args, with_n30=True):
         prof_reset = reg.profile()
         launches = reg.launch_count
         norm = reg.norm2()
+        # measure_state on the state find_period measures (collapses it: rebuilt before each variate)
+        measure_ms = {}
+        reg.set_option(q.OPT_PROFILE, 0)                           # per-launch events would be timed too
+        for r in (0.9, 0.25, 0.6180339887, 0.9):                   # the first call allocates the scan's scratch
+            t0 = time.perf_counter()                               # a synchronous call: the host clock is the cost.  (The
+            idx = int(reg.measure_state(r))                        # collapse stays pending and the next reset drops it.)
+            measure_ms[f"r={r:.3g}"] = round(1e3 * (time.perf_counter() - t0), 3)
+            reg.reset_register(); reg.quantum_computation(Cn, a, q.POW_MODULAR)
+            reg.norm2()                                            # nothing deferred is left for the next timing
+        reg.set_option(q.OPT_PROFILE, 1)
         idx = int(reg.measure_state(0.6180339887))
         # (b) the general path
         reg.fill_synthetic(SEED)
@@ -599,6 +609,7 @@ def shor_block(q, ranks, args, with_n30=True):
                                    f"per step: {L} H, {L} controlled a^(2^k) mod C, inverse QFT on the L register), "
                                    f"the sequence of find_period (qc_shor.c:922-923)",
                        "qubits": 30, "norm_after": norm, "measured_index": idx,
+                       "measure_state_ms": measure_ms,
                        "kernels_from_reset": per_class_reset,
                        "general_state": {"ms_per_quantum_computation": ms_general / big_runs, "norm_after": norm_general,
                                          "what": "the same quantum_computation on a synthetic (non-reset) state: "

@@ -176,13 +176,31 @@ __device__ __forceinline__ pair64 compose(pair64 f1, pair64 f2)
     return r;
 }
 
-// Every addend of the (sub-)chunk is below half an ulp of ANY running sum >= 2^e_lo: RN(s + p) = s all the
-// way through, whichever binade s is in -- the chunk is skipped like a ZERO one.  This is what keeps the
-// plateaus of a symmetric state cheap: a Shor state after the inverse QFT parks the running sum within
-// rounding of 1/4 and 1/2 for a hundred chunks of 1e-30 addends, where no bound can name the binade.
-__device__ __forceinline__ bool absorbed(double biggest, int e_lo)
+// floor(log2 x) of a positive normal x (-1023 for a subnormal one: never classified) and 2^e (0 below the
+// normal range, +inf at e = 1024) -- bit patterns instead of frexp / ldexp, which are library calls
+__device__ __forceinline__ int binade_of(double x)
 {
-    return biggest < ldexp(1.0, e_lo - 53);      // 0 when e_lo - 53 < -1074: never true then
+    return (int) (((unsigned long long) __double_as_longlong(x) >> 52) & 0x7ff) - 1023;
+}
+__device__ __forceinline__ double pow2(int e)
+{
+    return e < -1022 ? 0.0 : __longlong_as_double((long long) (e + 1023) << 52);
+}
+
+// Class of a (sub-)chunk from rigorous bounds lo <= (exact sequential sum at its start), (the same at its
+// end) <= hi, lo > 0, and its largest addend:
+//   ZERO (skipped)  every addend is below half an ulp of ANY running sum >= 2^e, e = binade of lo:
+//                   RN(s + p) = s all the way through, whichever binade s is in.  This keeps the plateaus
+//                   of a symmetric state cheap -- a Shor state after the inverse QFT parks the running
+//                   sum within rounding of 2^-k for runs of chunks, where no bound can name the binade;
+//   CLEAN(e)        the sum stays inside binade e and below r;
+//   SEQ             otherwise.
+__device__ __forceinline__ int classify(double lo, double hi, double biggest, double r)
+{
+    const int e = binade_of(lo);
+    if (biggest < pow2(e - 53)) return kCodeZero;
+    if (hi < r && hi < pow2(e + 1) && e > -960) return e + 2000;
+    return kCodeSeq;
 }
 
 // 2^(52 - e): p * scale = p / ulp of binade e (exact: a power of two; -960 < e keeps it finite)
@@ -191,16 +209,18 @@ __device__ __forceinline__ double binade_scale(int e)
     return __longlong_as_double((long long) (1023 + 52 - e) << 52);
 }
 
-// the map of one addend p inside the binade whose scale is given.  x = p / ulp < 2^53 exactly;
-// RN(a + x) - a = RNint(x) unless x is an exact tie k + 1/2, where the parity of a decides: an even a
-// rounds like x itself (half to even), an odd a takes the other neighbour.  Branch-free: this runs once
-// per amplitude of the scanned range.
+// the map of one addend p inside the binade whose scale is given.  x = p / ulp, exactly, and x < 2^52: a
+// p >= 2^e would carry the sum out of binade e.  RN(a + x) - a = RNint(x) unless x is an exact tie k + 1/2,
+// where the parity of a decides: an even a rounds like x itself (half to even), an odd a takes the other
+// neighbour.  RNint by the 2^52 trick, read back from the bit pattern (which also covers y = 2^53): no
+// branch, no 64-bit float <-> integer conversion -- this runs once per amplitude of the scanned range.
 __device__ __forceinline__ pair64 element_map(double p, double scale)
 {
     const double x = p * scale;
     pair64 r;
-    r.de = __double2ll_rn(x);
-    const double t = x - (double) r.de;              // exact
+    const double y = __dadd_rn(x, 0x1p52);
+    const double t = __dadd_rn(x, -__dadd_rn(y, -0x1p52));       // exact
+    r.de = __double_as_longlong(y) - __double_as_longlong(0x1p52);
     r.od = r.de + (t == 0.5 ? 1 : 0) - (t == -0.5 ? 1 : 0);
     return r;
 }
@@ -244,93 +264,135 @@ __global__ void __launch_bounds__(1024)
 k_classify(const double *__restrict__ csum, const double *__restrict__ cmax, uint64_t n_chunks, double cum_in,
            double r, double delta, int *__restrict__ code, int *__restrict__ super_code)
 {
-    __shared__ double warp_tot[32];
+    __shared__ double warp_tot[32], warp_off[32];
     __shared__ double carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = cum_in;
     __syncthreads();
     for (uint64_t seg = 0; seg < n_chunks; seg += 1024) {
         const uint64_t c = seg + threadIdx.x;
         const double v = c < n_chunks ? csum[c] : 0.0;
-        // inclusive warp scan
-        double x = v;
+        const double big = c < n_chunks ? cmax[c] : 0.0;
+        double x = v;                                // inclusive warp scan
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const double y = __shfl_up_sync(0xffffffffu, x, o);
-            if ((threadIdx.x & 31) >= o) x += y;
+            if (lane >= o) x += y;
         }
-        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+        double excl = __shfl_up_sync(0xffffffffu, x, 1);
+        if (lane == 0) excl = 0.0;
+        if (lane == 31) warp_tot[warp] = x;
         __syncthreads();
-        double before = carry_s;
-        for (int w = 0; w < (int) (threadIdx.x >> 5); w++) before += warp_tot[w];
-        const double P = before + (x - v);          // approximate sum before the chunk
+        if (warp == 0) {                             // scan of the 32 warp totals on top of the carry
+            double t = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double y = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += y;
+            }
+            double before = __shfl_up_sync(0xffffffffu, t, 1);
+            if (lane == 0) before = 0.0;
+            const double carry = carry_s;
+            warp_off[lane] = carry + before;
+            __syncwarp();
+            if (lane == 31) carry_s = carry + t;
+        }
+        __syncthreads();
+        const double P = warp_off[warp] + excl;      // approximate sum before the chunk (additions only)
         if (c < n_chunks) {
-            int cd = kCodeSeq;
             const double lo = P * (1.0 - delta), hi = (P + v) * (1.0 + delta);
-            if (v == 0.0) cd = kCodeZero;
-            else if (lo > 0.0) {
-                int e;
-                frexp(lo, &e);                       // lo = f * 2^e, f in [0.5, 1)  ->  binade e-1
-                e -= 1;
-                if (absorbed(cmax[c], e)) cd = kCodeZero;
-                else if (hi < r && hi < ldexp(1.0, e + 1) && e > -960) cd = e + 2000;
-            }
-            code[c] = cd;
+            code[c] = v == 0.0 ? kCodeZero : lo > 0.0 ? classify(lo, hi, big, r) : kCodeSeq;
         }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = before + x;
-        __syncthreads();
     }
-    // super-chunks: uniform when every chunk is ZERO or CLEAN with one common binade
+    __syncthreads();
+    // super-chunks: uniform when every chunk is ZERO or CLEAN with one common binade (a warp each)
     const uint64_t n_super = (n_chunks + kSuper - 1) >> kSuperBits;
-    for (uint64_t sc = threadIdx.x; sc < n_super; sc += 1024) {
-        int common = kCodeZero;
-        bool ok = true;
-        const uint64_t end = ((sc + 1) << kSuperBits) < n_chunks ? ((sc + 1) << kSuperBits) : n_chunks;
-        for (uint64_t c = sc << kSuperBits; c < end && ok; c++) {
-            const int cd = code[c];
-            if (cd == kCodeSeq) ok = false;
-            else if (cd != kCodeZero) {
-                if (common == kCodeZero) common = cd;
-                else if (common != cd) ok = false;
-            }
+    for (uint64_t sc = warp; sc < n_super; sc += 32) {
+        int lo_cd = 0x7fffffff, hi_cd = -1;
+        bool seq = false;
+#pragma unroll
+        for (int k = 0; k < kSuper / 32; k++) {
+            const uint64_t c = (sc << kSuperBits) + k * 32 + lane;
+            const int cd = c < n_chunks ? code[c] : kCodeZero;
+            seq |= cd == kCodeSeq;
+            if (cd >= 0) { lo_cd = min(lo_cd, cd); hi_cd = max(hi_cd, cd); }
         }
-        super_code[sc] = ok ? common : kCodeSeq;
+        seq = __any_sync(0xffffffffu, seq);
+        lo_cd = __reduce_min_sync(0xffffffffu, lo_cd);
+        hi_cd = __reduce_max_sync(0xffffffffu, hi_cd);
+        if (lane == 0) super_code[sc] = seq || (hi_cd >= 0 && lo_cd != hi_cd) ? kCodeSeq : (hi_cd >= 0 ? hi_cd : kCodeZero);
     }
 }
 
-// (de, do) of every CLEAN chunk: 128 threads, each composes 32 consecutive
-// elements from shared memory, then an ordered tree over the threads
-__global__ void __launch_bounds__(128)
+// (de, do) of every CLEAN chunk.  256 threads in two roles over a double-buffered chunk of probabilities:
+// warps 0-3 fetch the NEXT clean chunk (|amp|^2 into shared memory, 16 loads in flight per thread) while
+// warps 4-7 compose the current one -- 32 consecutive elements per thread, an ordered tree over the lanes,
+// a short chain over the 4 warps.  With one role per CTA (load, then compose) the kernel sat at 4.8 TB/s:
+// 24 warps per SM, idle memory during every compose phase (ncu: long_scoreboard 11.5 per issue).
+constexpr int kMapThreads = 256;
+constexpr int kMapRun = 32;                                      // consecutive elements per composing thread
+constexpr int kMapBuf = kChunk + kChunk / kMapRun;               // one pad per run: conflict-free both ways
+constexpr size_t kMapSmem = 2 * kMapBuf * sizeof(double);
+
+__global__ void __launch_bounds__(kMapThreads, 3)
 k_chunk_maps(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks, const int *__restrict__ code,
              pair64 *__restrict__ maps)
 {
-    __shared__ double p[kChunk + kChunk / 32];
+    extern __shared__ double map_smem[];
     __shared__ pair64 warp_map[4];
-    for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-        const int cd = code[c];
-        if (cd < 0) continue;
-        const double scale = binade_scale(cd - 2000);
+    const bool loader = threadIdx.x < 128;
+    const int t = threadIdx.x & 127;
+    auto next_clean = [&](uint64_t c) {
+        while (c < n_chunks && code[c] < 0) c += gridDim.x;
+        return c;
+    };
+    auto fetch = [&](uint64_t c, int buf) {
+        double *p = map_smem + buf * kMapBuf;
         const uint64_t base = c << kChunkBits;
-        for (int u = 0; u < kChunk / 128; u++) {
-            const int i = u * 128 + threadIdx.x;
-            p[i + (i >> 5)] = base + i < limit ? abs2_ref(amp[base + i]) : 0.0;
-        }
-        __syncthreads();
-        pair64 f = {0, 0};
-        for (int k = 0; k < 32; k++) f = compose(f, element_map(p[threadIdx.x * 33 + k], scale));
-        // ordered reduction: lane 0 ends with the composition of lanes 0..31 in order
+#pragma unroll 1
+        for (int h = 0; h < kChunk / 128; h += 16) {             // 16 loads issued before the first use
+            double2 v[16];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            pair64 g;
-            g.de = __shfl_down_sync(0xffffffffu, f.de, o);
-            g.od = __shfl_down_sync(0xffffffffu, f.od, o);
-            if ((threadIdx.x & 31) + o < 32 && ((threadIdx.x & 31) & (2 * o - 1)) == 0) f = compose(f, g);
+            for (int u = 0; u < 16; u++) {
+                const uint64_t i = base + (uint64_t) ((h + u) * 128 + t);
+                v[u] = i < limit ? amp[i] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                const int i = (h + u) * 128 + t;
+                p[i + i / kMapRun] = abs2_ref(v[u]);
+            }
         }
-        if ((threadIdx.x & 31) == 0) warp_map[threadIdx.x >> 5] = f;
+    };
+    uint64_t c = next_clean(blockIdx.x);
+    int buf = 0;
+    if (loader && c < n_chunks) fetch(c, 0);
+    __syncthreads();
+    while (c < n_chunks) {
+        const uint64_t c_next = next_clean(c + gridDim.x);
+        if (loader) {
+            if (c_next < n_chunks) fetch(c_next, buf ^ 1);
+        } else {
+            const double *p = map_smem + buf * kMapBuf;
+            const double scale = binade_scale(code[c] - 2000);
+            pair64 f = {0, 0};
+#pragma unroll 4
+            for (int k = 0; k < kMapRun; k++) f = compose(f, element_map(p[t * (kMapRun + 1) + k], scale));
+            // ordered reduction: lane 0 ends with the composition of lanes 0..31 in order
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                pair64 g;
+                g.de = __shfl_down_sync(0xffffffffu, f.de, o);
+                g.od = __shfl_down_sync(0xffffffffu, f.od, o);
+                if ((t & 31) + o < 32 && ((t & 31) & (2 * o - 1)) == 0) f = compose(f, g);
+            }
+            if ((t & 31) == 0) warp_map[t >> 5] = f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 composing warps only
+            if (t == 0) maps[c] = compose(compose(warp_map[0], warp_map[1]), compose(warp_map[2], warp_map[3]));
+        }
         __syncthreads();
-        if (threadIdx.x == 0)
-            maps[c] = compose(compose(warp_map[0], warp_map[1]), compose(warp_map[2], warp_map[3]));
-        __syncthreads();
+        c = c_next;
+        buf ^= 1;
     }
 }
 
@@ -489,18 +551,8 @@ k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
                 gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 1));
                 gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 2));
                 gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 4));
-                int cd = kCodeSeq;
-                if (gsum == 0.0) cd = kCodeZero;
-                else {
-                    const double lo = p_start * (1.0 - kSubDelta), hi = p_end * (1.0 + kSubDelta);
-                    if (lo > 0.0) {
-                        int e;
-                        frexp(lo, &e);
-                        e -= 1;
-                        if (absorbed(gmax, e)) cd = kCodeZero;
-                        else if (hi < r && hi < ldexp(1.0, e + 1) && e > -960) cd = e + 2000;
-                    }
-                }
+                const double lo = p_start * (1.0 - kSubDelta), hi = p_end * (1.0 + kSubDelta);
+                const int cd = gsum == 0.0 ? kCodeZero : lo > 0.0 ? classify(lo, hi, gmax, r) : kCodeSeq;
                 pair64 f = {0, 0};
                 if (cd >= 0) {
                     const double scale = binade_scale(cd - 2000);
@@ -643,12 +695,32 @@ static int scan_scratch(qcs_register *reg, scan_buffers &b)
     return QCS_NO_ERROR;
 }
 
-static unsigned scan_grid(const qcs_register *reg, uint64_t n_chunks)
+// grid-stride over the chunks with exactly one wave of CTAs: a partial second wave would run at a fraction
+// of the occupancy for as long as the first (k_chunk_maps fits 6 CTAs per SM, not 8: it cost 1.5x)
+static unsigned scan_grid(const qcs_register *reg, uint64_t n_chunks, int ctas_per_sm)
 {
     uint64_t grid = n_chunks;
-    const uint64_t cap = (uint64_t) reg->sm_count * 8;
+    const uint64_t cap = (uint64_t) reg->sm_count * (uint64_t) (ctas_per_sm > 0 ? ctas_per_sm : 1);
     if (grid > cap) grid = cap;
     return (unsigned) (grid < 1 ? 1 : grid);
+}
+
+static int resident_sums()
+{
+    static int n = 0;
+    if (!n && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_chunk_sums, 256, 0) != cudaSuccess) n = 4;
+    return n;
+}
+
+static int resident_maps()
+{
+    static int n = 0;
+    if (!n) {
+        if (cudaFuncSetAttribute(k_chunk_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMapSmem) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_chunk_maps, kMapThreads, kMapSmem) != cudaSuccess || n < 1)
+            n = -1;
+    }
+    return n;
 }
 
 // pass 1: per-chunk approximate sums of amp[first .. first + limit)
@@ -658,7 +730,7 @@ static int scan_sums(qcs_register *reg, uint64_t first, uint64_t limit)
     QCS_TRY(scan_scratch(reg, b));
     const uint64_t n_chunks = (limit + kChunk - 1) >> kChunkBits;
     qcs_launch_begin(reg, QCS_K_REDUCE, 16.0 * (double) limit);
-    k_chunk_sums<<<scan_grid(reg, n_chunks), 256, 0, reg->stream>>>(reg->amp + first, limit, n_chunks, b.csum, b.cmax);
+    k_chunk_sums<<<scan_grid(reg, n_chunks, resident_sums()), 256, 0, reg->stream>>>(reg->amp + first, limit, n_chunks, b.csum, b.cmax);
     return qcs_launch_end(reg, QCS_K_REDUCE, "k_chunk_sums");
 }
 
@@ -679,7 +751,8 @@ static int scan_maps(qcs_register *reg, uint64_t first, double approx_cum_in, do
     k_classify<<<1, 1024, 0, reg->stream>>>(b.csum, b.cmax, n_chunks, approx_cum_in, r, delta, b.code, b.super_code);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_classify"));
     qcs_launch_begin(reg, QCS_K_REDUCE, 16.0 * (double) limit * (r < 1.0 ? (r > 0.0 ? r : 0.0) : 1.0));
-    k_chunk_maps<<<scan_grid(reg, n_chunks), 128, 0, reg->stream>>>(amp, limit, n_chunks, b.code, b.maps);
+    if (resident_maps() < 1) return QCS_UNKNOWN_ERROR;
+    k_chunk_maps<<<scan_grid(reg, n_chunks, resident_maps()), kMapThreads, kMapSmem, reg->stream>>>(amp, limit, n_chunks, b.code, b.maps);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_chunk_maps"));
     qcs_launch_begin(reg, QCS_K_REDUCE, 20.0 * (double) n_chunks);
     k_super_maps<<<(unsigned) ((n_super + 255) / 256), 256, 0, reg->stream>>>(n_chunks, n_super, b.code, b.super_code,

@@ -17,8 +17,10 @@ with q.Register(L, M) as reg:
             else:
                 reg.reset_register()
                 reg.quantum_computation(4087 if M >= 12 else 21, 7 if M >= 12 else 2, q.POW_MODULAR)
-            reg.synchronize()
+            reg.norm2()                      # flushes anything deferred
+            reg.timer_start()
             t0 = time.perf_counter()
             idx = reg.measure_state(r)
             dt = time.perf_counter() - t0
-            print(f"{name} r={r}: index {idx}, measure_state {1e3 * dt:.3f} ms", flush=True)
+            ev = reg.timer_stop()
+            print(f"{name} r={r}: index {idx}, measure_state {1e3 * dt:.3f} ms (host clock), {ev:.3f} ms (CUDA events)", flush=True)
