@@ -396,17 +396,28 @@ k_chunk_maps(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
     }
 }
 
+// (de, do) of every uniform super-chunk: a warp each, 8 consecutive chunk maps per lane, ordered tree
 __global__ void __launch_bounds__(256)
 k_super_maps(uint64_t n_chunks, uint64_t n_super, const int *__restrict__ code, const int *__restrict__ super_code,
              const pair64 *__restrict__ maps, pair64 *__restrict__ super_maps)
 {
-    const uint64_t sc = (uint64_t) blockIdx.x * 256 + threadIdx.x;
-    if (sc >= n_super || super_code[sc] < 0) return;
+    const uint64_t sc = ((uint64_t) blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (sc >= n_super || super_code[sc] < 0) return;             // the whole warp
     pair64 f = {0, 0};
-    const uint64_t end = ((sc + 1) << kSuperBits) < n_chunks ? ((sc + 1) << kSuperBits) : n_chunks;
-    for (uint64_t c = sc << kSuperBits; c < end; c++)
-        if (code[c] >= 0) f = compose(f, maps[c]);
-    super_maps[sc] = f;
+#pragma unroll
+    for (int k = 0; k < kSuper / 32; k++) {
+        const uint64_t c = (sc << kSuperBits) + lane * (kSuper / 32) + k;
+        if (c < n_chunks && code[c] >= 0) f = compose(f, maps[c]);
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        pair64 g;
+        g.de = __shfl_down_sync(0xffffffffu, f.de, o);
+        g.od = __shfl_down_sync(0xffffffffu, f.od, o);
+        if (lane + o < 32 && (lane & (2 * o - 1)) == 0) f = compose(f, g);
+    }
+    if (lane == 0) super_maps[sc] = f;
 }
 
 struct walk_result {
@@ -538,8 +549,7 @@ k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
                 if (lane == 0) excl = 0.0;
                 if (lane == 31) warp_tot[threadIdx.x >> 5] = x;
                 __syncthreads();
-                double before = 0.0;
-                for (int w = 0; w < (int) (threadIdx.x >> 5); w++) before += warp_tot[w];
+                const double before = warp_sum(lane < (int) (threadIdx.x >> 5) ? warp_tot[lane] : 0.0);
                 const int g0 = lane & ~7;
                 const double p_start = s_run + (before + __shfl_sync(0xffffffffu, excl, g0));
                 const double p_end = s_run + (before + __shfl_sync(0xffffffffu, x, g0 | 7));
@@ -755,7 +765,7 @@ static int scan_maps(qcs_register *reg, uint64_t first, double approx_cum_in, do
     k_chunk_maps<<<scan_grid(reg, n_chunks, resident_maps()), kMapThreads, kMapSmem, reg->stream>>>(amp, limit, n_chunks, b.code, b.maps);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_chunk_maps"));
     qcs_launch_begin(reg, QCS_K_REDUCE, 20.0 * (double) n_chunks);
-    k_super_maps<<<(unsigned) ((n_super + 255) / 256), 256, 0, reg->stream>>>(n_chunks, n_super, b.code, b.super_code,
+    k_super_maps<<<(unsigned) ((n_super + 7) / 8), 256, 0, reg->stream>>>(n_chunks, n_super, b.code, b.super_code,
                                                                               b.maps, b.super_maps);
     return qcs_launch_end(reg, QCS_K_REDUCE, "k_super_maps");
 }
