@@ -578,6 +578,16 @@ def shor_block(q, ranks, args, with_n30=True):
             measure_ms[f"r={r:.3g}"] = round(1e3 * (time.perf_counter() - t0), 3)
             reg.reset_register(); reg.quantum_computation(Cn, a, q.POW_MODULAR)
             reg.norm2()                                            # nothing deferred is left for the next timing
+        # the parallel exact scan against the single-CTA sequential scan (the reference's loop, one thread) on this state
+        scan_check = {}
+        for r in (0.25, 0.6180339887):
+            par = int(reg.measure_state(r))
+            reg.reset_register(); reg.quantum_computation(Cn, a, q.POW_MODULAR)
+            reg.set_option(q.OPT_MEASURE_SEQUENTIAL, 1)
+            seq = int(reg.measure_state(r))
+            reg.set_option(q.OPT_MEASURE_SEQUENTIAL, 0)
+            reg.reset_register(); reg.quantum_computation(Cn, a, q.POW_MODULAR)
+            scan_check[f"r={r:.3g}"] = {"parallel": par, "sequential": seq, "same": par == seq}
         reg.set_option(q.OPT_PROFILE, 1)
         idx = int(reg.measure_state(0.6180339887))
         # (b) the general path
@@ -601,7 +611,8 @@ def shor_block(q, ranks, args, with_n30=True):
     mx = prof["modexp_sweep"]
     mx_gbps = mx[2] / (mx[1] * 1e-3) / 1e9 if mx[1] > 0 else 0.0
     gates30 = 3 * L + L * (L - 1) // 2
-    ok = (all(c["measured_indices_identical"] for c in cases) and abs(norm - 1.0) < 1e-10 and abs(norm_general - 1.0) < 1e-10)
+    ok = (all(c["measured_indices_identical"] for c in cases) and abs(norm - 1.0) < 1e-10 and abs(norm_general - 1.0) < 1e-10
+          and all(v["same"] for v in scan_check.values()))
     line = {"metric": "shor_quantum_computation_gates_per_sec", "value": gates30 * big_runs / (ms * 1e-3), "unit": "gates/s",
             "n_gpus": 1, "steps": big_runs, "warmup": 1, "ms_per_step": ms / big_runs, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 amplitudes, u32 index arithmetic", "data": "synthetic",
@@ -609,7 +620,7 @@ def shor_block(q, ranks, args, with_n30=True):
                                    f"per step: {L} H, {L} controlled a^(2^k) mod C, inverse QFT on the L register), "
                                    f"the sequence of find_period (qc_shor.c:922-923)",
                        "qubits": 30, "norm_after": norm, "measured_index": idx,
-                       "measure_state_ms": measure_ms,
+                       "measure_state_ms": measure_ms, "measure_parallel_vs_sequential_scan": scan_check,
                        "kernels_from_reset": per_class_reset,
                        "general_state": {"ms_per_quantum_computation": ms_general / big_runs, "norm_after": norm_general,
                                          "what": "the same quantum_computation on a synthetic (non-reset) state: "
