@@ -110,7 +110,13 @@ enum {
     /* 16: reserved (direct stores from registers were measured slower and removed) */
     /* 1 (default): a contiguous 2^12 tile whose steps are radix-16 at bits 8, 4, 0 is held in the
      * split-3 shared-memory layout (bank-conflict free; qft_common.cuh); 0: plain 128-byte swizzle */
-    QCS_OPT_SPLIT3 = 17
+    QCS_OPT_SPLIT3 = 17,
+    /* 1 (default): quantum_computation right after reset_register does not write the state |x, a^x mod C>
+     * at all -- the first sweep of the inverse QFT builds each tile in shared memory from a table of
+     * f(x) and skips the tiles that hold no non-zero amplitude (single GPU, when the transform starts
+     * with a strided sweep of the pipelined kernel; otherwise, and with 0, the state is written in one
+     * pass first) */
+    QCS_OPT_GEN_SWEEP = 18
 };
 
 /* kernel classes reported by qcs_profile_get */

@@ -20,6 +20,7 @@ OPT_FUSION, OPT_PROFILE, OPT_TILE_BITS, OPT_MEASURE_SEQUENTIAL, OPT_PIPELINE, OP
 OPT_PIPE_SHAPE, OPT_MIN_RUN_BITS, OPT_GLOBAL_RUN_BITS, OPT_OVERLAP_SLICES, OPT_GLOBAL_SMS = 7, 8, 9, 10, 11
 OPT_L2_PAIR, OPT_L2_PAIR_LAG, OPT_L2_PAIR_MAX_BLOCK, OPT_L2_PAIR_HINTS = 12, 13, 14, 15
 OPT_SPLIT3 = 17
+OPT_GEN_SWEEP = 18
 KERNEL_CLASSES = ["hadamard", "cphase", "amodc", "fill", "reduce", "tile_sweep",
                   "modexp_sweep", "exchange", "scale", "dense_block", "diag_multi", "global_sweep", "gate_1q"]
 

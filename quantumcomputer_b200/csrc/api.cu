@@ -252,10 +252,15 @@ static int create_common(qcs_register **out, int L_size, int M_size, int device,
     reg->d_meas = nullptr;
     reg->d_pair = nullptr;
     reg->d_dense = nullptr;
+    reg->d_gen_table = nullptr;
+    reg->gen_table_cap = 0;
+    reg->gen.f = nullptr;
+    reg->gen.armed = 0;
     reg->d_pair_cap = 0;
     reg->opt_l2_pair = 1;
     reg->opt_l2_pair_hints = 1;
     reg->opt_split3 = 1;
+    reg->opt_gen_sweep = 1;
     reg->opt_l2_pair_lag = 3 * 148;
     reg->opt_l2_pair_max_block = 16ll << 20;     // measured: 32 MiB blocks (n = 30) no longer stay in the L2 (profiles/README.md)
     reg->fusing = 0;
@@ -359,6 +364,7 @@ extern "C" void qcs_register_destroy(qcs_register *reg)
     if (reg->d_meas) cudaFree(reg->d_meas);
     if (reg->d_pair) cudaFree(reg->d_pair);
     if (reg->d_dense) cudaFree(reg->d_dense);
+    if (reg->d_gen_table) cudaFree(reg->d_gen_table);
     if (reg->d_diag) cudaFree(reg->d_diag);
     if (reg->h_small) cudaFreeHost(reg->h_small);
     if (reg->stream) cudaStreamDestroy(reg->stream);
@@ -425,6 +431,7 @@ extern "C" int qcs_set_option(qcs_register *reg, int option, long long value)
             return QCS_NO_ERROR;
         case QCS_OPT_L2_PAIR_HINTS: reg->opt_l2_pair_hints = value != 0; return QCS_NO_ERROR;
         case QCS_OPT_SPLIT3: reg->opt_split3 = value != 0; return QCS_NO_ERROR;
+        case QCS_OPT_GEN_SWEEP: reg->opt_gen_sweep = value != 0; return QCS_NO_ERROR;
         case QCS_OPT_L2_PAIR_MAX_BLOCK:
             if (value < (1 << 20)) return QCS_BAD_ARGUMENTS;
             reg->opt_l2_pair_max_block = value;
@@ -454,6 +461,7 @@ extern "C" long long qcs_get_option(const qcs_register *reg, int option)
         case QCS_OPT_L2_PAIR_MAX_BLOCK: return reg->opt_l2_pair_max_block;
         case QCS_OPT_L2_PAIR_HINTS: return reg->opt_l2_pair_hints;
         case QCS_OPT_SPLIT3: return reg->opt_split3;
+        case QCS_OPT_GEN_SWEEP: return reg->opt_gen_sweep;
         default: return -1;
     }
 }
@@ -668,6 +676,20 @@ extern "C" int qcs_quantum_computation(qcs_register *reg, unsigned C, unsigned a
         std::vector<unsigned> A((size_t) reg->L_size);
         for (int k = 0; k < reg->L_size; k++) A[(size_t) k] = (unsigned) (atox[(size_t) k] % C);
         if (from_reset) {
+            // ... or not written at all: the first sweep of the inverse QFT builds its tiles from f(x)
+            bool armed = false;
+            QCS_TRY(qcs_shor_state_generated(reg, C, A.data(), (unsigned) reg->L_size, &armed));
+            if (armed) {
+                reg->lazy_reset = 0;
+                const int rc = qft_any(reg, (unsigned) reg->M_size, reg->n, true);
+                if (rc == QCS_NO_ERROR && reg->gen.armed) {          // the plan check and the launch path disagree
+                    reg->gen.armed = 0;
+                    fprintf(stderr, "qcs: the generating sweep was armed but never launched\n");
+                    return QCS_UNKNOWN_ERROR;
+                }
+                reg->gen.armed = 0;
+                return rc;
+            }
             bool done = false;
             QCS_TRY(qcs_shor_state_from_reset(reg, C, A.data(), (unsigned) reg->L_size, &done));
             if (done) {

@@ -160,6 +160,19 @@ k_shor_state_from_reset(double2 *__restrict__ amp, uint64_t n_windows, int windo
     }
 }
 
+// f(x) for every block x of the L register (the same gate-by-gate rule), for the generating sweep
+__global__ void __launch_bounds__(256)
+k_shor_f_table(unsigned *__restrict__ table, uint64_t n_blocks, const closed_params P)
+{
+    const unsigned maskM = (1u << P.M) - 1u;
+    for (uint64_t x = (uint64_t) blockIdx.x * 256 + threadIdx.x; x < n_blocks; x += (uint64_t) gridDim.x * 256) {
+        unsigned f = 1u;
+        for (unsigned k = 0; k < P.L; k++)
+            if (((x >> k) & 1ull) && f < P.C) f = ((P.A[k] * f) % P.C) & maskM;
+        table[x] = f;
+    }
+}
+
 unsigned h_gcd(unsigned a, unsigned b)
 {
     while (b) { const unsigned t = a % b; a = b; b = t; }
@@ -283,5 +296,43 @@ int qcs_shor_state_from_reset(qcs_register *reg, unsigned C, const unsigned *A_p
     k_shor_state_from_reset<<<(unsigned) grid, 256, 0, reg->stream>>>(reg->amp, n_windows, window_bits, P);
     QCS_TRY(qcs_launch_end(reg, QCS_K_FILL, "k_shor_state_from_reset"));
     *done = true;
+    return QCS_NO_ERROR;
+}
+
+
+int qcs_shor_state_generated(qcs_register *reg, unsigned C, const unsigned *A_per_gate, unsigned n_gates, bool *armed)
+{
+    *armed = false;
+    const unsigned M = (unsigned) reg->M_size, L = n_gates;
+    if (reg->world != 1 || !reg->opt_gen_sweep || M < 1 || M > 30 || L != (unsigned) reg->L_size || L > (unsigned) kMaxGates || L > 26 ||
+        C == 0 || C > 65536u || reg->n != M + L || reg->n != reg->n_local || !qcs_fused_gen_supported(reg, M, reg->n))
+        return QCS_NO_ERROR;
+    const uint64_t n_blocks = 1ull << L;
+    if (reg->gen_table_cap < n_blocks) {
+        if (reg->d_gen_table) cudaFree(reg->d_gen_table);
+        reg->d_gen_table = nullptr;
+        reg->gen_table_cap = 0;
+        QCS_CUDA(cudaMalloc((void **) &reg->d_gen_table, n_blocks * sizeof(unsigned)));
+        reg->gen_table_cap = n_blocks;
+    }
+    closed_params P;
+    P.M = M;
+    P.L = L;
+    P.C = C;
+    P.n_local = reg->n_local;
+    P.rank = 0;
+    for (unsigned k = 0; k < L; k++) P.A[k] = A_per_gate[k] % C;
+    P.value = L % 2 == 0 ? ldexp(1.0, -(int) L / 2) : ldexp(0.70710678118654752440, -((int) L - 1) / 2);
+    uint64_t grid = (n_blocks + 255) / 256;
+    const uint64_t cap = (uint64_t) reg->sm_count * 8;
+    if (grid > cap) grid = cap;
+    qcs_launch_begin(reg, QCS_K_FILL, 4.0 * (double) n_blocks);
+    k_shor_f_table<<<(unsigned) grid, 256, 0, reg->stream>>>(reg->d_gen_table, n_blocks, P);
+    QCS_TRY(qcs_launch_end(reg, QCS_K_FILL, "k_shor_f_table"));
+    reg->gen.f = reg->d_gen_table;
+    reg->gen.M = M;
+    reg->gen.value = P.value;
+    reg->gen.armed = 1;
+    *armed = true;
     return QCS_NO_ERROR;
 }

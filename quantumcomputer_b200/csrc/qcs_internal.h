@@ -47,6 +47,11 @@ struct qcs_register {
     void *h_small;          // 4 KiB pinned host mirror
     void *d_meas;           // chunk summaries of the exact parallel measurement scan (lazy)
     void *d_dense;          // A-fragment buffer of qcs_apply_dense_block (lazy, 8 KiB)
+    // quantum_computation from the reset state: f(x) of every block x (built gate by gate), and the order for
+    // the NEXT pipelined sweep launch to generate its tiles from it instead of loading them (qft_pipeline.cu)
+    unsigned *d_gen_table;
+    size_t gen_table_cap;   // entries
+    struct { const unsigned *f; unsigned M; double value; int armed; } gen;
     void *d_pair;           // ticket + per-block counters of an L2-paired sweep launch (lazy)
     size_t d_pair_cap;      // bytes
 
@@ -65,6 +70,7 @@ struct qcs_register {
     int opt_measure_sequential;   // 1: always use the single-CTA sequential scan
     int opt_l2_pair;              // 1: the last strided sweep and the contiguous sweep of a transform share one launch
                                   // whose intermediate state stays in L2 (qft_pipeline.cu)
+    int opt_gen_sweep;            // 1: quantum_computation from reset lets the first inverse-QFT sweep generate its tiles
     int opt_split3;               // 1: contiguous 2^12 tiles of radix-16 steps use the conflict-free split-3 layout
     int opt_l2_pair_hints;        // 1: L2 eviction-priority hints on the TMA traffic of a paired launch
     int opt_l2_pair_lag;          // tiles the second sweep of a pair trails the first by, beyond one block
@@ -202,6 +208,10 @@ int qcs_fused_modexp(qcs_register *reg, unsigned C, const unsigned *A_per_gate, 
 // the same two loops applied to the reset state |0...01> in closed form: one write pass.  *done = false: the
 // shape is not covered (caller writes the reset state and takes the general path)
 int qcs_shor_state_from_reset(qcs_register *reg, unsigned C, const unsigned *A_per_gate, unsigned n_gates, bool *done);
+// the same state, not written: arms the generating first sweep of the inverse QFT on [M, n) when the launch
+// plan allows it (*armed tells; qcs_fused_gen_supported, qft_fused.cu)
+int qcs_shor_state_generated(qcs_register *reg, unsigned C, const unsigned *A_per_gate, unsigned n_gates, bool *armed);
+bool qcs_fused_gen_supported(const qcs_register *reg, unsigned lo, unsigned hi);
 
 // ---- general gates: gates_general.cu ------------------------------------------
 int qcs_k_gate_1q(qcs_register *reg, unsigned q, int c /* < 0: no control */, const double *u_interleaved);

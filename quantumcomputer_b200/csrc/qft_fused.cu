@@ -147,7 +147,7 @@ static int launch_plan_inner(qcs_register *reg, const sweep_target &tg, const sw
 // a list of consecutive sweeps on one target: neighbours that can share an L2-paired launch do.
 // Pairs are formed from the contiguous sweep outwards (it is the last sweep of an inverse transform
 // and the first of a forward one), so that it always has a partner.
-static int launch_plans(qcs_register *reg, const sweep_target &tg, const std::vector<sweep_plan> &plans)
+static std::vector<int> pair_flags(const qcs_register *reg, const sweep_target &tg, const std::vector<sweep_plan> &plans)
 {
     const size_t n = plans.size();
     std::vector<int> with_next(n, 0);
@@ -165,6 +165,13 @@ static int launch_plans(qcs_register *reg, const sweep_target &tg, const std::ve
             }
         }
     }
+    return with_next;
+}
+
+static int launch_plans(qcs_register *reg, const sweep_target &tg, const std::vector<sweep_plan> &plans)
+{
+    const size_t n = plans.size();
+    const std::vector<int> with_next = pair_flags(reg, tg, plans);
     for (size_t k = 0; k < n; k++) {
         if (with_next[k]) {
             reg->launch_stream = tg.stream;
@@ -195,6 +202,24 @@ static int run_sweeps(qcs_register *reg, unsigned lo, unsigned hi, bool inverse,
         if (hadamard_only) p.d.wcol_total = 0;
     }
     return launch_plans(reg, tg, plans);
+}
+
+// Can the first sweep of the inverse transform on [lo, hi) GENERATE its tiles (quantum_computation from the
+// reset state, modexp_fused.cu)?  It must be the first sweep launched, a strided tile of the pipelined
+// kernel (laid out linearly), and its rows must lie inside one block: low run inside the M register (a <= lo),
+// stage bits inside the L register (lo <= g_lo), nothing sliced.
+bool qcs_fused_gen_supported(const qcs_register *reg, unsigned lo, unsigned hi)
+{
+    if (!reg->opt_pipeline || reg->world != 1 || lo >= hi || hi > reg->n_local) return false;
+    std::vector<sweep_plan> plans;
+    plan_inverse(reg->n_local, lo, hi, default_tile_bits(reg), reg->opt_min_run_bits, plans);
+    if (plans.empty()) return false;
+    const sweep_target tg = {reg->amp, reg->n_local, reg->stream};
+    const sweep_desc &d = plans[0].d;
+    if (!(d.g_lo > d.a) || d.a > (int) lo || d.g_lo < (int) lo || d.slice_bits != 0 || d.tile_first != 0 ||
+        d.t != qcs_pipeline_tile_bits(reg) || !qcs_pipeline_supports(reg, tg, plans[0]))
+        return false;
+    return true;                 // alone or as the first sweep of an L2-paired launch
 }
 
 int qcs_plan_hadamard_sweeps(const qcs_register *reg, unsigned lo, unsigned hi, std::vector<sweep_plan> &plans)

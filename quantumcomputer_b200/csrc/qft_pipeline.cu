@@ -71,6 +71,11 @@ struct pipe_params {
     unsigned long long *ticket;     // pair: the queue head
     unsigned *done;                 // pair: stored A tiles per block
     unsigned long long *timing;     // -DQCS_PIPE_TIMING builds only: per-CTA cycle counters
+    // GEN kernels (quantum_computation from the reset state): the tiles are not loaded but built from
+    // f(x) -- amplitude gen_value at (x, f(x)) of every block x, zero elsewhere (modexp_fused.cu)
+    const unsigned *gen_f;
+    unsigned gen_M;
+    double gen_value;
 };
 
 constexpr uint64_t kNoItem = ~0ull;
@@ -164,6 +169,16 @@ __device__ __forceinline__ void group_barrier(int group, int threads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(threads) : "memory");
 }
+// the same barrier, OR-reducing a predicate over the group
+__device__ __forceinline__ bool group_barrier_or(int group, int threads, bool pred)
+{
+    unsigned r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %3, 0;\n\tbar.red.or.pred q, %1, %2, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                 : "=r"(r)
+                 : "r"(group + 1), "r"(threads), "r"((unsigned) pred)
+                 : "memory");
+    return r != 0;
+}
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
 {
     unsigned v;
@@ -215,7 +230,10 @@ __host__ __device__ __forceinline__ uint64_t pair_item(const pipe_params &P, uin
 // a launch small (the instruction cache holds about 40 KiB).
 enum { kWalsh = 0, kInverse = 1, kForward = 2 };
 
-template <int TB, int STAGES, int GROUPS, int GT, int MODE, bool PAIRED>
+// GEN: the (first) sweep's input is the state |x, f(x)> quantum_computation builds from the reset state.  Nothing
+// is loaded for it: the consumer group zeroes the stage, sets the amplitudes of the blocks x whose f(x) falls into
+// the tile's rows, and skips the steps of a tile that holds none (its output is zero as well).
+template <int TB, int STAGES, int GROUPS, int GT, int MODE, bool PAIRED, bool GEN = false>
 __global__ void __launch_bounds__(64 + GROUPS * GT, 1)
 k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, const pipe_params P)
 {
@@ -320,10 +338,13 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
                 }
                 int c0, c1, c2;
                 tile_coords<TB>(Q, tix, c0, c1, c2);
-                mbar_expect_tx(&full[s], kTileBytes);
+                const bool generated = GEN && ph == 0;
+                if (generated) mbar_arrive(&full[s]);      // nothing to wait for: the stage is free, the group fills it
+                else mbar_expect_tx(&full[s], kTileBytes);
                 unsigned char *dst = (unsigned char *) (stage_buf + (size_t) s * (1u << TB));
                 const CUtensorMap *map = ph ? &tmap1 : &tmap0;
-                if (P.l2_hints) {
+                if (generated) {
+                } else if (P.l2_hints) {
                     // A's input and B's input (A's output, read for the last time) may leave the L2 first
                     for (int b = 0; b < Q.n_boxes; b++)
                         tma_load_3d_hint(dst + (size_t) b * Q.box_bytes, map, &full[s], c0, c1 + b * Q.box_rows, c2, pol_stream);
@@ -420,7 +441,38 @@ k_qft_sweep_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             G.sw = Q.d.sw;
             const double2 *my_wcol = wcol + Q.wcol_base;
             const diag_gate *my_diag = sdiag + (ph ? P.ph[0].d.n_diag : 0);
-            for (int st = 0; st < Q.d.n_steps; st++) {
+            bool live = true;
+            if (GEN && ph == 0) {
+                // rows j of the tile = blocks x_base | j << (g_lo - M); columns = the f values f_hi << a | [0, 2^a)
+                const unsigned a = (unsigned) Q.d.a, M = P.gen_M, rows = 1u << (TB - Q.d.a);
+                const unsigned f_hi = ((unsigned) base & ((1u << M) - 1u)) >> a;
+                const uint64_t x_base = base >> M;
+                const int x_shift = Q.d.g_lo - (int) M;
+                unsigned fx[4];                              // the table reads travel while the stage is zeroed
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const unsigned j = tig + (unsigned) u * GT;
+                    fx[u] = j < rows ? P.gen_f[x_base | ((uint64_t) j << x_shift)] : 0xffffffffu;
+                }
+                for (unsigned e = tig; e < (1u << TB); e += GT) tile[e] = make_double2(0.0, 0.0);
+                group_barrier(group, GT);
+                bool hit = false;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const unsigned j = tig + (unsigned) u * GT;
+                    if (j < rows && (fx[u] >> a) == f_hi) { tile[(j << a) | (fx[u] & ((1u << a) - 1u))] = make_double2(P.gen_value, 0.0); hit = true; }
+                }
+                for (unsigned j = tig + 4u * GT; j < rows; j += GT) {
+                    const unsigned f = P.gen_f[x_base | ((uint64_t) j << x_shift)];
+                    if ((f >> a) == f_hi) { tile[(j << a) | (f & ((1u << a) - 1u))] = make_double2(P.gen_value, 0.0); hit = true; }
+                }
+                live = group_barrier_or(group, GT, hit);
+                if (!live) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zeroes -> visible to the TMA store
+                    group_barrier(group, GT);
+                }
+            }
+            for (int st = 0; live && st < Q.d.n_steps; st++) {
                 const sweep_step S = Q.d.step[st];
                 const bool last = st == Q.d.n_steps - 1;
                 const double2 wb = wbase[s * kMaxSteps + st];
@@ -504,13 +556,19 @@ int launch_mode(qcs_register *reg, const CUtensorMap &tmap0, const CUtensorMap &
                 const qft::sweep_target &tg)
 {
     auto kern = P.n_phases > 1 ? k_qft_sweep_tma<TB, STAGES, GROUPS, GT, MODE, true> : k_qft_sweep_tma<TB, STAGES, GROUPS, GT, MODE, false>;
+    if (P.gen_f) {
+        if (MODE != kInverse) return QCS_BAD_ARGUMENTS;
+        kern = P.n_phases > 1 ? k_qft_sweep_tma<TB, STAGES, GROUPS, GT, kInverse, true, true>
+                              : k_qft_sweep_tma<TB, STAGES, GROUPS, GT, kInverse, false, true>;
+    }
     QCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     uint64_t grid = (uint64_t) reg->sm_count;
     if (tg.max_ctas > 0 && grid > (uint64_t) tg.max_ctas) grid = (uint64_t) tg.max_ctas;
     if (grid > P.n_tiles) grid = P.n_tiles;
     // algorithmic bytes = sweeps made x 32 B per amplitude; a paired launch makes two sweeps
     // (its DRAM traffic is lower: the intermediate state stays in the L2)
-    qcs_launch_begin(reg, tg.kind, tg.bytes > 0.0 ? tg.bytes : 32.0 * (double) P.n_phases * (double) (P.n_tiles << TB));
+    // (a generating sweep only writes)
+    qcs_launch_begin(reg, tg.kind, tg.bytes > 0.0 ? tg.bytes : (32.0 * (double) P.n_phases - (P.gen_f ? 16.0 : 0.0)) * (double) (P.n_tiles << TB));
     kern<<<(unsigned) grid, 64 + GROUPS * GT, smem, tg.stream>>>(tmap0, tmap1, P);
     return qcs_launch_end(reg, tg.kind, "k_qft_sweep_tma");
 }
@@ -671,6 +729,22 @@ bool qcs_pipeline_supports(const qcs_register *reg, const qft::sweep_target &tg,
     return pipe_smem(sh, p.d.wcol_total, p.d.n_diag) <= reg->smem_optin;
 }
 
+// quantum_computation from the reset state (qcs_shor_state_generated) has armed the generator: this launch's
+// first sweep is the first sweep of its inverse QFT; qcs_fused_gen_supported has checked the geometry
+static int take_generator(qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &first, pipe_params &P)
+{
+    if (!reg->gen.armed) return QCS_NO_ERROR;
+    const bool strided = first.d.g_lo > first.d.a;
+    if (!strided || !first.d.inverse || first.d.hadamard_only || first.d.a > (int) reg->gen.M || first.d.g_lo < (int) reg->gen.M ||
+        tg.amp != reg->amp)
+        return QCS_BAD_ARGUMENTS;
+    P.gen_f = reg->gen.f;
+    P.gen_M = reg->gen.M;
+    P.gen_value = reg->gen.value;
+    reg->gen.armed = 0;
+    return QCS_NO_ERROR;
+}
+
 int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qft::sweep_plan &plan)
 {
     const pipe_shape sh = shape_of(reg);
@@ -682,6 +756,7 @@ int qcs_pipeline_launch(qcs_register *reg, const qft::sweep_target &tg, const qf
     P.n_phases = 1;
     P.n_tiles = plan.n_tiles;
     P.l2_hints = 0;              // evict_first on a single sweep's traffic was measured: no effect (21.6 ms either way)
+    QCS_TRY(take_generator(reg, tg, plan, P));
     return run_launch(reg, sh, shape_id, tmap, tmap, P, pipe_smem(sh, plan.d.wcol_total, plan.d.n_diag), tg);
 }
 
@@ -755,6 +830,7 @@ int qcs_pipeline_launch_pair(qcs_register *reg, const qft::sweep_target &tg, con
     if (lag > a.n_tiles) lag = a.n_tiles;
     P.lag = lag;
     P.l2_hints = reg->opt_l2_pair_hints;
+    QCS_TRY(take_generator(reg, tg, a, P));
     // queue head + one counter per block, zeroed in stream order
     const size_t need = 8 + 4 * (size_t) n_blocks;
     if (need > reg->d_pair_cap) {

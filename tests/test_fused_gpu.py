@@ -297,3 +297,62 @@ def test_quantum_computation_from_reset_closed_form(qcs, L, M, Cn, a, mode):
         fused.quantum_computation(Cn, a, mode)
         exact.quantum_computation(Cn, a, mode)
         assert rel_l2(fused.get_state(), exact.get_state()) <= TOL
+
+
+@pytest.mark.parametrize("L,M,Cn,a,mode", [(12, 6, 35, 4, 1), (13, 6, 35, 4, 1), (16, 8, 221, 6, 1), (10, 12, 4001, 7, 1), (14, 9, 511, 5, 0),
+                                           (15, 5, 21, 2, 1), (11, 9, 300, 10, 1), (18, 4, 15, 7, 1), (12, 12, 5000, 3, 1)])
+def test_quantum_computation_from_reset_generating_sweep(qcs, L, M, Cn, a, mode):
+    """Registers large enough for the pipelined sweeps: after reset_register the state |x, f(x)> is not written at
+    all -- the first sweep of the inverse QFT builds its tiles from the table of f(x) and skips the empty ones.
+    Same state as with the closed-form write pass (QCS_OPT_GEN_SWEEP = 0) and as the gate-by-gate kernels, for
+    bijective and non-bijective multipliers, C > 2^M and INT_POW overflow; where the launch plan allows the
+    generating sweep, no pass over the whole state is accounted to the fill class."""
+    N = 1 << (L + M)
+    with qcs.Register(L, M) as gen, qcs.Register(L, M) as written, qcs.Register(L, M) as exact:
+        written.set_option(qcs.OPT_GEN_SWEEP, 0)
+        exact.set_option(qcs.OPT_FUSION, 0)
+        for reg in (gen, written, exact):
+            reg.set_option(qcs.OPT_PROFILE, 1)
+            reg.profile_reset()
+            reg.reset_register()
+            reg.quantum_computation(Cn, a, mode)
+        want = exact.get_state()
+        assert rel_l2(gen.get_state(), want) <= TOL
+        assert rel_l2(written.get_state(), want) <= TOL
+        assert written.profile()["fill"][2] >= 16.0 * N
+        generated = gen.profile()["fill"][2] < 16.0 * N
+        print(f"L={L} M={M}: generating sweep {'used' if generated else 'not used'}")
+        # twice in a row (the table is rebuilt, the pending reset consumed again), then the measured index
+        gen.reset_register()
+        gen.quantum_computation(Cn, a, mode)
+        assert rel_l2(gen.get_state(), want) <= TOL
+        exact.set_option(qcs.OPT_FUSION, 1)
+        assert gen.measure_state(0.37) == written.measure_state(0.37) == exact.measure_state(0.37)
+
+
+def test_generating_sweep_is_used_at_scale(qcs):
+    """n = 28 (L = 16, M = 12): the plan starts with an unpaired strided sweep, so the generating sweep must
+    engage -- and the state must equal the one built by the write pass (probes + norm + measured indices)."""
+    L, M, Cn, a = 16, 12, 4087, 7
+    N = 1 << (L + M)
+    rng = np.random.default_rng(3)
+    probes = [int(i) for i in rng.integers(0, N, size=48)]
+    with qcs.Register(L, M) as gen, qcs.Register(L, M) as written:
+        written.set_option(qcs.OPT_GEN_SWEEP, 0)
+        for reg in (gen, written):
+            reg.set_option(qcs.OPT_PROFILE, 1)
+            reg.profile_reset()
+            reg.reset_register()
+            reg.quantum_computation(Cn, a, qcs.POW_MODULAR)
+        assert written.profile()["fill"][2] >= 16.0 * N
+        assert gen.profile()["fill"][2] < 16.0 * N, gen.profile()
+        assert abs(gen.norm2() - 1.0) < 1e-12
+        got = np.array([gen.get_state(i, 1)[0] for i in probes])
+        want = np.array([written.get_state(i, 1)[0] for i in probes])
+        assert np.max(np.abs(got - want)) <= 1e-15
+        # the heaviest amplitudes agree too: measured indices for several variates
+        for r in (0.05, 0.37, 0.62, 0.93):
+            for reg in (gen, written):
+                reg.reset_register()
+                reg.quantum_computation(Cn, a, qcs.POW_MODULAR)
+            assert gen.measure_state(r) == written.measure_state(r)
