@@ -225,12 +225,35 @@ __device__ __forceinline__ pair64 element_map(double p, double scale)
     return r;
 }
 
+// Pass 1 runs in up to kScanSegments launches over consecutive ranges of chunks.  A launch first adds up what
+// the launches before it found (one atomicAdd per CTA and segment): once that provably exceeds r -- by the
+// margin delta that covers the rounding of the sequential sum and of these tree sums -- the variate is
+// reached before this segment, and this launch and the ones behind it do nothing but record where the
+// summaries end (*n_valid).  On average half of the pass is saved; r = huge never stops.
+constexpr int kScanSegments = 16;
+
+__global__ void k_scan_init(double *acc, unsigned long long *n_valid, unsigned long long n_chunks)
+{
+    if (threadIdx.x < kScanSegments) acc[threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) *n_valid = n_chunks;
+}
+
 __global__ void __launch_bounds__(256)
-k_chunk_sums(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks, double *__restrict__ csum,
-             double *__restrict__ cmax)
+k_chunk_sums(const double2 *__restrict__ amp, uint64_t limit, uint64_t c_begin, uint64_t c_end, double *__restrict__ csum,
+             double *__restrict__ cmax, int segment, double *__restrict__ acc, unsigned long long *__restrict__ n_valid,
+             double approx_cum_in, double r, double delta)
 {
     __shared__ double warp_part[8], warp_big[8];
-    for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    if (segment > 0) {
+        double before = approx_cum_in;
+        for (int t = 0; t < segment; t++) before += acc[t];
+        if (before * (1.0 - delta) > r) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) atomicMin(n_valid, (unsigned long long) c_begin);
+            return;
+        }
+    }
+    double mine = 0.0;                                          // thread 0: this CTA's share of the segment
+    for (uint64_t c = c_begin + blockIdx.x; c < c_end; c += gridDim.x) {
         const uint64_t base = c << kChunkBits;
         double s = 0.0, big = 0.0;
 #pragma unroll 4
@@ -253,17 +276,20 @@ k_chunk_sums(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
             v = warp_sum(v);
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (threadIdx.x == 0) { csum[c] = v; cmax[c] = m; }
+            if (threadIdx.x == 0) { csum[c] = v; cmax[c] = m; mine += v; }
         }
         __syncthreads();
     }
+    if (threadIdx.x == 0 && mine != 0.0) atomicAdd(acc + segment, mine);
 }
 
 // single CTA: exclusive prefix over chunk sums + classification
 __global__ void __launch_bounds__(1024)
-k_classify(const double *__restrict__ csum, const double *__restrict__ cmax, uint64_t n_chunks, double cum_in,
-           double r, double delta, int *__restrict__ code, int *__restrict__ super_code)
+k_classify(const double *__restrict__ csum, const double *__restrict__ cmax, uint64_t n_all, const unsigned long long *__restrict__ n_valid,
+           double cum_in, double r, double delta, int *__restrict__ code, int *__restrict__ super_code)
 {
+    // chunks from *n_valid on (a multiple of kSuper, or all of them) were not summarised: r is reached before them
+    const uint64_t n_chunks = *n_valid < n_all ? (uint64_t) *n_valid : n_all;
     __shared__ double warp_tot[32], warp_off[32];
     __shared__ double carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -306,8 +332,12 @@ k_classify(const double *__restrict__ csum, const double *__restrict__ cmax, uin
     }
     __syncthreads();
     // super-chunks: uniform when every chunk is ZERO or CLEAN with one common binade (a warp each)
-    const uint64_t n_super = (n_chunks + kSuper - 1) >> kSuperBits;
+    const uint64_t n_super = (n_all + kSuper - 1) >> kSuperBits;
     for (uint64_t sc = warp; sc < n_super; sc += 32) {
+        if ((sc << kSuperBits) >= n_chunks) {                    // never walked; SEQ keeps the walk exact regardless
+            if (lane == 0) super_code[sc] = kCodeSeq;
+            continue;
+        }
         int lo_cd = 0x7fffffff, hi_cd = -1;
         bool seq = false;
 #pragma unroll
@@ -335,10 +365,11 @@ constexpr int kMapBuf = kChunk + kChunk / kMapRun;               // one pad per 
 constexpr size_t kMapSmem = 2 * kMapBuf * sizeof(double);
 
 __global__ void __launch_bounds__(kMapThreads, 3)
-k_chunk_maps(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks, const int *__restrict__ code,
-             pair64 *__restrict__ maps)
+k_chunk_maps(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_all, const unsigned long long *__restrict__ n_valid,
+             const int *__restrict__ code, pair64 *__restrict__ maps)
 {
     extern __shared__ double map_smem[];
+    const uint64_t n_chunks = *n_valid < n_all ? (uint64_t) *n_valid : n_all;
     __shared__ pair64 warp_map[4];
     const bool loader = threadIdx.x < 128;
     const int t = threadIdx.x & 127;
@@ -682,7 +713,8 @@ static int measure_scan_sequential(qcs_register *reg, double cum_in, double r, u
 // scratch of the parallel scan (lazily allocated, sized for the whole shard)
 struct scan_buffers {
     pair64 *maps = nullptr, *super_maps = nullptr;
-    double *csum = nullptr, *cmax = nullptr;
+    double *csum = nullptr, *cmax = nullptr, *acc = nullptr;
+    unsigned long long *n_valid = nullptr;
     int *code = nullptr, *super_code = nullptr;
 };
 
@@ -692,7 +724,7 @@ static int scan_scratch(qcs_register *reg, scan_buffers &b)
     const uint64_t cap_super = (cap_chunks + kSuper - 1) >> kSuperBits;
     if (!reg->d_meas) {
         const size_t bytes = cap_chunks * (2 * sizeof(double) + sizeof(int) + sizeof(pair64)) +
-                             cap_super * (sizeof(int) + sizeof(pair64)) + 64;
+                             cap_super * (sizeof(int) + sizeof(pair64)) + 64 + (kScanSegments + 1) * sizeof(double);
         QCS_CUDA(cudaMalloc(&reg->d_meas, bytes));
     }
     unsigned char *at = (unsigned char *) reg->d_meas;
@@ -700,6 +732,8 @@ static int scan_scratch(qcs_register *reg, scan_buffers &b)
     b.super_maps = (pair64 *) at;      at += cap_super * sizeof(pair64);
     b.csum = (double *) at;            at += cap_chunks * sizeof(double);
     b.cmax = (double *) at;            at += cap_chunks * sizeof(double);
+    b.acc = (double *) at;             at += kScanSegments * sizeof(double);
+    b.n_valid = (unsigned long long *) at; at += sizeof(double);
     b.code = (int *) at;               at += cap_chunks * sizeof(int);
     b.super_code = (int *) at;
     return QCS_NO_ERROR;
@@ -733,14 +767,33 @@ static int resident_maps()
     return n;
 }
 
-// pass 1: per-chunk approximate sums of amp[first .. first + limit)
-static int scan_sums(qcs_register *reg, uint64_t first, uint64_t limit)
+static double scan_delta(const qcs_register *reg)
+{
+    // rigorous relative margin: |sequential - exact| <= (N-1) u and the same for
+    // the tree sums, u = 2^-53; 2^(n+3-53) covers both with slack (n: ALL qubits of the register,
+    // so the margin also covers an approximate running sum handed over from the shards before)
+    return ldexp(1.0, (int) reg->n + 3 - 53);
+}
+
+// pass 1: per-chunk approximate sums (and largest addends) of amp[first .. first + limit), in segments that
+// stop once the variate r is provably behind them (r = 1e300: everything is summarised)
+static int scan_sums(qcs_register *reg, uint64_t first, uint64_t limit, double approx_cum_in, double r)
 {
     scan_buffers b;
     QCS_TRY(scan_scratch(reg, b));
     const uint64_t n_chunks = (limit + kChunk - 1) >> kChunkBits;
+    k_scan_init<<<1, 32, 0, reg->stream>>>(b.acc, b.n_valid, (unsigned long long) n_chunks);
+    const int n_seg = (n_chunks >= (1ull << 14) && r < 1e299) ? kScanSegments : 1;
+    uint64_t per_seg = (n_chunks + (uint64_t) n_seg - 1) / (uint64_t) n_seg;
+    per_seg = (per_seg + kSuper - 1) & ~(uint64_t) (kSuper - 1);             // whole super-chunks
     qcs_launch_begin(reg, QCS_K_REDUCE, 16.0 * (double) limit);
-    k_chunk_sums<<<scan_grid(reg, n_chunks, resident_sums()), 256, 0, reg->stream>>>(reg->amp + first, limit, n_chunks, b.csum, b.cmax);
+    for (int sg = 0; sg < n_seg; sg++) {
+        const uint64_t c_begin = (uint64_t) sg * per_seg;
+        if (c_begin >= n_chunks) break;
+        const uint64_t c_end = c_begin + per_seg < n_chunks ? c_begin + per_seg : n_chunks;
+        k_chunk_sums<<<scan_grid(reg, c_end - c_begin, resident_sums()), 256, 0, reg->stream>>>(
+            reg->amp + first, limit, c_begin, c_end, b.csum, b.cmax, sg, b.acc, b.n_valid, approx_cum_in, r, scan_delta(reg));
+    }
     return qcs_launch_end(reg, QCS_K_REDUCE, "k_chunk_sums");
 }
 
@@ -753,16 +806,13 @@ static int scan_maps(qcs_register *reg, uint64_t first, double approx_cum_in, do
     const double2 *amp = reg->amp + first;
     const uint64_t n_chunks = (limit + kChunk - 1) >> kChunkBits;
     const uint64_t n_super = (n_chunks + kSuper - 1) >> kSuperBits;
-    // rigorous relative margin: |sequential - exact| <= (N-1) u and the same for
-    // the tree sums, u = 2^-53; 2^(n+3-53) covers both with slack (n: ALL qubits of the register,
-    // so the margin also covers an approximate running sum handed over from the shards before)
-    const double delta = ldexp(1.0, (int) reg->n + 3 - 53);
+    const double delta = scan_delta(reg);
     qcs_launch_begin(reg, QCS_K_REDUCE, 12.0 * (double) n_chunks);
-    k_classify<<<1, 1024, 0, reg->stream>>>(b.csum, b.cmax, n_chunks, approx_cum_in, r, delta, b.code, b.super_code);
+    k_classify<<<1, 1024, 0, reg->stream>>>(b.csum, b.cmax, n_chunks, b.n_valid, approx_cum_in, r, delta, b.code, b.super_code);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_classify"));
     qcs_launch_begin(reg, QCS_K_REDUCE, 16.0 * (double) limit * (r < 1.0 ? (r > 0.0 ? r : 0.0) : 1.0));
     if (resident_maps() < 1) return QCS_UNKNOWN_ERROR;
-    k_chunk_maps<<<scan_grid(reg, n_chunks, resident_maps()), kMapThreads, kMapSmem, reg->stream>>>(amp, limit, n_chunks, b.code, b.maps);
+    k_chunk_maps<<<scan_grid(reg, n_chunks, resident_maps()), kMapThreads, kMapSmem, reg->stream>>>(amp, limit, n_chunks, b.n_valid, b.code, b.maps);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_chunk_maps"));
     qcs_launch_begin(reg, QCS_K_REDUCE, 20.0 * (double) n_chunks);
     k_super_maps<<<(unsigned) ((n_super + 7) / 8), 256, 0, reg->stream>>>(n_chunks, n_super, b.code, b.super_code,
@@ -824,7 +874,7 @@ static int scan_walk(qcs_register *reg, uint64_t first, double cum_in, double r,
 static int parallel_scan(qcs_register *reg, uint64_t first, double cum_in, double r, uint64_t limit,
                          int *found, uint64_t *index, double *cum_out, double *d_bnd, int *bad)
 {
-    QCS_TRY(scan_sums(reg, first, limit));
+    QCS_TRY(scan_sums(reg, first, limit, cum_in, d_bnd ? 1e300 : r));
     QCS_TRY(scan_maps(reg, first, cum_in, r, limit));
     return scan_walk(reg, first, cum_in, r, limit, found, index, cum_out, d_bnd, bad);
 }
@@ -837,7 +887,7 @@ bool qcs_k_scan_parallel_ok(const qcs_register *reg, uint64_t limit)
 
 int qcs_k_scan_sums(qcs_register *reg, uint64_t limit, double *approx_total)
 {
-    QCS_TRY(scan_sums(reg, 0, limit));
+    QCS_TRY(scan_sums(reg, 0, limit, 0.0, 1e300));
     scan_buffers b;
     QCS_TRY(scan_scratch(reg, b));
     const uint64_t n_chunks = (limit + kChunk - 1) >> kChunkBits;
