@@ -146,7 +146,9 @@ k_measure_scan(const double2 *__restrict__ amp, uint64_t limit, double cum_in, d
 //          sequential sum stays inside binade e throughout the chunk AND stays
 //          below r; ZERO when all its p are 0 -- or all below half an ulp of
 //          the smallest possible running sum, so that none of them moves it
-//          (pass 1 also keeps each chunk's largest p); otherwise SEQ
+//          (pass 1 also keeps each chunk's largest p); DUAL(e) when it stays
+//          below r and inside binades e and e + 1 (both maps are computed,
+//          the walk picks); otherwise SEQ
 //  pass 3  (de, do) of every CLEAN chunk, then of every uniform super-chunk
 //  pass 4  one CTA walks the summaries in index order carrying the exact s;
 //          a SEQ chunk (binade crossing, the neighbourhood of r) is refined on
@@ -162,8 +164,14 @@ constexpr int kChunkBits = 12;
 constexpr int kChunk = 1 << kChunkBits;
 constexpr int kSuperBits = 8;
 constexpr int kSuper = 1 << kSuperBits;
-constexpr int kWalkBlock = 512;                  // summaries staged per round of the walk (>= kSuper)
+constexpr int kWalkBlock = 512;                  // summaries staged per round of the walk (>= 2 kSuper: both maps of DUAL chunks)
+static_assert(kWalkBlock >= 2 * kSuper, "the chunk-level staging keeps two maps per chunk");
 constexpr int kCodeSeq = -1, kCodeZero = -2;     // otherwise: binade exponent + 2000
+// DUAL(e) = kCodeDual + e + 2000: the chunk stays below r and inside binades e and e + 1, but the bounds cannot
+// tell on which side of 2^(e+1) it runs.  Pass 3 computes its map for BOTH binades; the walk, which knows the
+// exact running sum, picks one (or refines the chunk when the sum really crosses inside it).
+constexpr int kCodeDual = -100000;
+__host__ __device__ __forceinline__ bool is_dual(int cd) { return cd <= kCodeDual + 4000; }
 constexpr double kSubDelta = 0x1p-36;            // relative bound on a running sum over <= 4096 additions, with margin
 
 struct pair64 { long long de, od; };
@@ -194,12 +202,17 @@ __device__ __forceinline__ double pow2(int e)
 //                   of a symmetric state cheap -- a Shor state after the inverse QFT parks the running
 //                   sum within rounding of 2^-k for runs of chunks, where no bound can name the binade;
 //   CLEAN(e)        the sum stays inside binade e and below r;
+//   DUAL(e)         (chunks only) below r, inside binades e and e + 1: one boundary possibly crossed;
 //   SEQ             otherwise.
+template <bool DUAL_OK>
 __device__ __forceinline__ int classify(double lo, double hi, double biggest, double r)
 {
     const int e = binade_of(lo);
     if (biggest < pow2(e - 53)) return kCodeZero;
-    if (hi < r && hi < pow2(e + 1) && e > -960) return e + 2000;
+    if (hi < r && e > -960) {
+        if (hi < pow2(e + 1)) return e + 2000;
+        if (DUAL_OK && hi < pow2(e + 2)) return kCodeDual + e + 2000;
+    }
     return kCodeSeq;
 }
 
@@ -327,7 +340,7 @@ k_classify(const double *__restrict__ csum, const double *__restrict__ cmax, uin
         const double P = warp_off[warp] + excl;      // approximate sum before the chunk (additions only)
         if (c < n_chunks) {
             const double lo = P * (1.0 - delta), hi = (P + v) * (1.0 + delta);
-            code[c] = v == 0.0 ? kCodeZero : lo > 0.0 ? classify(lo, hi, big, r) : kCodeSeq;
+            code[c] = v == 0.0 ? kCodeZero : lo > 0.0 ? classify<true>(lo, hi, big, r) : kCodeSeq;
         }
     }
     __syncthreads();
@@ -344,7 +357,7 @@ k_classify(const double *__restrict__ csum, const double *__restrict__ cmax, uin
         for (int k = 0; k < kSuper / 32; k++) {
             const uint64_t c = (sc << kSuperBits) + k * 32 + lane;
             const int cd = c < n_chunks ? code[c] : kCodeZero;
-            seq |= cd == kCodeSeq;
+            seq |= cd == kCodeSeq || is_dual(cd);
             if (cd >= 0) { lo_cd = min(lo_cd, cd); hi_cd = max(hi_cd, cd); }
         }
         seq = __any_sync(0xffffffffu, seq);
@@ -366,7 +379,7 @@ constexpr size_t kMapSmem = 2 * kMapBuf * sizeof(double);
 
 __global__ void __launch_bounds__(kMapThreads, 3)
 k_chunk_maps(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_all, const unsigned long long *__restrict__ n_valid,
-             const int *__restrict__ code, pair64 *__restrict__ maps)
+             const int *__restrict__ code, pair64 *__restrict__ maps, pair64 *__restrict__ maps_upper)
 {
     extern __shared__ double map_smem[];
     const uint64_t n_chunks = *n_valid < n_all ? (uint64_t) *n_valid : n_all;
@@ -374,7 +387,7 @@ k_chunk_maps(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_all, co
     const bool loader = threadIdx.x < 128;
     const int t = threadIdx.x & 127;
     auto next_clean = [&](uint64_t c) {
-        while (c < n_chunks && code[c] < 0) c += gridDim.x;
+        while (c < n_chunks && code[c] < 0 && !is_dual(code[c])) c += gridDim.x;
         return c;
     };
     auto fetch = [&](uint64_t c, int buf) {
@@ -405,21 +418,28 @@ k_chunk_maps(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_all, co
             if (c_next < n_chunks) fetch(c_next, buf ^ 1);
         } else {
             const double *p = map_smem + buf * kMapBuf;
-            const double scale = binade_scale(code[c] - 2000);
-            pair64 f = {0, 0};
+            const int cd = code[c];
+            const bool dual = is_dual(cd);
+            const int e = dual ? cd - kCodeDual - 2000 : cd - 2000;
+            for (int half = 0; half < (dual ? 2 : 1); half++) {          // DUAL: binade e into maps, e + 1 into maps_upper
+                const double scale = binade_scale(e + half);
+                pair64 f = {0, 0};
 #pragma unroll 4
-            for (int k = 0; k < kMapRun; k++) f = compose(f, element_map(p[t * (kMapRun + 1) + k], scale));
-            // ordered reduction: lane 0 ends with the composition of lanes 0..31 in order
+                for (int k = 0; k < kMapRun; k++) f = compose(f, element_map(p[t * (kMapRun + 1) + k], scale));
+                // ordered reduction: lane 0 ends with the composition of lanes 0..31 in order
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                pair64 g;
-                g.de = __shfl_down_sync(0xffffffffu, f.de, o);
-                g.od = __shfl_down_sync(0xffffffffu, f.od, o);
-                if ((t & 31) + o < 32 && ((t & 31) & (2 * o - 1)) == 0) f = compose(f, g);
+                for (int o = 1; o < 32; o <<= 1) {
+                    pair64 g;
+                    g.de = __shfl_down_sync(0xffffffffu, f.de, o);
+                    g.od = __shfl_down_sync(0xffffffffu, f.od, o);
+                    if ((t & 31) + o < 32 && ((t & 31) & (2 * o - 1)) == 0) f = compose(f, g);
+                }
+                if ((t & 31) == 0) warp_map[t >> 5] = f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 composing warps only
+                if (t == 0)
+                    (half ? maps_upper : maps)[c] = compose(compose(warp_map[0], warp_map[1]), compose(warp_map[2], warp_map[3]));
+                if (dual) asm volatile("bar.sync 1, 128;" ::: "memory");   // warp_map is written again
             }
-            if ((t & 31) == 0) warp_map[t >> 5] = f;
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 composing warps only
-            if (t == 0) maps[c] = compose(compose(warp_map[0], warp_map[1]), compose(warp_map[2], warp_map[3]));
         }
         __syncthreads();
         c = c_next;
@@ -482,6 +502,7 @@ template <bool RECORD>
 __global__ void __launch_bounds__(1024)
 k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks, double cum_in, double r,
              const int *__restrict__ code, const int *__restrict__ super_code, const pair64 *__restrict__ maps,
+             const pair64 *__restrict__ maps_upper, const double *__restrict__ csum,
              const pair64 *__restrict__ super_maps, walk_result *__restrict__ out, double *__restrict__ bnd)
 {
     __shared__ double p[kChunk];
@@ -534,9 +555,11 @@ k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
             const uint64_t c_begin = sc << kSuperBits;
             const uint64_t c_end = c_begin + kSuper < n_chunks ? c_begin + kSuper : n_chunks;
             __syncthreads();
-            if (threadIdx.x < kWalkBlock && c_begin + threadIdx.x < c_end) {
-                s_code[threadIdx.x] = code[c_begin + threadIdx.x];
-                s_map[threadIdx.x] = s_code[threadIdx.x] >= 0 ? maps[c_begin + threadIdx.x] : pair64{0, 0};
+            if (threadIdx.x < kSuper && c_begin + threadIdx.x < c_end) {
+                const int cd = code[c_begin + threadIdx.x];
+                s_code[threadIdx.x] = cd;
+                s_map[threadIdx.x] = (cd >= 0 || is_dual(cd)) ? maps[c_begin + threadIdx.x] : pair64{0, 0};
+                if (is_dual(cd)) s_map[kSuper + threadIdx.x] = maps_upper[c_begin + threadIdx.x];
             }
             __syncthreads();
             uint64_t c_next = c_begin;
@@ -548,6 +571,22 @@ k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
                         const int cd = s_code[c - c_begin];
                         if (cd == kCodeZero) continue;
                         if (cd == kCodeSeq) { req = (long long) c; break; }
+                        if (is_dual(cd)) {
+                            // the exact sum decides the side of 2^(e+1): at or above it the whole chunk runs in binade
+                            // e + 1 (it ends below 2^(e+2)); provably below it to the end, in binade e (the margin covers
+                            // 4096 additions and the tree sum); else the sum crosses inside this chunk: refine it
+                            const int e = cd - kCodeDual - 2000;
+                            const double edge = pow2(e + 1);
+                            if (s >= edge) {
+                                if (!apply_map(s, s_map[kSuper + (c - c_begin)], e + 1)) { s_bad = 1; break; }
+                            } else if ((s + csum[c]) * (1.0 + kSubDelta) < edge) {
+                                if (!apply_map(s, s_map[c - c_begin], e)) { s_bad = 1; break; }
+                            } else {
+                                req = (long long) c;
+                                break;
+                            }
+                            continue;
+                        }
                         if (!apply_map(s, s_map[c - c_begin], cd - 2000)) { s_bad = 1; break; }
                     }
                 }
@@ -593,7 +632,7 @@ k_exact_walk(const double2 *__restrict__ amp, uint64_t limit, uint64_t n_chunks,
                 gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 2));
                 gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 4));
                 const double lo = p_start * (1.0 - kSubDelta), hi = p_end * (1.0 + kSubDelta);
-                const int cd = gsum == 0.0 ? kCodeZero : lo > 0.0 ? classify(lo, hi, gmax, r) : kCodeSeq;
+                const int cd = gsum == 0.0 ? kCodeZero : lo > 0.0 ? classify<false>(lo, hi, gmax, r) : kCodeSeq;
                 pair64 f = {0, 0};
                 if (cd >= 0) {
                     const double scale = binade_scale(cd - 2000);
@@ -712,7 +751,7 @@ static int measure_scan_sequential(qcs_register *reg, double cum_in, double r, u
 
 // scratch of the parallel scan (lazily allocated, sized for the whole shard)
 struct scan_buffers {
-    pair64 *maps = nullptr, *super_maps = nullptr;
+    pair64 *maps = nullptr, *maps_upper = nullptr, *super_maps = nullptr;
     double *csum = nullptr, *cmax = nullptr, *acc = nullptr;
     unsigned long long *n_valid = nullptr;
     int *code = nullptr, *super_code = nullptr;
@@ -723,12 +762,13 @@ static int scan_scratch(qcs_register *reg, scan_buffers &b)
     const uint64_t cap_chunks = (reg->N_local + kChunk - 1) >> kChunkBits;
     const uint64_t cap_super = (cap_chunks + kSuper - 1) >> kSuperBits;
     if (!reg->d_meas) {
-        const size_t bytes = cap_chunks * (2 * sizeof(double) + sizeof(int) + sizeof(pair64)) +
+        const size_t bytes = cap_chunks * (2 * sizeof(double) + sizeof(int) + 2 * sizeof(pair64)) +
                              cap_super * (sizeof(int) + sizeof(pair64)) + 64 + (kScanSegments + 1) * sizeof(double);
         QCS_CUDA(cudaMalloc(&reg->d_meas, bytes));
     }
     unsigned char *at = (unsigned char *) reg->d_meas;
     b.maps = (pair64 *) at;            at += cap_chunks * sizeof(pair64);
+    b.maps_upper = (pair64 *) at;      at += cap_chunks * sizeof(pair64);
     b.super_maps = (pair64 *) at;      at += cap_super * sizeof(pair64);
     b.csum = (double *) at;            at += cap_chunks * sizeof(double);
     b.cmax = (double *) at;            at += cap_chunks * sizeof(double);
@@ -812,7 +852,7 @@ static int scan_maps(qcs_register *reg, uint64_t first, double approx_cum_in, do
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_classify"));
     qcs_launch_begin(reg, QCS_K_REDUCE, 16.0 * (double) limit * (r < 1.0 ? (r > 0.0 ? r : 0.0) : 1.0));
     if (resident_maps() < 1) return QCS_UNKNOWN_ERROR;
-    k_chunk_maps<<<scan_grid(reg, n_chunks, resident_maps()), kMapThreads, kMapSmem, reg->stream>>>(amp, limit, n_chunks, b.n_valid, b.code, b.maps);
+    k_chunk_maps<<<scan_grid(reg, n_chunks, resident_maps()), kMapThreads, kMapSmem, reg->stream>>>(amp, limit, n_chunks, b.n_valid, b.code, b.maps, b.maps_upper);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_chunk_maps"));
     qcs_launch_begin(reg, QCS_K_REDUCE, 20.0 * (double) n_chunks);
     k_super_maps<<<(unsigned) ((n_super + 7) / 8), 256, 0, reg->stream>>>(n_chunks, n_super, b.code, b.super_code,
@@ -834,10 +874,10 @@ static int scan_walk(qcs_register *reg, uint64_t first, double cum_in, double r,
     qcs_launch_begin(reg, QCS_K_REDUCE, 20.0 * (double) n_super);
     if (d_bnd)
         k_exact_walk<true><<<1, 1024, 0, reg->stream>>>(amp, limit, n_chunks, cum_in, r, b.code, b.super_code, b.maps,
-                                                        b.super_maps, d_res, d_bnd);
+                                                        b.maps_upper, b.csum, b.super_maps, d_res, d_bnd);
     else
         k_exact_walk<false><<<1, 1024, 0, reg->stream>>>(amp, limit, n_chunks, cum_in, r, b.code, b.super_code, b.maps,
-                                                         b.super_maps, d_res, nullptr);
+                                                         b.maps_upper, b.csum, b.super_maps, d_res, nullptr);
     QCS_TRY(qcs_launch_end(reg, QCS_K_REDUCE, "k_exact_walk"));
     QCS_CUDA(cudaMemcpyAsync(reg->h_small, d_res, sizeof(walk_result), cudaMemcpyDeviceToHost, reg->stream));
     QCS_CUDA(cudaStreamSynchronize(reg->stream));
