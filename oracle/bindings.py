@@ -268,6 +268,7 @@ def _load_reference():
     lib.qcref_shors_algorithm.argtypes = [vp, _u, _u, C.POINTER(_u)]
     lib.qcref_norm2.restype = C.c_double
     lib.qcref_norm2.argtypes = [vp]
+    lib.qcref_issue_warnings.argtypes = [_u, C.c_int, C.c_int]
     return lib
 
 
@@ -356,6 +357,15 @@ class Reference:
         f = (_u * 2)(0, 0)
         err = self.lib().qcref_shors_algorithm(self._h, Cn, forced_a, f)
         return err, (int(f[0]), int(f[1]))
+
+    @staticmethod
+    def warnings_text(Cn, L_size, M_size):
+        """What issue_warnings (qc_shor.c:340-351) prints for these sizes: run in a child process, because
+        the reference writes to the C stdout."""
+        import sys
+        code = ("import sys; sys.path.insert(0, %r); from oracle.bindings import Reference; "
+                "Reference.lib().qcref_issue_warnings(%d, %d, %d)" % (os.path.dirname(_HERE), Cn, L_size, M_size))
+        return subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True, timeout=120).stdout
 
     @classmethod
     def int_pow(cls, b, p):

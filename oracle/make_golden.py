@@ -166,9 +166,15 @@ def shor_runs():
                             "runs": runs})
 
 
+def warnings():
+    cases = [{"C": Cn, "L": L, "M": M, "stdout": Reference.warnings_text(Cn, L, M)}
+             for (Cn, L, M) in [(15, 3, 4), (15, 8, 4), (15, 8, 3), (21, 3, 3), (21, 10, 5), (21, 9, 5), (33, 5, 5),
+                                (35, 11, 6), (16, 8, 4), (17, 8, 4), (255, 16, 8), (257, 16, 8), (4087, 18, 12)]]
+    dump("warnings.json", {"doc": "stdout of issue_warnings (qc_shor.c:340-351) of the unmodified reference", "cases": cases})
+
+
 if __name__ == "__main__":
-    shor_states()
-    single_gates()
-    iqft()
-    scalars()
-    shor_runs()
+    only = sys.argv[1:]
+    for fn in (shor_states, single_gates, iqft, scalars, shor_runs, warnings):
+        if not only or fn.__name__ in only:
+            fn()

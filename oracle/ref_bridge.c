@@ -148,6 +148,17 @@ void qcref_continued_fraction_denominators(double omega, unsigned int n, unsigne
     get_continued_fractions_denominators(omega, n, out);
 }
 
+/* issue_warnings, qc_shor.c:340-351: prints to stdout */
+void qcref_issue_warnings(unsigned int C, int L_size, int M_size)
+{
+    Register reg;
+    memset(&reg, 0, sizeof reg);
+    reg.L_size = L_size;
+    reg.M_size = M_size;
+    issue_warnings(C, reg);
+    fflush(stdout);
+}
+
 unsigned int qcref_gcd(unsigned int a, unsigned int b) { return greatest_common_divisor(a, b); }
 
 /* find_period (qc_shor.c:912-964): returns the ErrorCode, period in *period */

@@ -10,6 +10,7 @@
  * All state lives on the GPU; this file only makes the three calls the
  * reference's find_period makes into the gate path (qc_shor.c:922-928).
  */
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <time.h>
@@ -24,11 +25,14 @@ static const char *USAGE =
 
 static void issue_warnings(unsigned C, int L, int M)
 {
-    /* qc_shor.c:340-351: 2^M >= C and 2^L >= C^2 give full confidence */
-    if (M < 31 && (1ull << M) < (unsigned long long) C)
-        printf("Warning: M register too small to hold values up to C; results may be unreliable.\n");
-    if (L < 62 && (1ull << L) < (unsigned long long) C * C)
-        printf("Warning: L register smaller than 2 log2(C) qubits; the period may not be resolved.\n");
+    /* qc_shor.c:340-351, text and arithmetic as there: INT_POW(2, M) < C, and INT_POW(2, L) < C*C with
+     * the product taken in unsigned int */
+    if (qcs_int_pow(2, (unsigned) M) < C)
+        printf(" --- *WARNING* The M register is not large enough for reliable results. Ensure 2^M >= C. Minimum: M = %d.\n",
+               ((int) (log2(C) + 0.5)) + 1);
+    if (qcs_int_pow(2, (unsigned) L) < C * C)
+        printf(" --- *WARNING* The L register is not large enough for full confidence in finding the period. Ensure 2^L >= C^2 for confidence. Suggested: L = %d.\n",
+               (int) (log2(C * C) + 0.5));
 }
 
 int main(int argc, char *argv[])

@@ -90,3 +90,20 @@ def test_period_validity(host):
     # 2^60 wraps INT_POW (verbatim says 0 % 21 != 1) but is 1 mod 21
     assert host.qcsh_period_is_valid(2, 60, 21, 0) == 0 and host.qcsh_period_is_valid(2, 60, 21, 1) == 1
     assert host.qcsh_modpow(7, 123456789, 1000003) == pow(7, 123456789, 1000003)
+
+
+def test_register_size_warnings_are_the_references():
+    """The host driver prints issue_warnings' text (qc_shor.c:340-351) before it touches a device: stdout
+    compared with the unmodified reference's (tests/golden/warnings.json, and live when oracle/_ref exists).
+    -d 9999 makes register creation fail at once on any box, so only the warnings are printed."""
+    import subprocess
+    import oracle
+    binary = os.path.join(ROOT, "quantumcomputer_b200", "bin", "qc_shor_b200")
+    assert os.path.exists(binary), "build the host driver with `make host`"
+    for case in load_golden("warnings.json")["cases"]:
+        out = subprocess.run([binary, "-C", str(case["C"]), "-L", str(case["L"]), "-M", str(case["M"]), "-d", "9999"],
+                             capture_output=True, text=True, timeout=60)
+        assert out.returncode != 0 and "Error" in out.stderr          # no device 9999: fails loudly, no CPU path
+        assert out.stdout == case["stdout"], case
+        if oracle.have_reference():
+            assert oracle.Reference.warnings_text(case["C"], case["L"], case["M"]) == case["stdout"]
