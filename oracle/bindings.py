@@ -359,6 +359,20 @@ class Reference:
         return err, (int(f[0]), int(f[1]))
 
     @staticmethod
+    def shor_stdout(Cn, L_size, M_size, forced_a, seed, verbose=0, very_verbose=0):
+        """(ErrorCode, factors, stdout) of the reference's shors_algorithm (qc_shor.c:1003-1134) with
+        gsl_rng_set(seed) and the -v / -V flags, run in a child process (the program prints as it goes)."""
+        import json
+        import sys
+        code = ("import sys, json; sys.path.insert(0, %r); from oracle.bindings import Reference; "
+                "ref = Reference(%d, %d); Reference.lib().qcref_set_verbosity(%d, %d); ref.seed(%d); "
+                "err, f = ref.shors_algorithm(%d, %d); sys.stderr.write(json.dumps([err, list(f)]))"
+                % (os.path.dirname(_HERE), L_size, M_size, verbose, very_verbose, seed, Cn, forced_a))
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True, timeout=600)
+        err, f = json.loads(out.stderr.strip().splitlines()[-1])
+        return err, f, out.stdout
+
+    @staticmethod
     def warnings_text(Cn, L_size, M_size):
         """What issue_warnings (qc_shor.c:340-351) prints for these sizes: run in a child process, because
         the reference writes to the C stdout."""

@@ -166,6 +166,29 @@ def shor_runs():
                             "runs": runs})
 
 
+def shor_stdout():
+    """Everything shors_algorithm prints, per verbosity level; the wall-time figure is replaced by <t>.
+    Only runs in which a candidate period passes legitimately (Appendix B #1)."""
+    import re
+    runs = [(15, 3, 4, 7, 12345), (15, 3, 4, 7, 1), (15, 3, 4, 2, 5), (15, 3, 4, 11, 9), (21, 5, 5, 2, 2021),
+            (21, 5, 5, 2, 3), (15, 3, 4, 0, 42), (21, 4, 5, 0, 7),
+            (15, 3, 4, 14, 3),      # period 2, 14 = C - 1: rejected
+            (15, 3, 4, 4, 8),       # period 2
+            (21, 5, 5, 8, 6),       # period 2
+            (21, 5, 5, 20, 2),      # period 2, 20 = C - 1: rejected
+            (21, 5, 5, 4, 10)]      # period 3, odd: rejected (and INT_POW(4, 16) wraps: an A = 0 gate on the way)
+    cases = []
+    for (Cn, L, M, a, seed) in runs:
+        for (v, vv) in ((0, 0), (1, 0), (1, 1)):
+            err, factors, out = Reference.shor_stdout(Cn, L, M, a, seed, v, vv)
+            out = re.sub(r"Algorithm: [0-9.]+s\.", "Algorithm: <t>s.", out)
+            cases.append({"C": Cn, "L": L, "M": M, "a": a, "seed": seed, "verbose": v, "very_verbose": vv,
+                          "error": err, "factors": factors, "stdout": out})
+    dump("shor_stdout.json", {"doc": "stdout of shors_algorithm (qc_shor.c:1003-1134) of the unmodified reference, "
+                                     "gsl_rng_set(seed), flags -v / -V; <t> stands for the wall-time figure",
+                              "cases": cases})
+
+
 def warnings():
     cases = [{"C": Cn, "L": L, "M": M, "stdout": Reference.warnings_text(Cn, L, M)}
              for (Cn, L, M) in [(15, 3, 4), (15, 8, 4), (15, 8, 3), (21, 3, 3), (21, 10, 5), (21, 9, 5), (33, 5, 5),
@@ -175,6 +198,6 @@ def warnings():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (shor_states, single_gates, iqft, scalars, shor_runs, warnings):
+    for fn in (shor_states, single_gates, iqft, scalars, shor_runs, warnings, shor_stdout):
         if not only or fn.__name__ in only:
             fn()

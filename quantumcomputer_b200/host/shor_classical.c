@@ -97,7 +97,13 @@ int qcsh_find_period(unsigned *period, unsigned C, unsigned a, struct qcs_regist
     unsigned long long measured = 0;
     int rc;
 
-    if (opt->very_verbose) printf("      - Performing quantum computation...\n");
+    if (opt->very_verbose) {
+        /* the three stages are one library call here; the reference names them as it goes (qc_shor.c:717-735) */
+        printf("      - Performing quantum computation...\n");
+        printf("         - Applying Hadamard matrices.\n");
+        printf("         - Applying a^x mod (C) gates.\n");
+        printf("         - Performing inverse quantum Fourier transform.\n");
+    }
     if ((rc = qcs_reset_register(reg)) != QCS_NO_ERROR) return rc;
     rc = qcs_quantum_computation(reg, C, a, opt->mode == QCSH_ROBUST ? QCS_POW_MODULAR : QCS_POW_VERBATIM);
     if (rc != QCS_NO_ERROR) return rc;
