@@ -4,6 +4,8 @@
 #   make lib        quantumcomputer_b200/lib/libqcs.so
 #   make host       quantumcomputer_b200/bin/qc_shor_b200
 #   make oracle     oracle/_build + oracle/_ref (test infrastructure)
+#   make dropin     oracle/_ref/qc_shor_{ref,dropin,dropin_fused}: the reference program with INTEGRATION.md's edits,
+#                   linked against libqcs.so (test infrastructure; only where /root/reference exists)
 
 NVCC      ?= nvcc
 CC        ?= gcc
@@ -20,7 +22,7 @@ HOSTLIB   := $(PKG)/lib/libqcshost.so
 CU_SRCS   := $(wildcard $(CSRC)/*.cu)
 CU_OBJS   := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
 
-all: lib host oracle
+all: lib host oracle dropin
 
 lib: $(LIB)
 
@@ -52,8 +54,11 @@ $(HOSTBIN): $(PKG)/host/qc_shor_b200.c $(PKG)/host/mt19937.c $(PKG)/host/mt19937
 oracle:
 	$(MAKE) -C oracle --no-print-directory
 
+dropin: $(LIB)
+	python oracle/make_dropin.py
+
 clean:
 	rm -rf build $(PKG)/lib $(PKG)/bin
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib host oracle clean timing
+.PHONY: all lib host oracle dropin clean timing

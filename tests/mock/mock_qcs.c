@@ -1,5 +1,5 @@
 /*
- * mock_qcs.c -- TEST INFRASTRUCTURE ONLY (tests/test_host_stdout.py, CPU).
+ * mock_qcs.c -- TEST INFRASTRUCTURE ONLY (tests/test_host_stdout.py, tests/test_dropin.py; CPU).
  *
  * The handful of libqcs.so entry points the C host driver calls (include/qcs.h; qc_shor.c:922-928,
  * 1316-1333), answered by the CPU oracle (oracle/qcs_oracle.c), so that the classical half of the
@@ -64,5 +64,30 @@ int qcs_quantum_computation(qcs_register *reg, unsigned C, unsigned a, int pow_m
 int qcs_measure_state(qcs_register *reg, double r, unsigned long long *state_num)
 {
     *state_num = (unsigned long long) orc_measure_state(reg->o, r);
+    return QCS_NO_ERROR;
+}
+
+/* the primitive gates (oracle/make_dropin.py: the reference's own quantum_computation on top of them) */
+int qcs_hadamard_gate(qcs_register *reg, unsigned qubit_num)
+{
+    orc_hadamard_gate(reg->o, qubit_num);
+    return QCS_NO_ERROR;
+}
+
+int qcs_c_phase_shift_gate(qcs_register *reg, unsigned c_qubit_num, unsigned qubit_num, double theta)
+{
+    orc_c_phase_shift_gate(reg->o, c_qubit_num, qubit_num, theta);
+    return QCS_NO_ERROR;
+}
+
+int qcs_c_amodc_gate(qcs_register *reg, unsigned C, unsigned long long atox, unsigned c_qubit_num)
+{
+    orc_c_amodc_gate(reg->o, C, atox, c_qubit_num);
+    return QCS_NO_ERROR;
+}
+
+int qcs_inverse_QFT(qcs_register *reg)
+{
+    orc_inverse_QFT(reg->o);
     return QCS_NO_ERROR;
 }
