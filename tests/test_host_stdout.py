@@ -71,3 +71,22 @@ def test_host_driver_stdout_is_the_references_cpu(mock_so):
 @pytest.mark.gpu
 def test_host_driver_stdout_is_the_references_gpu():
     check_all()
+
+
+@pytest.mark.parametrize("args,factors", [
+    (["-C", "35", "-L", "11", "-M", "6", "-a", "2"], {5, 7}),        # period 12
+    (["-C", "33", "-L", "11", "-M", "6"], {3, 11}),                  # loop: a = 2 (period 10, 2^5 = -1: rejected), a = 3 ...
+    (["-C", "55", "-L", "12", "-M", "6", "-a", "2"], {5, 11}),       # period 20
+    (["-C", "77", "-L", "13", "-M", "7", "-a", "2"], {7, 11}),       # period 30
+])
+def test_robust_mode_factors_numbers_whose_period_needs_the_continued_fraction(mock_so, args, factors):
+    """with -r (modular a^p, terminated expansion, initialised flags) the host driver factors
+    numbers whose period is > 10, i.e. where the period really has to come out of the measured index through
+    read_omega and the continued fraction (the reference's verbatim arithmetic wraps INT_POW there, Appendix B
+    #3) -- end to end on the CPU over the mock ABI, three seeds each."""
+    env = dict(os.environ, LD_PRELOAD=mock_so)
+    for seed in ("1", "2", "3"):
+        out = subprocess.run([BIN] + args + ["-s", seed, "-r"], capture_output=True, text=True, timeout=300, env=env)
+        m = re.search(r"Factors of (\d+) found: \((\d+), (\d+)\)", out.stdout)
+        assert out.returncode == 0 and m, (args, seed, out.stdout, out.stderr)
+        assert {int(m.group(2)), int(m.group(3))} == factors and "incorrect" not in out.stdout, (args, seed, out.stdout)
