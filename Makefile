@@ -42,8 +42,8 @@ timing:
 host: $(HOSTBIN) $(HOSTLIB)
 
 # the classical half as a shared object, so tests can drive it through ctypes
-$(HOSTLIB): $(PKG)/host/mt19937.c $(PKG)/host/mt19937.h $(PKG)/host/shor_classical.c $(PKG)/host/shor_classical.h $(LIB)
-	$(CC) -O2 -Wall -fPIC -shared -Iinclude -o $@ $(PKG)/host/mt19937.c $(PKG)/host/shor_classical.c \
+$(HOSTLIB): $(PKG)/host/mt19937.c $(PKG)/host/mt19937.h $(PKG)/host/shor_classical.c $(PKG)/host/shor_classical.h $(PKG)/host/state_debug.c $(PKG)/host/state_debug.h $(LIB)
+	$(CC) -O2 -Wall -fPIC -shared -Iinclude -o $@ $(PKG)/host/mt19937.c $(PKG)/host/shor_classical.c $(PKG)/host/state_debug.c \
 	      -L$(PKG)/lib -lqcs -Wl,-rpath,'$$ORIGIN' -lm
 
 $(HOSTBIN): $(PKG)/host/qc_shor_b200.c $(PKG)/host/mt19937.c $(PKG)/host/mt19937.h $(PKG)/host/shor_classical.c $(PKG)/host/shor_classical.h $(LIB)

@@ -373,6 +373,19 @@ class Reference:
         return err, f, out.stdout
 
     @staticmethod
+    def debug_stdout(Cn, a, L_size, M_size):
+        """stdout of display_state, then of check_normalisation (testing_and_debug.c:7-37), on the state after
+        reset_register + quantum_computation(C, a); child process, the helpers print."""
+        import sys
+        code = ("import sys; sys.path.insert(0, %r); from oracle.bindings import Reference; "
+                "ref = Reference(%d, %d); ref.reset_register(); ref.quantum_computation(%d, %d); "
+                "Reference.lib().qcref_display_state.argtypes = [__import__('ctypes').c_void_p]; "
+                "Reference.lib().qcref_check_normalisation.argtypes = [__import__('ctypes').c_void_p]; "
+                "Reference.lib().qcref_display_state(ref._h); Reference.lib().qcref_check_normalisation(ref._h)"
+                % (os.path.dirname(_HERE), L_size, M_size, Cn, a))
+        return subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True, timeout=600).stdout
+
+    @staticmethod
     def warnings_text(Cn, L_size, M_size):
         """What issue_warnings (qc_shor.c:340-351) prints for these sizes: run in a child process, because
         the reference writes to the C stdout."""

@@ -189,6 +189,13 @@ def shor_stdout():
                               "cases": cases})
 
 
+def debug_stdout():
+    cases = [{"C": Cn, "a": a, "L": L, "M": M, "stdout": Reference.debug_stdout(Cn, a, L, M)}
+             for (Cn, a, L, M) in [(15, 7, 3, 4), (21, 2, 5, 5), (15, 6, 3, 4), (21, 4, 6, 5)]]
+    dump("debug_stdout.json", {"doc": "stdout of display_state, then check_normalisation (testing_and_debug.c:7-37, unmodified) "
+                                      "on the state after reset_register + quantum_computation(C, a)", "cases": cases})
+
+
 def warnings():
     cases = [{"C": Cn, "L": L, "M": M, "stdout": Reference.warnings_text(Cn, L, M)}
              for (Cn, L, M) in [(15, 3, 4), (15, 8, 4), (15, 8, 3), (21, 3, 3), (21, 10, 5), (21, 9, 5), (33, 5, 5),
@@ -198,6 +205,6 @@ def warnings():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (shor_states, single_gates, iqft, scalars, shor_runs, warnings, shor_stdout):
+    for fn in (shor_states, single_gates, iqft, scalars, shor_runs, warnings, shor_stdout, debug_stdout):
         if not only or fn.__name__ in only:
             fn()

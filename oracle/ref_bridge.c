@@ -21,6 +21,11 @@
 #define main qc_ref_main
 #include QC_REF_SOURCE
 #undef main
+/* the two development helpers the reference keeps in a file of their own, "not linked to by qc_shor.c so
+ * should be inserted ... by hand" (testing_and_debug.c:1-5): inserted here, unmodified */
+#ifdef QC_REF_DEBUG_SOURCE
+#include QC_REF_DEBUG_SOURCE
+#endif
 
 #include <string.h>
 
@@ -184,3 +189,18 @@ double qcref_norm2(void *hv)
         s += gsl_complex_abs2(gsl_vector_complex_get(*h->reg.current_state, i));
     return s;
 }
+
+#ifdef QC_REF_DEBUG_SOURCE
+/* display_state / check_normalisation, testing_and_debug.c:7-37: print to stdout */
+void qcref_display_state(void *hv)
+{
+    display_state(((qcref_handle *) hv)->reg);
+    fflush(stdout);
+}
+
+void qcref_check_normalisation(void *hv)
+{
+    check_normalisation(((qcref_handle *) hv)->reg);
+    fflush(stdout);
+}
+#endif

@@ -8,6 +8,7 @@
  * a GPU.  It is injected with LD_PRELOAD by that one test and is never built into, linked by or
  * shipped with the product: libqcs.so itself has no CPU path.
  */
+#include <math.h>
 #include <stdlib.h>
 
 #include "qcs.h"
@@ -89,5 +90,37 @@ int qcs_c_amodc_gate(qcs_register *reg, unsigned C, unsigned long long atox, uns
 int qcs_inverse_QFT(qcs_register *reg)
 {
     orc_inverse_QFT(reg->o);
+    return QCS_NO_ERROR;
+}
+
+/* read-back used by the host-side debug helpers (quantumcomputer_b200/host/state_debug.c) */
+unsigned qcs_num_qubits(const qcs_register *reg) { return (unsigned) (reg->L_size + reg->M_size); }
+
+int qcs_norm2(qcs_register *reg, double *sum_of_sq)
+{
+    *sum_of_sq = orc_norm2(reg->o);
+    return QCS_NO_ERROR;
+}
+
+int qcs_nonzero_states(qcs_register *reg, unsigned long long capacity, unsigned long long *indices,
+                       double *abs_values, unsigned long long *count)
+{
+    const unsigned long long N = (unsigned long long) orc_num_states(reg->o);
+    double *amp = (double *) malloc(2 * N * sizeof *amp);
+    if (!amp) return QCS_INSUFFICIENT_MEMORY;
+    orc_get_state(reg->o, amp);
+    unsigned long long total = 0;
+    for (unsigned long long i = 0; i < N; i++) {
+        const double m = hypot(amp[2 * i], amp[2 * i + 1]);      /* gsl_complex_abs */
+        if (m != 0.0) {
+            if (total < capacity) {
+                if (indices) indices[total] = i;
+                if (abs_values) abs_values[total] = m;
+            }
+            total++;
+        }
+    }
+    free(amp);
+    *count = total;
     return QCS_NO_ERROR;
 }
