@@ -79,15 +79,17 @@ def classify(lo, hi, biggest, r, dual_ok):
     return SEQ
 
 
-def model_scan(p, s0, r, n_qubits, stats):
-    """The four passes of measure.cu on probabilities p: (found, index, sum) or None (invariant failed)."""
+def model_scan(p, s0, r, n_qubits, stats, s0_approx=None):
+    """The four passes of measure.cu on probabilities p: (found, index, sum) or None (invariant failed).
+    s0_approx: the running sum before p as passes 1-3 know it on a shard of a sharded register (the shards'
+    approximate totals, all-gathered) -- the walk alone carries the exact one (api.cu locate_state)."""
     if s0 >= r:                                                   # qcs_k_measure_scan: the sum only grows, so a running sum
         return sequential(p[:1], s0, r)                           # that already reaches r stops at the first index
     delta = 2.0 ** (n_qubits + 3 - 53)
     chunks = [p[c:c + CHUNK] for c in range(0, len(p), CHUNK)]
     csum = [float(np.sum(np.asarray(c))) for c in chunks]         # pass 1: any summation order
     cmax = [max(c) for c in chunks]
-    codes, before = [], s0
+    codes, before = [], (s0 if s0_approx is None else s0_approx)
     for v, big in zip(csum, cmax):                                # pass 2: approximate prefix + classes
         lo, hi = before * (1.0 - delta), (before + v) * (1.0 + delta)
         codes.append(ZERO if v == 0.0 else classify(lo, hi, big, r, True) if lo > 0.0 else SEQ)
@@ -219,3 +221,33 @@ def test_compose_is_associative_and_matches_the_loop():
         for cut in (1, 17, 150, 299):
             assert compose(chunk_map(p[:cut], e), chunk_map(p[cut:], e)) == whole
         assert apply_map(s, whole, e) == want
+
+
+@pytest.mark.parametrize("kind", ["random", "plateau", "below", "shor", "wide"])
+@pytest.mark.parametrize("shards", [2, 8])
+def test_model_scan_sharded_hand_off(kind, shards):
+    """Sharded registers (api.cu locate_state): every shard classifies its chunks from the all-gathered APPROXIMATE
+    totals of the shards before it, the exact running sum is handed from shard to shard by the walk.  Same index
+    as one sequential loop over the whole register."""
+    n = 13
+    rng = np.random.default_rng(23)
+    p = [float(x) for x in make_state(kind, n, rng)]
+    scanned = p[:-1]
+    per = len(p) // shards
+    stats = {"dual_upper": 0, "dual_lower": 0, "refined": 0}
+    margin_qubits = 30 if kind in ("plateau", "below") else n
+    for r in variates(np.asarray(p), rng):
+        want = sequential(scanned, 0.0, r)
+        s, got = 0.0, None
+        totals = [float(np.sum(np.asarray(scanned[k * per:(k + 1) * per])[::-1])) for k in range(shards)]   # another order
+        for k in range(shards):
+            part = scanned[k * per:(k + 1) * per]
+            res = model_scan(part, s, r, margin_qubits, stats, s0_approx=float(sum(totals[:k])))
+            assert res is not None, (kind, r, k)
+            found, i, s = res
+            if found:
+                got = (True, k * per + i, s)
+                break
+        if got is None:
+            got = (False, 0, s)
+        assert got == want, (kind, r)
