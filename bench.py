@@ -737,12 +737,10 @@ def run_ours(args):
     parity = None
     if circuit is None and not args.no_parity:
         parity = parity_block(q, reg, n, ranks)
-        if not parity["ok"]:
-            if rank == 0:
-                print(json.dumps({"error": "parity check failed", "parity": parity}), flush=True)
-            reg.close()
-            ranks.close()
-            raise SystemExit(3)
+        if not parity["ok"] and rank == 0:
+            # said at once (should a later step hang) and again in the line, which then carries "error" and
+            # the process exits 3: a number next to a failed check is not a result
+            print(json.dumps({"error": "parity check failed", "parity": parity}), file=sys.stderr, flush=True)
 
     # synthetic state, generated on the device, normalised
     reg.fill_synthetic(SEED)
@@ -817,6 +815,8 @@ def run_ours(args):
         }
         if parity is not None:
             line["parity"] = parity
+            if not parity["ok"]:
+                line["error"] = "parity check failed"
         if e2e is not None:
             line["e2e"] = e2e
     reg.close()
