@@ -64,3 +64,22 @@ def test_product_does_not_link_the_oracle():
             if f.endswith((".py", ".cu", ".c", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "qcs_oracle" not in src, f
+
+
+def test_host_library_exports_its_headers(qcs):
+    """libqcshost.so (the classical half + the debug helpers, host C) exports what its headers declare, and the
+    product never mentions the test-only mock."""
+    lib = C.CDLL(os.path.join(ROOT, "quantumcomputer_b200", "lib", "libqcshost.so"))
+    host = os.path.join(ROOT, "quantumcomputer_b200", "host")
+    names = set()
+    for header in ("shor_classical.h", "state_debug.h", "mt19937.h"):
+        text = re.sub(r"/\*.*?\*/", "", open(os.path.join(host, header)).read(), flags=re.S)
+        names |= set(re.findall(r"\b(qcsh_[A-Za-z0-9_]+)\s*\(", text))
+    assert {"qcsh_shors_algorithm", "qcsh_find_period", "qcsh_display_state", "qcsh_check_normalisation"} <= names
+    for name in sorted(names):
+        assert hasattr(lib, name), f"{name} declared under quantumcomputer_b200/host but not exported by libqcshost.so"
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "quantumcomputer_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".c", ".h", ".cuh")):
+                assert "mock_qcs" not in open(os.path.join(dirpath, f)).read(), f
+    assert "mock" not in open(os.path.join(ROOT, "bench.py")).read()
