@@ -53,3 +53,29 @@ def test_bench_helpers_on_cpu(oracle_built):
         assert many["cores"] >= 1 and many["value"] > 0
     traffic, src = bench.profiled_traffic(30)
     assert traffic is None or (3.3e10 < traffic < 3.6e10 and src.startswith("profiles/"))
+
+
+def test_workload_generators_follow_the_reference_rng(oracle_built):
+    """BASELINE configs[3] draws its angles from gsl_rng_mt19937 / gsl_rng_uniform: the Python
+    generator behind bench.py --workload layered against the golden draws of the unmodified reference's RNG
+    (KAT-3) and, where oracle/_ref exists, against the reference's RNG live; then the circuit's definition."""
+    import math
+    from conftest import load_golden
+    from quantumcomputer_b200.workloads import layered_circuit, mt19937_uniforms
+    g = load_golden("scalars.json")["mt19937"]
+    assert [x.hex() for x in mt19937_uniforms(5489, 4)] == g["seed5489_first_uniform"]
+    assert [x.hex() for x in mt19937_uniforms(0, 2)] == g["seed0_first_uniform"] == g["seed4357_first_uniform"]
+    if oracle_built.have_reference():
+        ref = oracle_built.Reference(1, 1)
+        for seed in (33, 34, 40, 12345):
+            ref.seed(seed)
+            assert mt19937_uniforms(seed, 700) == [ref.rng_uniform() for _ in range(700)]     # past one state refill
+        ref.close()
+    n, layers = 33, 8
+    gates = layered_circuit(n, layers)
+    assert len(gates) == 528                                              # 66 gates per layer
+    for d in range(layers):
+        layer = gates[d * 2 * n:(d + 1) * 2 * n]
+        u = mt19937_uniforms(n + d, n)
+        assert layer[:n] == [("h", q) for q in range(n)]
+        assert layer[n:] == [("cp", q, (q + 1 + d) % n, 2.0 * math.pi * u[q]) for q in range(n)]
