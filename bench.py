@@ -438,10 +438,8 @@ def apply_tuning(q, reg, args):
         reg.set_option(q.OPT_OVERLAP_SLICES, args.overlap_slices)
     if args.global_sms > 0:
         reg.set_option(q.OPT_GLOBAL_SMS, args.global_sms)
-    for name, opt in (("l2_pair", "OPT_L2_PAIR"), ("keep_permuted", "OPT_KEEP_PERMUTED")):
-        v = getattr(args, name, -1)
-        if v >= 0 and hasattr(q, opt):
-            reg.set_option(getattr(q, opt), v)
+    if args.l2_pair >= 0:
+        reg.set_option(q.OPT_L2_PAIR, args.l2_pair)
 
 
 def north_star_block(q, ranks, args, peak, peak_src):
@@ -879,7 +877,6 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the Shor cfg1/cfg2 and layered n = 33 blocks (N = 1)")
     ap.add_argument("--north-star-steps", type=int, default=5)
     ap.add_argument("--l2-pair", type=int, default=-1)
-    ap.add_argument("--keep-permuted", type=int, default=-1)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
