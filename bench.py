@@ -347,7 +347,8 @@ def parity_block(q, reg, n, ranks):
     linear = max(abs(idx / N - r) for idx, r in zip(many, rs))
     measured = int(reg.measure_state(rs[0]))
     norm_collapsed = reg.norm2()
-    measure_ok = many == single and measured == many[0] and norm_collapsed == 1.0 and linear < 1e-3
+    # (1e-3 at the sizes the bench runs at, n >= 24; wider for the small registers of --qubits runs)
+    measure_ok = many == single and measured == many[0] and norm_collapsed == 1.0 and linear < max(1e-3, 4.0 / math.sqrt(N))
 
     err_closed = ranks.max(max(err_closed, back))       # `back`: |amp[k] - 1| after the forward transform
     err_round = ranks.max(err_round)
