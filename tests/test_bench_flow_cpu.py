@@ -136,7 +136,8 @@ def make_fake_q(oracle, break_transform=False):
             self.set_state(float64_array, first)
 
         def fused(self):
-            return self
+            import contextlib
+            return contextlib.nullcontext()
 
         def timer_start(self):
             self.t0 = time.perf_counter()
@@ -236,3 +237,15 @@ def test_shor_block_bookkeeping(monkeypatch, oracle_built):
     cfg1 = out["find_period"][0]
     assert (cfg1["C"], cfg1["a"], cfg1["L"], cfg1["M"], cfg1["gates"]) == (15, 7, 3, 4, 12)
     assert cfg1["measured_indices_identical"] and cfg1["cpu_kind"] in ("reference", "port") and cfg1["indices"][0] == 55
+
+
+def test_layered_workload_flow(monkeypatch, capsys, oracle_built):
+    """--workload layered (BASELINE configs[3]) through the same arm: the gates are issued one by one through the
+    reference's operator names inside a fuse window."""
+    code, line, _ = run_arm(monkeypatch, capsys, make_fake_q(oracle_built),
+                            bench_args(workload="layered", qubits=9, layers=2, steps=2, no_e2e=True))
+    assert code == 0 and "error" not in line
+    assert line["metric"] == "layered_circuit_gates_per_sec" and line["config"]["gates_per_step"] == 36
+    assert "layered circuit (BASELINE configs[3])" in line["config"]["workload"]
+    assert line["gpu_launches"] == 2 * 36 and "parity" not in line and "cpu_baseline" not in line
+    assert abs(line["config"]["norm_after"] - 1.0) < 1e-12
