@@ -443,10 +443,11 @@ def apply_tuning(q, reg, args):
         reg.set_option(q.OPT_L2_PAIR, args.l2_pair)
 
 
-def north_star_block(q, ranks, args, peak, peak_src):
-    """BASELINE `metric`: QFT time at n = 33 (1 GPU), 34 (2), 35 (4 and 8), timed in this run."""
+def north_star_block(q, ranks, args, peak, peak_src, n_override=None):
+    """BASELINE `metric`: QFT time at n = 33 (1 GPU), 34 (2), 35 (4 and 8), timed in this run.
+    (n_override: the CPU dry run of tests/test_bench_flow_cpu.py.)"""
     world = ranks.world
-    n = {1: 33, 2: 34, 4: 35, 8: 35}.get(world)
+    n = n_override or {1: 33, 2: 34, 4: 35, 8: 35}.get(world)
     if n is None:
         return None
     p = int(math.log2(world))
@@ -456,7 +457,7 @@ def north_star_block(q, ranks, args, peak, peak_src):
         import numpy as np
         # parity at this size: closed form of a basis state at 8 probes per shard
         N, nl = 1 << n, reg.local_states
-        k = (N - 1) - 0x54321
+        k = (N - 1) - 0x54321 if n > 20 else N - 3
         reg.reset_register()
         if ranks.rank == 0:
             reg.set_state(np.array([0j]), first=1)
@@ -645,12 +646,13 @@ def run_shor(q, ranks, args):
         raise SystemExit(3)
 
 
-def layered_block(q, ranks, args, peak, peak_src):
+def layered_block(q, ranks, args, peak, peak_src, n_override=None):
     """BASELINE configs[3] in the default run: the layered H / C-phase circuit at n = 33 on one GPU,
-    issued gate by gate inside qcs_fuse_begin / qcs_fuse_end; checked by applying the inverse circuit."""
+    issued gate by gate inside qcs_fuse_begin / qcs_fuse_end; checked by applying the inverse circuit.
+    (n_override: the CPU dry run of tests/test_bench_flow_cpu.py.)"""
     import numpy as np
     from quantumcomputer_b200.workloads import apply_gates, layered_circuit
-    n, layers = 33, args.layers
+    n, layers = n_override or 33, args.layers
     circuit = layered_circuit(n, layers)
     inverse = [g if g[0] == "h" else ("cp", g[1], g[2], -g[3]) for g in reversed(circuit)]
     with q.Register(n, 0, device=ranks.local_rank) as reg:
@@ -658,7 +660,7 @@ def layered_block(q, ranks, args, peak, peak_src):
         reg.fill_synthetic(SEED)
         reg.scale(1.0 / math.sqrt(reg.norm2()))
         nl = reg.local_states
-        probes = [0, 1, nl - 1, nl // 2 + 9, nl // 3, (nl // 7) * 5, 123456789, nl // 5 + 1]
+        probes = [0, 1, nl - 1, nl // 2 + 9, nl // 3, (nl // 7) * 5, min(123456789, nl - 2), nl // 5 + 1]
         before = np.array([reg.get_state(i, 1)[0] for i in probes])
 
         def one_step():

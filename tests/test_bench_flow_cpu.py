@@ -249,3 +249,22 @@ def test_layered_workload_flow(monkeypatch, capsys, oracle_built):
     assert "layered circuit (BASELINE configs[3])" in line["config"]["workload"]
     assert line["gpu_launches"] == 2 * 36 and "parity" not in line and "cpu_baseline" not in line
     assert abs(line["config"]["norm_after"] - 1.0) < 1e-12
+
+
+def test_north_star_and_layered_blocks(oracle_built):
+    """The two blocks the default N = 1 line carries besides the headline (BASELINE's n = 33 transform and
+    configs[3]), at a size the oracle finishes in a moment."""
+    import bench
+    fake = make_fake_q(oracle_built)
+    ranks = types.SimpleNamespace(local_rank=0, rank=0, world=1, comm_id=lambda: None, barrier=lambda reg=None: None,
+                                  max=lambda x: x)
+    ns = bench.north_star_block(fake, ranks, bench_args(qubits=0), 6500.0, "test", n_override=11)
+    assert ns["qubits"] == 11 and ns["parity"]["ok"] and ns["parity"]["closed_form_max_rel_err"] <= 1e-12
+    assert ns["gates_per_step"] == 11 + 55 and ns["steps"] == 3 and ns["gpu_launches"] == 9
+    assert ns["roofline"]["kernel"] == "tile_sweep" and ns["ms_per_qft"] > 0
+    lay = bench.layered_block(fake, ranks, bench_args(layers=2), 6500.0, "test", n_override=9)
+    assert lay["parity"]["ok"] and lay["parity"]["round_trip_max_rel_err"] <= 1e-11
+    assert lay["gates_per_step"] == 36 and lay["qubits"] == 9 and lay["steps"] == 3
+    broken = bench.north_star_block(make_fake_q(oracle_built, break_transform=True), ranks, bench_args(qubits=0), 6500.0,
+                                    "test", n_override=11)
+    assert broken["parity"]["ok"] is False
