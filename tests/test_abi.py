@@ -83,3 +83,21 @@ def test_host_library_exports_its_headers(qcs):
             if f.endswith((".py", ".cu", ".c", ".h", ".cuh")):
                 assert "mock_qcs" not in open(os.path.join(dirpath, f)).read(), f
     assert "mock" not in open(os.path.join(ROOT, "bench.py")).read()
+
+
+def test_documents_name_only_entry_points_that_exist():
+    """Every qcs_* / qcsh_* call INTEGRATION.md, README.md and DESIGN.md mention is declared in a header."""
+    declared = set(declared_symbols())
+    host = os.path.join(ROOT, "quantumcomputer_b200", "host")
+    for header in os.listdir(host):
+        if header.endswith(".h"):
+            declared |= set(re.findall(r"\b(qcsh_[A-Za-z0-9_]+)\s*\(", open(os.path.join(host, header)).read()))
+    internal = {"qcs_k_", "qcs_dist_", "qcs_peer_", "qcs_group_", "qcs_fused_", "qcs_pipeline_", "qcs_launch_", "qcs_map_",
+                "qcs_materialise_", "qcs_sharded_", "qcs_profile_resolve", "qcs_fuse_flush", "qcs_internal", "qcs_oracle",
+                "qcs_register_create_", "qcs_standin"}
+    for doc in ("INTEGRATION.md", "README.md", "DESIGN.md"):
+        text = open(os.path.join(ROOT, doc)).read()
+        for name in set(re.findall(r"\b(qcsh?_[a-z][A-Za-z0-9_]*)\b", text)):
+            if name in declared or any(name.startswith(p) for p in internal) or name in ("qcs_register", "qcs_group", "qcsh_rng", "qcsh_options"):
+                continue
+            raise AssertionError(f"{doc} mentions {name}, which no header declares")
